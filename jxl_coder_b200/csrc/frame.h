@@ -1,0 +1,162 @@
+// Plain-data description of one JPEG XL frame as the CUDA kernels see it, plus the VarDCT constant tables
+// (block strategies, coefficient-order ids, context tables).  Shared by host and device.
+// Format digest: SURVEY.md App. B.2-B.7.
+#pragma once
+#include "hd.h"
+#include "entropy.h"
+#include "modular.h"
+
+namespace jxlb {
+
+static constexpr int kNumStrategies = 27;
+static constexpr int kNumOrders = 13;
+static constexpr int kNumQuantTables = 17;
+static constexpr uint32_t kGroupDim = 256;       // VarDCT group size in pixels
+static constexpr uint32_t kGroupCells = 32;      // ... in 8x8 cells
+static constexpr uint32_t kLfGroupCells = 256;   // LF group size in cells
+static constexpr uint32_t kZeroDensityContexts = 458;
+static constexpr uint32_t kNonZeroBuckets = 37;
+static constexpr uint32_t kContextsPerBlockCtx = 495;
+
+// cells covered (x, y), coefficient-order id, quant-table id per strategy (App. B.7 strategy table)
+JXLB_HD uint32_t StrategyCellsX(uint32_t s) {
+  const uint8_t k[kNumStrategies] = {1, 1, 1, 1, 2, 4, 1, 2, 1, 4, 2, 4, 1, 1, 1, 1, 1, 1, 8, 4, 8, 16, 8, 16, 32, 16, 32};
+  return k[s];
+}
+JXLB_HD uint32_t StrategyCellsY(uint32_t s) {
+  const uint8_t k[kNumStrategies] = {1, 1, 1, 1, 2, 4, 2, 1, 4, 1, 4, 2, 1, 1, 1, 1, 1, 1, 8, 8, 4, 16, 16, 8, 32, 32, 16};
+  return k[s];
+}
+JXLB_HD uint32_t StrategyOrder(uint32_t s) {
+  const uint8_t k[kNumStrategies] = {0, 1, 1, 1, 2, 3, 4, 4, 5, 5, 6, 6, 1, 1, 1, 1, 1, 1, 7, 8, 8, 9, 10, 10, 11, 12, 12};
+  return k[s];
+}
+JXLB_HD uint32_t StrategyQuantTable(uint32_t s) {
+  const uint8_t k[kNumStrategies] = {0, 1, 2, 3, 4, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 10, 10, 11, 12, 12, 13, 14, 14, 15, 16, 16};
+  return k[s];
+}
+// a representative strategy for each coefficient-order id
+JXLB_HD uint32_t OrderRepresentative(uint32_t o) {
+  const uint8_t k[kNumOrders] = {0, 1, 4, 5, 6, 8, 10, 18, 19, 21, 22, 24, 25};
+  return k[o];
+}
+// a representative strategy for each quant table (both orientations share the table)
+JXLB_HD uint32_t QuantTableRepresentative(uint32_t q) {
+  const uint8_t k[kNumQuantTables] = {0, 1, 2, 3, 4, 5, 6, 8, 10, 12, 14, 18, 19, 21, 22, 24, 25};
+  return k[q];
+}
+
+// Zero-density context tables (App. B.7: FREQ / NZ)
+JXLB_HD uint32_t ZeroDensityFreqCtx(uint32_t k) {
+  const uint8_t t[64] = {0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 15, 16, 16, 17, 17, 18, 18, 19, 19, 20, 20, 21, 21, 22, 22,
+                         23, 23, 23, 23, 24, 24, 24, 24, 25, 25, 25, 25, 26, 26, 26, 26, 27, 27, 27, 27, 28, 28, 28, 28, 29, 29, 29, 29, 30, 30, 30, 30};
+  return t[k];
+}
+JXLB_HD uint32_t ZeroDensityNnzCtx(uint32_t n) {
+  const uint8_t t[64] = {0, 0, 31, 62, 62, 93, 93, 93, 93, 123, 123, 123, 123, 152, 152, 152, 152, 152, 152, 152, 152, 180, 180, 180, 180, 180,
+                         180, 180, 180, 180, 180, 180, 180, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206,
+                         206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206};
+  return t[n];
+}
+
+// ---- block-context map (LfGlobal) ----
+static constexpr int kMaxThresholds = 15;
+struct BlockCtxMap {
+  int32_t lf_thr[3][kMaxThresholds];  // X, Y, B
+  uint32_t num_lf_thr[3];
+  uint32_t qf_thr[kMaxThresholds];
+  uint32_t num_qf_thr;
+  uint32_t num_lf_ctx;                // product of (num_lf_thr[c] + 1)
+  uint32_t num_ctx;                   // nb_block_ctx = max(map) + 1
+  uint32_t map_size;
+  // ctx_map bytes live in FrameDev::bctx_map (host: std::vector)
+};
+
+struct CflParams {
+  uint32_t colour_factor;
+  float base_x, base_b;
+  uint32_t x_factor_lf, b_factor_lf;
+};
+
+struct RestorationFilter {
+  uint8_t gab, epf_iters, gab_custom, pad;
+  float gab_w1[3], gab_w2[3];
+  float epf_sharp_lut[8];
+  float epf_channel_scale[3];
+  float epf_quant_mul, epf_pass0_sigma_scale, epf_pass2_sigma_scale, epf_border_sad_mul, epf_sigma_for_modular;
+};
+
+// Coefficient order tables: for order id o and channel c (0=X 1=Y 2=B), order[k] = position of the k-th coded
+// coefficient inside the block's 8·min × 8·max coefficient array.  Offsets (in uint16/uint32 entries) per (o, c).
+struct OrderTableIndex {
+  uint32_t offset[kNumOrders][3];  // into the uint32_t order pool; 0xFFFFFFFF if the order cannot occur
+};
+
+// Everything global to one frame that the device needs (POD; device pointers filled by the decoder).
+struct FrameDev {
+  // geometry of the coded frame
+  uint32_t width, height;          // pixels
+  uint32_t w8, h8;                 // 8x8 cells
+  uint32_t w64, h64;               // CfL tiles
+  uint32_t ngx, ngy, nlfx, nlfy;
+  uint32_t num_groups, num_lf_groups, num_passes;
+  uint32_t group_dim;              // 256 for VarDCT, 128 << shift for modular
+  uint32_t encoding;               // 0 VarDCT, 1 modular
+  uint32_t flags;
+  uint32_t single_section;         // toc_entries == 1
+  uint32_t x_qm_scale, b_qm_scale;
+  // bitstream (HBM copy of the padded codestream) and the section table in logical order
+  const uint8_t* cs;
+  uint64_t cs_bytes;               // padded size, multiple of 4
+  const uint64_t* sec_bit_begin;   // [toc_entries]
+  const uint64_t* sec_bit_end;
+  uint32_t toc_entries;
+  // LfGlobal
+  float lf_dequant[3];             // X, Y, B
+  uint32_t global_scale, quant_lf;
+  BlockCtxMap bctx;
+  const uint8_t* bctx_map;
+  CflParams cfl;
+  // global MA tree + its code (may be absent)
+  const TreeNode* global_tree;
+  uint32_t global_tree_nodes, global_tree_uses_wp, global_tree_max_property;
+  const uint8_t* global_code;      // code blob
+  uint64_t global_modular_bit;     // absolute bit position of the global modular stream's GroupHeader
+  // HfGlobal (multi-section frames: parsed on the host)
+  uint32_t num_hf_presets;
+  uint32_t used_orders;
+  const uint8_t* ac_code;          // code blob
+  const uint16_t* order_pool;
+  OrderTableIndex orders;
+  RestorationFilter rf;
+  // extra channels / modular image
+  uint32_t num_mod_channels;       // channels of the frame's modular image (colour for modular frames + extras)
+  uint32_t num_color_mod_channels; // 0 for VarDCT, 1 or 3 for modular
+  uint32_t global_mod_decoded;     // channels fully decoded in the global stream (filled by host plan)
+  uint32_t global_nb_transforms;   // frame-level modular transforms (multi-section frames; host-parsed)
+  ModTransform global_tr[kMaxTransforms];
+  // ---- planes (device) ----
+  int32_t* lf_quant;               // [3][h8][lf_stride]  (Y, X, B as coded)
+  uint32_t lf_stride;
+  int32_t* xfromy;                 // [h64][w64]
+  int32_t* bfromy;
+  int32_t* sharpness_i32;          // [h8][lf_stride]
+  int32_t* blockinfo;              // per LF group: [2][cells of that LF group]; see blockinfo_off
+  const uint32_t* blockinfo_off;   // [num_lf_groups] offset in int32 entries
+  uint32_t* nb_blocks;             // [num_lf_groups] decoded block count
+  uint32_t* lf_extra_precision;    // [num_lf_groups]
+  uint8_t* cell_strategy;          // [h8][w8]: strategy | 0x80 if top-left cell of its block, 0xFF = uncovered
+  uint16_t* cell_hfmul;            // [h8][w8]: hf_mul of the covering block
+  uint8_t* cell_sharp;             // [h8][w8]
+  int16_t* coef;                   // [3][coef_h][coef_stride] quantised coefficients (X, Y, B), block-rectangle layout
+  uint32_t coef_stride, coef_h;
+  float* lf;                       // [3][h8][lf_stride] dequantised (X, Y, B)
+  float* xyb0;                     // [3][plane_h][plane_stride]
+  float* xyb1;
+  uint32_t plane_stride, plane_h;
+  int32_t* mod;                    // [num_mod_channels][height][mod_stride]
+  uint32_t mod_stride;
+  int32_t* status;                 // [num_streams] per-stream status (see StreamStatus)
+};
+
+}  // namespace jxlb

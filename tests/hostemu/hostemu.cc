@@ -1,0 +1,152 @@
+// TEST TOOL — not part of the product and never loaded by it.
+// Runs the *shared host/device* section decoders (jxl_coder_b200/csrc/{entropy,modular,vardct_sections}.h) serially on
+// the CPU over host buffers laid out by the same FramePlan the GPU decoder uses.  tests/test_sections_host.py compares
+// the resulting planes with the Python oracle, so the bit-level logic of the CUDA kernels is verified on a box without
+// a GPU; the GPU tests then only need to show that the kernels produce the same planes as this run.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../jxl_coder_b200/csrc/frame_parser.h"
+#include "../../jxl_coder_b200/csrc/plan.h"
+#include "../../jxl_coder_b200/csrc/vardct_sections.h"
+
+using namespace jxlb;
+
+struct Emu {
+  ImageMetadata md;
+  FrameHeader fh;
+  FrameGlobals g;
+  FramePlan plan;
+  std::vector<uint8_t> cs, cregion, wregion;
+  FrameDev f;
+  int status = 0;
+  int failed_stream = -1;
+};
+
+static void SetErr(char* err, size_t n, const std::string& s) {
+  if (err && n) snprintf(err, n, "%s", s.c_str());
+}
+
+extern "C" {
+
+// frame_index: which frame of the codestream to decode (0 = first).
+void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, size_t errlen) {
+  Emu* e = new Emu();
+  size_t cs_len = 0;
+  std::string msg;
+  int st = ExtractCodestream(data, len, &e->cs, &cs_len);
+  if (st) {
+    SetErr(err, errlen, "extract codestream: " + std::to_string(st));
+    delete e;
+    return nullptr;
+  }
+  uint64_t frame_bit = 0;
+  st = ParseImageHeader(e->cs.data(), e->cs.size(), cs_len, &e->md, &frame_bit, &msg);
+  if (st) {
+    SetErr(err, errlen, "image header: " + msg);
+    delete e;
+    return nullptr;
+  }
+  for (int i = 0;; ++i) {
+    e->fh = FrameHeader();
+    st = ParseFrameHeader(e->cs.data(), e->cs.size(), cs_len, e->md, frame_bit, &e->fh, &msg);
+    if (st) {
+      SetErr(err, errlen, "frame header: " + msg);
+      delete e;
+      return nullptr;
+    }
+    if (i == frame_index) break;
+    if (e->fh.is_last) {
+      SetErr(err, errlen, "no such frame");
+      delete e;
+      return nullptr;
+    }
+    frame_bit = e->fh.end_byte * 8;
+  }
+  st = ParseFrameGlobals(e->cs.data(), e->cs.size(), e->md, e->fh, &e->g, &msg);
+  if (st) {
+    SetErr(err, errlen, "frame globals (" + std::to_string(st) + "): " + msg);
+    delete e;
+    return nullptr;
+  }
+  MakeFramePlan(e->md, e->fh, e->g, e->cs.size(), &e->plan);
+  e->cregion.resize(e->plan.const_bytes);
+  e->wregion.assign(e->plan.work_bytes, 0);
+  FillConstRegion(e->plan, e->cs.data(), e->fh, e->g, e->cregion.data());
+  e->f = BindFrameDev(e->plan, e->cregion.data(), e->wregion.data());
+  const FrameDev& f = e->f;
+  // scratch
+  std::vector<uint8_t> arena_mem(8u << 20), hf_mem(8u << 20);
+  std::vector<int32_t> wp(WPState::ScratchInts(4096 + 64));
+  std::vector<uint32_t> lz(1u << 20), perm(2 * 65536);
+  std::vector<uint8_t> nz(3 * 1024);
+  StreamScratch s;
+  s.arena.Init(arena_mem.data(), (uint32_t) arena_mem.size());
+  s.wp = wp.data();
+  s.lz77 = lz.data();
+  s.lz77_mask = (1u << 20) - 1;
+  s.nzmap = nz.data();
+  const NaturalOrders& nat = NaturalOrderPoolHost();
+  const uint32_t kMaxNodes = 1u << 16;
+  if (f.single_section) {
+    Arena hf;
+    hf.Init(hf_mem.data(), (uint32_t) hf_mem.size());
+    e->status = DecodeSingleSectionFrame(f, nat, s, hf, perm.data(), kMaxNodes);
+    if (e->status) e->failed_stream = 0;
+  } else {
+    for (uint32_t l = 0; l < f.num_lf_groups && !e->status && f.encoding == 0; ++l) {
+      BitReader br;
+      br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[1 + l], f.sec_bit_end[1 + l]);
+      s.arena.used = 0;
+      e->status = DecodeLfGroupSection(br, f, l, s, kMaxNodes);
+      if (e->status) e->failed_stream = (int) l;
+    }
+    for (uint32_t gi = 0; gi < f.num_groups && !e->status; ++gi) {
+      uint32_t sec = 1 + f.num_lf_groups + 1 + gi;
+      BitReader br;
+      br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);
+      s.arena.used = 0;
+      if (f.encoding == 0) e->status = DecodeAcGroup(br, f, gi, nat, s);
+      if (!e->status) e->status = DecodeModularGroup(br, f, gi, s, kMaxNodes);
+      if (e->status) e->failed_stream = (int) (f.num_lf_groups + gi);
+    }
+  }
+  return e;
+}
+
+void emu_free(void* h) { delete static_cast<Emu*>(h); }
+int emu_status(void* h) { return static_cast<Emu*>(h)->status; }
+int emu_failed_stream(void* h) { return static_cast<Emu*>(h)->failed_stream; }
+
+// out[]: width, height, w8, h8, lf_stride, coef_stride, coef_h, num_groups, num_lf_groups, encoding, num_mod_channels,
+//        mod_stride, w64, h64, single_section, global_nb_transforms, xsize, ysize, bits, num_extra, is_last, orientation
+void emu_info(void* h, uint32_t* out) {
+  Emu* e = static_cast<Emu*>(h);
+  const FrameDev& f = e->f;
+  uint32_t v[] = {f.width, f.height, f.w8, f.h8, f.lf_stride, f.coef_stride, f.coef_h, f.num_groups, f.num_lf_groups, f.encoding,
+                  f.num_mod_channels, f.mod_stride, f.w64, f.h64, f.single_section, f.global_nb_transforms, e->md.xsize, e->md.ysize,
+                  e->md.bits_per_sample, (uint32_t) e->md.extra.size(), (uint32_t) e->fh.is_last, e->md.orientation};
+  memcpy(out, v, sizeof v);
+}
+const int32_t* emu_lf_quant(void* h) { return static_cast<Emu*>(h)->f.lf_quant; }
+const int32_t* emu_xfromy(void* h) { return static_cast<Emu*>(h)->f.xfromy; }
+const int32_t* emu_bfromy(void* h) { return static_cast<Emu*>(h)->f.bfromy; }
+const uint8_t* emu_cell_strategy(void* h) { return static_cast<Emu*>(h)->f.cell_strategy; }
+const uint16_t* emu_cell_hfmul(void* h) { return static_cast<Emu*>(h)->f.cell_hfmul; }
+const uint8_t* emu_cell_sharp(void* h) { return static_cast<Emu*>(h)->f.cell_sharp; }
+const int16_t* emu_coef(void* h) { return static_cast<Emu*>(h)->f.coef; }
+const int32_t* emu_mod(void* h) { return static_cast<Emu*>(h)->f.mod; }
+
+// Unit hooks for table checks.
+uint32_t emu_freq_ctx(uint32_t k) { return ZeroDensityFreqCtx(k); }
+uint32_t emu_nnz_ctx(uint32_t k) { return ZeroDensityNnzCtx(k); }
+void emu_logcount(uint32_t idx7, uint32_t* nb, uint32_t* sym) { LogCountLookup(idx7, nb, sym); }
+uint32_t emu_natural_order(uint32_t order_id, uint16_t* out) {
+  const NaturalOrders& nat = NaturalOrderPoolHost();
+  memcpy(out, nat.pool + nat.offset[order_id], nat.size[order_id] * 2);
+  return nat.size[order_id];
+}
+
+}  // extern "C"
