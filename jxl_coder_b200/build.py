@@ -1,0 +1,53 @@
+"""Builds libjxlb200.so (CUDA kernels + C ABI) in-tree for sm_100a with nvcc."""
+import concurrent.futures
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libjxlb200.so")
+OBJ = os.path.join(HERE, "build")
+SOURCES = ["kernels.cu", "decoder.cu", "c_api.cu", "anim.cu", "frame_parser.cc", "plan.cc", "natural_orders.cc", "numeric_tables.cc",
+           "color_params.cc"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+              "-Xcompiler", "-Wno-unknown-pragmas"]
+
+
+def _newest_header():
+    t = 0
+    for root, _, files in os.walk(CSRC):
+        for f in files:
+            if f.endswith((".h", ".inc")):
+                t = max(t, os.path.getmtime(os.path.join(root, f)))
+    t = max(t, os.path.getmtime(os.path.join(HERE, "..", "include", "jxlb200.h")))
+    return t
+
+
+def _compile(src, hdr_time, verbose):
+    obj = os.path.join(OBJ, src + ".o")
+    sp = os.path.join(CSRC, src)
+    if os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(sp), hdr_time):
+        return obj
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-x", "cu"] if src.endswith(".cu") else []) + ["-c", sp, "-o", obj]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return obj
+
+
+def build(verbose=False, force=False):
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_time = 1e18 if force else _newest_header()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(lambda s: _compile(s, hdr_time, verbose), SOURCES))
+    if force or not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
+        cmd = ["nvcc", "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(verbose=True, force="--force" in sys.argv))

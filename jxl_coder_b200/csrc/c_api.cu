@@ -1,0 +1,103 @@
+// extern "C" surface of libjxlb200.so (include/jxlb200.h).
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/jxlb200.h"
+#include "decoder.h"
+#include "frame_parser.h"
+#include "kernels.h"
+
+using namespace jxlb;
+
+namespace {
+std::mutex g_tm_mu;
+BatchTimings g_last_timings;
+
+void FillImage(const DecodedImage& d, jxlb_image* out) {
+  memset(out, 0, sizeof *out);
+  out->data = d.data;
+  out->width = d.width;
+  out->height = d.height;
+  out->stride_bytes = d.stride_bytes;
+  out->format = d.format;
+  out->color_space = d.color_space;
+  out->premultiplied = d.premultiplied;
+  out->device = d.device;
+  snprintf(out->message, sizeof out->message, "%s", d.message.c_str());
+}
+}  // namespace
+
+extern "C" {
+
+int jxlb_decode_batch(const jxlb_request* reqs, size_t n, jxlb_image* outs, int32_t* status, const jxlb_batch_opts* opts) {
+  if (!reqs || !outs) return JXLB_BAD_ARG;
+  jxlb_batch_opts o{0, -1, -1, 0};
+  if (opts) o = *opts;
+  std::vector<DecodedImage> res;
+  BatchTimings tm;
+  int rc = DecodeBatch(reqs, n, o.api_level, o.device, o.output_device, &res, &tm);
+  {
+    std::lock_guard<std::mutex> l(g_tm_mu);
+    g_last_timings = tm;
+  }
+  for (size_t i = 0; i < n; ++i) {
+    FillImage(res[i], &outs[i]);
+    if (status) status[i] = res[i].status;
+  }
+  return rc;
+}
+
+int jxlb_decode_sampled(const uint8_t* data, size_t len, int32_t width, int32_t height, int32_t color_config, int32_t scale_mode,
+                        int32_t filter, int32_t api_level, jxlb_image* out) {
+  if (!out) return JXLB_BAD_ARG;
+  jxlb_request r{data, len, width, height, color_config, scale_mode, filter};
+  jxlb_batch_opts o{api_level, -1, -1, 0};
+  int32_t st = JXLB_OK;
+  jxlb_decode_batch(&r, 1, out, &st, &o);
+  return st;
+}
+
+int jxlb_get_size(const uint8_t* data, size_t len, uint32_t* width, uint32_t* height) {
+  // DecodeBasicInfo (interop/JxlDecoding.cpp:178-226): header-only, CPU.
+  if (!data || !width || !height) return JXLB_BAD_ARG;
+  std::vector<uint8_t> cs;
+  size_t cs_len = 0;
+  int st = ExtractCodestream(data, len, &cs, &cs_len);
+  if (st == kParseNotJxl) return JXLB_NOT_JXL;
+  if (st) return JXLB_INVALID_JXL;
+  ImageMetadata md;
+  uint64_t fb = 0;
+  std::string err;
+  st = ParseImageHeader(cs.data(), cs.size(), cs_len, &md, &fb, &err);
+  if (st == kParseNotJxl) return JXLB_NOT_JXL;
+  if (st == kParseInvalid) return JXLB_INVALID_JXL;
+  // an unsupported feature later in the headers does not prevent reporting the size
+  if (md.xsize == 0 || md.ysize == 0) return JXLB_INVALID_JXL;
+  *width = md.xsize;
+  *height = md.ysize;
+  if (md.orientation >= 5) {
+    *width = md.ysize;
+    *height = md.xsize;
+  }
+  return JXLB_OK;
+}
+
+void jxlb_image_free(jxlb_image* img) {
+  if (!img || !img->data) return;
+  FreeImageMemory(img->data, img->device);
+  img->data = nullptr;
+}
+
+// ---- animated images: implemented in anim.cu ----
+
+uint64_t jxlb_kernel_launches(void) { return KernelLaunchCount(); }
+void jxlb_last_batch_timings(float* ms6) {
+  std::lock_guard<std::mutex> l(g_tm_mu);
+  for (int i = 0; i < 6; ++i) ms6[i] = g_last_timings.ms[i];
+}
+const char* jxlb_version(void) { return "jxlb200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,653 @@
+// Host-side orchestration of one GPU: parse headers on the CPU, plan memory, upload the codestreams and the
+// host-parsed tables, run the kernels of kernels.cu over the whole batch, pack to the requested Bitmap format and
+// hand the results back (device memory or pinned host memory).
+//
+// Control flow per request mirrors decodeSampledImageImpl (/root/reference/jxlcoder/src/main/cpp/JniDecoding.cpp:45-331):
+// checkDecodePreconditions -> decode (DecodeJpegXlOneShot semantics: RGBA u8, or u16 when bits_per_sample > 8 and
+// api_level >= 26) -> [ICC] -> [rescale] -> [colour matrix when api_level < 34] -> ReformatColorConfig -> colour-space tag.
+// There is no CPU fallback: every pixel is produced by a CUDA kernel, and a missing / failing device is an error.
+#include "decoder.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+
+#include "color_params.h"
+#include "frame_parser.h"
+#include "kernels.h"
+#include "numeric_tables.h"
+#include "plan.h"
+
+namespace jxlb {
+
+namespace {
+
+#define CUDA_OK(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (expr);                                                            \
+    if (e_ != cudaSuccess) throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct CudaError {
+  std::string msg;
+  explicit CudaError(std::string m) : msg(std::move(m)) {}
+};
+
+size_t Align256(size_t v) { return (v + 255) & ~(size_t) 255; }
+
+struct DevBuffer {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  void Ensure(size_t n) {
+    if (n <= cap) return;
+    if (p) CUDA_OK(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + (1 << 20);
+    CUDA_OK(cudaMalloc(&p, want));
+    cap = want;
+  }
+};
+struct PinnedBuffer {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  void Ensure(size_t n) {
+    if (n <= cap) return;
+    if (p) CUDA_OK(cudaFreeHost(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + (1 << 20);
+    CUDA_OK(cudaMallocHost(&p, want));
+    cap = want;
+  }
+};
+
+// Pinned host result buffers are recycled: cudaMallocHost costs milliseconds per call.
+struct HostPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_list;
+  std::map<void*, size_t> live;
+  void* Get(size_t n) {
+    std::lock_guard<std::mutex> l(mu);
+    auto it = free_list.lower_bound(n);
+    if (it != free_list.end() && it->first <= n + n / 4 + 4096) {
+      void* p = it->second;
+      live[p] = it->first;
+      free_list.erase(it);
+      return p;
+    }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, n) != cudaSuccess) return nullptr;
+    live[p] = n;
+    return p;
+  }
+  bool Put(void* p) {
+    std::lock_guard<std::mutex> l(mu);
+    auto it = live.find(p);
+    if (it == live.end()) return false;
+    free_list.emplace(it->second, p);
+    live.erase(it);
+    return true;
+  }
+};
+HostPool& Pool() {
+  static HostPool* pool = new HostPool();
+  return *pool;
+}
+
+struct DeviceContext {
+  int device = 0;
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  DevBuffer const_buf, work_buf, scratch_buf, meta_buf, stage_out;
+  PinnedBuffer staging, status_host;
+  NumericTables* nt_dev = nullptr;
+  NaturalOrders nat_dev{};
+  cudaEvent_t ev[8]{};
+  bool ready = false;
+
+  void Init(int dev) {
+    device = dev;
+    CUDA_OK(cudaSetDevice(dev));
+    CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+    // constant tables
+    const HostNumericTables& h = GetHostNumericTables();
+    float* dq = nullptr;
+    float* llf = nullptr;
+    CUDA_OK(cudaMalloc(&dq, h.dequant_pool.size() * 4));
+    CUDA_OK(cudaMalloc(&llf, h.llf_pool.size() * 4));
+    CUDA_OK(cudaMemcpy(dq, h.dequant_pool.data(), h.dequant_pool.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(llf, h.llf_pool.data(), h.llf_pool.size() * 4, cudaMemcpyHostToDevice));
+    NumericTables t = h.tables;
+    t.dequant = dq;
+    for (int l = 0; l < 6; ++l) t.llf[l] = llf + h.llf_off[l];
+    CUDA_OK(cudaMalloc(&nt_dev, sizeof(NumericTables)));
+    CUDA_OK(cudaMemcpy(nt_dev, &t, sizeof t, cudaMemcpyHostToDevice));
+    const NaturalOrders& nh = NaturalOrderPoolHost();
+    uint32_t total = nh.offset[kNumOrders - 1] + nh.size[kNumOrders - 1];
+    uint16_t* pool = nullptr;
+    CUDA_OK(cudaMalloc(&pool, total * 2));
+    CUDA_OK(cudaMemcpy(pool, nh.pool, total * 2, cudaMemcpyHostToDevice));
+    nat_dev = nh;
+    nat_dev.pool = pool;
+    ready = true;
+  }
+};
+
+std::mutex g_ctx_mu;
+std::map<int, std::unique_ptr<DeviceContext>> g_ctx;
+
+DeviceContext* GetContext(int device) {
+  std::lock_guard<std::mutex> l(g_ctx_mu);
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) throw CudaError("no CUDA device");
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw CudaError("no CUDA device available");
+  if (device >= count) throw CudaError("CUDA device ordinal out of range");
+  auto& c = g_ctx[device];
+  if (!c) {
+    c.reset(new DeviceContext());
+    c->Init(device);
+  }
+  return c.get();
+}
+
+// Everything the host knows about one request after parsing.
+struct Parsed {
+  int status = JXLB_OK;
+  std::string message;
+  std::vector<uint8_t> cs;
+  size_t cs_len = 0;
+  ImageMetadata md;
+  FrameHeader fh;
+  FrameGlobals g;
+  FramePlan plan;
+  ColorParams cp{};
+  // decode-stage output (what libjxl would hand to the reference)
+  bool out16 = false;          // RGBA u16 (bits_per_sample > 8 and api_level >= 26)
+  uint32_t depth = 8;          // bitDepth the reference tracks (8 or 16)
+  bool has_alpha = false;      // hasAlphaInOrigin
+  bool alpha_premultiplied = false;
+  int format = JXLB_FORMAT_RGBA_8888;
+  int color_space = JXLB_CS_NONE;
+  // offsets into the batch buffers
+  size_t const_off = 0, work_off = 0, stage_off = 0, stage_stride = 0;
+  uint32_t status_base = 0;
+};
+
+int Fail(Parsed* p, int status, const std::string& msg) {
+  p->status = status;
+  p->message = msg;
+  return status;
+}
+
+// checkDecodePreconditions (Support.cpp:35-92)
+int CheckPreconditions(const jxlb_request& r, int api, Parsed* p) {
+  if (r.color_config < 1 || r.color_config > 6)
+    return Fail(p, JXLB_BAD_ARG, "Invalid Color Config: " + std::to_string(r.color_config) + " was passed");
+  if (r.color_config == JXLB_CONFIG_RGBA_1010102 && api < 33)
+    return Fail(p, JXLB_BAD_ARG, "Color Config RGBA_1010102 supported only 33+ OS version but current is: " + std::to_string(api));
+  if (r.color_config == JXLB_CONFIG_RGBA_F16 && api < 26)
+    return Fail(p, JXLB_BAD_ARG, "Color Config RGBA_1010102 supported only 26+ OS version but current is: " + std::to_string(api));
+  if (r.color_config == JXLB_CONFIG_HARDWARE && api < 29)
+    return Fail(p, JXLB_BAD_ARG, "Color Config HARDWARE supported only 29+ OS version but current is: " + std::to_string(api));
+  if (r.scale_mode < 1 || r.scale_mode > 3) return Fail(p, JXLB_BAD_ARG, "Invalid Scale Mode was passed");
+  if (r.filter < 1 || r.filter > 10) return Fail(p, JXLB_BAD_ARG, "Invalid Sampler: " + std::to_string(r.filter) + " was passed");
+  return JXLB_OK;
+}
+
+int MapParse(int st) { return st == kParseUnsupported ? JXLB_UNSUPPORTED : JXLB_INVALID_JXL; }
+
+int ColorSpaceTag(const ImageMetadata& md, int api) {
+  if (api < 34) return JXLB_CS_NONE;
+  // JniDecoding.cpp:236-253
+  const uint32_t prim = md.color.primaries, tf = md.color.have_gamma ? 0xFFFFu : md.color.transfer;
+  if (prim == 9 && tf == 16) return JXLB_CS_BT2020_PQ;
+  if (prim == 9 && tf == 18) return JXLB_CS_BT2020_HLG;
+  if (prim == 11 && tf == 13) return JXLB_CS_DISPLAY_P3;
+  if (prim == 1 && tf == 8) return JXLB_CS_LINEAR_SRGB;
+  if (prim == 11 && tf == 17) return JXLB_CS_DCI_P3;
+  if (prim == 1 && tf == 1) return JXLB_CS_BT2020_HLG;  // sic: the reference tags sRGB primaries + 709 TF as Hlg2100
+  return JXLB_CS_SRGB;
+}
+
+void ParseRequest(const jxlb_request& r, int api, Parsed* p) {
+  if (CheckPreconditions(r, api, p)) return;
+  if (!r.data || r.len == 0) {
+    Fail(p, JXLB_INVALID_JXL, "empty input");
+    return;
+  }
+  int st = ExtractCodestream(r.data, r.len, &p->cs, &p->cs_len);
+  if (st) {
+    Fail(p, JXLB_INVALID_JXL, "not a JPEG XL file");
+    return;
+  }
+  std::string err;
+  uint64_t frame_bit = 0;
+  st = ParseImageHeader(p->cs.data(), p->cs.size(), p->cs_len, &p->md, &frame_bit, &err);
+  if (st) {
+    Fail(p, MapParse(st), err);
+    return;
+  }
+  const ImageMetadata& md = p->md;
+  // DecodeJpegXlOneShot: 16-bit output iff bits_per_sample > 8 && allowedFloats (api >= 26)
+  p->out16 = md.bits_per_sample > 8 && api >= 26;
+  p->depth = p->out16 ? 16 : 8;
+  {
+    const uint64_t bytes = (uint64_t) md.xsize * md.ysize * 4 * (p->out16 ? 2 : 1);
+    if (bytes >= 0x7FFFFFFFull) {
+      Fail(p, JXLB_INVALID_SIZE, "Invalid image size exceed allowance, current size w: " + std::to_string(md.xsize) + ", h: " + std::to_string(md.ysize));
+      return;
+    }
+  }
+  p->has_alpha = false;
+  p->alpha_premultiplied = false;
+  if (!md.extra.empty()) {
+    int ai = md.alpha_channel();
+    if (ai >= 0 && md.extra[ai].bits > 0) {
+      p->has_alpha = true;
+      p->alpha_premultiplied = md.extra[ai].alpha_premultiplied;
+    }
+  }
+  if (md.orientation != 1) {
+    Fail(p, JXLB_UNSUPPORTED, "non-identity orientation");
+    return;
+  }
+  if (md.float_samples) {
+    Fail(p, JXLB_UNSUPPORTED, "float samples");
+    return;
+  }
+  // frames: decode the last one; earlier frames must not be needed
+  int nframes = 0;
+  for (;;) {
+    p->fh = FrameHeader();
+    st = ParseFrameHeader(p->cs.data(), p->cs.size(), p->cs_len, md, frame_bit, &p->fh, &err);
+    if (st) {
+      Fail(p, MapParse(st), err);
+      return;
+    }
+    ++nframes;
+    if (p->fh.is_last) break;
+    frame_bit = p->fh.end_byte * 8;
+  }
+  const FrameHeader& fh = p->fh;
+  if (nframes > 1 && (fh.blend.mode != 0 || fh.have_crop)) {
+    Fail(p, JXLB_UNSUPPORTED, "multi-frame image needing composition");
+    return;
+  }
+  if (fh.have_crop || fh.coded_w != md.xsize || fh.coded_h != md.ysize) {
+    Fail(p, JXLB_UNSUPPORTED, "cropped frame");
+    return;
+  }
+  st = ParseFrameGlobals(p->cs.data(), p->cs.size(), md, fh, &p->g, &err);
+  if (st) {
+    Fail(p, MapParse(st), err);
+    return;
+  }
+  if (fh.encoding == 0) {
+    if (!md.xyb_encoded) {
+      Fail(p, JXLB_UNSUPPORTED, "VarDCT frame that is not XYB encoded");
+      return;
+    }
+    st = MakeColorParams(md, &p->cp, &err);
+    if (st) {
+      Fail(p, MapParse(st), err);
+      return;
+    }
+  } else if (md.xyb_encoded) {
+    Fail(p, JXLB_UNSUPPORTED, "XYB-encoded modular frame");
+    return;
+  }
+  for (const ExtraChannelInfo& ec : md.extra)
+    if (ec.bits > 16 || ec.is_float) {
+      Fail(p, JXLB_UNSUPPORTED, "extra channel sample type");
+      return;
+    }
+  if (md.extra.size() > 4) {
+    Fail(p, JXLB_UNSUPPORTED, "more than 4 extra channels");
+    return;
+  }
+  // rescale (JniDecoding.cpp:116-136)
+  const bool use_sampler = (r.width > 0 || r.height > 0) && (r.width != 0 && r.height != 0);
+  if (use_sampler) {
+    Fail(p, JXLB_UNSUPPORTED, "rescale (decodeSampled with a target size)");
+    return;
+  }
+  if (api < 34) {
+    Fail(p, JXLB_UNSUPPORTED, "api_level < 34 colour-matrix pass");
+    return;
+  }
+  // ReformatColorConfig: resolve Default (ReformatBitmap.cpp:52-63)
+  int cfg = r.color_config;
+  if (cfg == JXLB_CONFIG_DEFAULT) {
+    if (p->depth > 8 && api >= 26) cfg = (api >= 33 && !p->has_alpha) ? JXLB_CONFIG_RGBA_1010102 : JXLB_CONFIG_RGBA_F16;
+    else cfg = JXLB_CONFIG_RGBA_8888;
+  }
+  if (cfg == JXLB_CONFIG_HARDWARE) {
+    Fail(p, JXLB_ERROR, "Error while decoding: Cannot load hardware buffers API");
+    return;
+  }
+  p->format = cfg == JXLB_CONFIG_RGBA_8888 ? JXLB_FORMAT_RGBA_8888 : cfg == JXLB_CONFIG_RGBA_F16 ? JXLB_FORMAT_RGBA_F16
+              : cfg == JXLB_CONFIG_RGB_565 ? JXLB_FORMAT_RGB_565 : JXLB_FORMAT_RGBA_1010102;
+  p->color_space = ColorSpaceTag(md, api);
+  MakeFramePlan(md, fh, p->g, p->cs.size(), &p->plan);
+}
+
+struct JobLists {
+  std::vector<StreamJob> single, lf, groups;
+};
+
+}  // namespace
+
+void FreeImageMemory(void* data, int device) {
+  if (!data) return;
+  if (device < 0) {
+    if (!Pool().Put(data)) cudaFreeHost(data);
+  } else {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    cudaFree(data);
+    cudaSetDevice(cur);
+  }
+}
+
+int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device, std::vector<DecodedImage>* out,
+                BatchTimings* timings) {
+  out->assign(n, DecodedImage());
+  if (api_level <= 0) api_level = 34;
+  std::vector<Parsed> ps(n);
+  for (size_t i = 0; i < n; ++i) ParseRequest(reqs[i], api_level, &ps[i]);
+  int overall = JXLB_OK;
+  auto finish_errors = [&]() {
+    for (size_t i = 0; i < n; ++i) {
+      (*out)[i].status = ps[i].status;
+      (*out)[i].message = ps[i].message;
+      if (ps[i].status != JXLB_OK) overall = ps[i].status;
+    }
+  };
+  bool any = false;
+  for (auto& p : ps) any |= p.status == JXLB_OK;
+  if (!any) {
+    finish_errors();
+    return overall;
+  }
+  DeviceContext* ctx = nullptr;
+  try {
+    ctx = GetContext(device);
+  } catch (CudaError& e) {
+    for (auto& p : ps)
+      if (p.status == JXLB_OK) Fail(&p, JXLB_ERROR_NO_DEVICE, e.msg);
+    finish_errors();
+    return overall;
+  }
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  try {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    // ---- plan the batch buffers
+    size_t const_total = 0, work_total = 0, stage_total = 0;
+    uint32_t nframes = 0;
+    JobLists jobs;
+    std::vector<uint32_t> frame_of(n, 0);
+    size_t lf_scratch = 0, grp_scratch = 0;
+    for (size_t i = 0; i < n; ++i) {
+      Parsed& p = ps[i];
+      if (p.status != JXLB_OK) continue;
+      p.const_off = const_total;
+      const_total += Align256(p.plan.const_bytes);
+      p.work_off = work_total;
+      work_total += Align256(p.plan.work_bytes);
+      p.stage_stride = Align256((size_t) p.md.xsize * 4 * (p.out16 ? 2 : 1));
+      p.stage_off = stage_total;
+      stage_total += Align256(p.stage_stride * p.md.ysize);
+      frame_of[i] = nframes++;
+      const FrameDev& f = p.plan.proto;
+      if (f.single_section) {
+        jobs.single.push_back(StreamJob{frame_of[i], 0, f.num_lf_groups + f.num_groups, 0});
+      } else {
+        if (f.encoding == 0)
+          for (uint32_t l = 0; l < f.num_lf_groups; ++l) jobs.lf.push_back(StreamJob{frame_of[i], l, l, 0});
+        for (uint32_t g = 0; g < f.num_groups; ++g) jobs.groups.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, 0});
+      }
+    }
+    // scratch layouts
+    ScratchLayout sl_single{}, sl_lf{}, sl_grp{};
+    auto job_bytes = [](const ScratchLayout& l) {
+      return Align256(l.arena_bytes) + Align256((size_t) l.wp_ints * 4) + 3 * 1024 + Align256(l.hf_arena_bytes) + (l.hf_arena_bytes ? 2 * 65536 * 4 : 0);
+    };
+    sl_single.arena_bytes = 1536u << 10;
+    sl_single.wp_ints = WPState::ScratchInts(1024 + 8);
+    sl_single.hf_arena_bytes = 2048u << 10;
+    sl_single.max_local_nodes = 32768;
+    sl_single.bytes_per_job = Align256(job_bytes(sl_single));
+    sl_lf.arena_bytes = 1536u << 10;
+    sl_lf.wp_ints = WPState::ScratchInts(kLfGroupCells + 8);
+    sl_lf.max_local_nodes = 32768;
+    sl_lf.bytes_per_job = Align256(job_bytes(sl_lf));
+    bool grp_modular = false, grp_local_tree = false;
+    uint32_t grp_dim = 256;
+    for (size_t i = 0; i < n; ++i) {
+      if (ps[i].status != JXLB_OK || ps[i].plan.proto.single_section) continue;
+      const FrameDev& f = ps[i].plan.proto;
+      if (f.num_mod_channels > f.global_mod_decoded) {
+        grp_modular = true;
+        grp_dim = std::max(grp_dim, f.group_dim);
+        if (!ps[i].g.has_global_tree) grp_local_tree = true;
+      }
+    }
+    sl_grp.arena_bytes = grp_modular ? (grp_local_tree ? (192u << 10) : (16u << 10)) : 0;
+    sl_grp.wp_ints = grp_modular ? WPState::ScratchInts(grp_dim + 8) : 0;
+    sl_grp.max_local_nodes = 2048;
+    sl_grp.bytes_per_job = Align256(job_bytes(sl_grp));
+    lf_scratch = sl_lf.bytes_per_job * jobs.lf.size();
+    grp_scratch = sl_grp.bytes_per_job * jobs.groups.size();
+    const size_t single_scratch = sl_single.bytes_per_job * jobs.single.size();
+    const size_t scratch_total = Align256(lf_scratch) + Align256(grp_scratch) + Align256(single_scratch);
+    const size_t njobs = jobs.single.size() + jobs.lf.size() + jobs.groups.size();
+    const size_t meta_total = Align256(nframes * sizeof(FrameDev)) + Align256(njobs * sizeof(StreamJob));
+
+    ctx->const_buf.Ensure(const_total);
+    ctx->work_buf.Ensure(work_total);
+    ctx->scratch_buf.Ensure(scratch_total);
+    ctx->meta_buf.Ensure(meta_total);
+    ctx->stage_out.Ensure(stage_total);
+    ctx->staging.Ensure(const_total + meta_total);
+    uint32_t status_total = 0;
+    for (size_t i = 0; i < n; ++i)
+      if (ps[i].status == JXLB_OK) {
+        ps[i].status_base = status_total;
+        status_total += ps[i].plan.num_streams;
+      }
+    ctx->status_host.Ensure((size_t) status_total * 4 + 256);
+
+    CUDA_OK(cudaEventRecord(ctx->ev[0], s));
+    // ---- stage + upload
+    uint8_t* stg = ctx->staging.p;
+    std::vector<FrameDev> frames(nframes);
+    for (size_t i = 0; i < n; ++i) {
+      Parsed& p = ps[i];
+      if (p.status != JXLB_OK) continue;
+      FillConstRegion(p.plan, p.cs.data(), p.fh, p.g, stg + p.const_off);
+      frames[frame_of[i]] = BindFrameDev(p.plan, ctx->const_buf.p + p.const_off, ctx->work_buf.p + p.work_off);
+    }
+    uint8_t* meta_h = stg + const_total;
+    memcpy(meta_h, frames.data(), nframes * sizeof(FrameDev));
+    StreamJob* jobs_h = reinterpret_cast<StreamJob*>(meta_h + Align256(nframes * sizeof(FrameDev)));
+    size_t jo = 0;
+    memcpy(jobs_h + jo, jobs.single.data(), jobs.single.size() * sizeof(StreamJob));
+    const size_t single_o = jo;
+    jo += jobs.single.size();
+    memcpy(jobs_h + jo, jobs.lf.data(), jobs.lf.size() * sizeof(StreamJob));
+    const size_t lf_o = jo;
+    jo += jobs.lf.size();
+    memcpy(jobs_h + jo, jobs.groups.data(), jobs.groups.size() * sizeof(StreamJob));
+    const size_t grp_o = jo;
+    CUDA_OK(cudaMemcpyAsync(ctx->const_buf.p, stg, const_total, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(ctx->meta_buf.p, meta_h, meta_total, cudaMemcpyHostToDevice, s));
+    const FrameDev* frames_d = reinterpret_cast<const FrameDev*>(ctx->meta_buf.p);
+    const StreamJob* jobs_d = reinterpret_cast<const StreamJob*>(ctx->meta_buf.p + Align256(nframes * sizeof(FrameDev)));
+    // zero: coefficient planes (the AC decoder scatters only non-zeros) and the status words
+    for (size_t i = 0; i < n; ++i) {
+      Parsed& p = ps[i];
+      if (p.status != JXLB_OK) continue;
+      uint8_t* wb = ctx->work_buf.p + p.work_off;
+      CUDA_OK(cudaMemsetAsync(wb + p.plan.off_status, 0xFF, (size_t) p.plan.num_streams * 4, s));
+      if (p.plan.coef_bytes) CUDA_OK(cudaMemsetAsync(wb + p.plan.off_coef, 0, p.plan.coef_bytes, s));
+    }
+    CUDA_OK(cudaEventRecord(ctx->ev[1], s));
+    // ---- entropy-coded sections
+    uint8_t* sc = ctx->scratch_buf.p;
+    sl_lf.base = sc;
+    sl_grp.base = sc + Align256(lf_scratch);
+    sl_single.base = sc + Align256(lf_scratch) + Align256(grp_scratch);
+    LaunchSingleSectionFrames(frames_d, jobs_d + single_o, (uint32_t) jobs.single.size(), ctx->nat_dev, sl_single, s);
+    LaunchLfGroups(frames_d, jobs_d + lf_o, (uint32_t) jobs.lf.size(), sl_lf, s);
+    LaunchPassGroups(frames_d, jobs_d + grp_o, (uint32_t) jobs.groups.size(), ctx->nat_dev, sl_grp, s);
+    CUDA_OK(cudaEventRecord(ctx->ev[2], s));
+    // ---- reconstruction
+    for (size_t i = 0; i < n; ++i) {
+      Parsed& p = ps[i];
+      if (p.status != JXLB_OK) continue;
+      const FrameDev& f = frames[frame_of[i]];
+      if (f.encoding == 0) {
+        LaunchLfFinal(f, s);
+        LaunchRecon(f, ctx->nt_dev, s);
+      }
+    }
+    CUDA_OK(cudaEventRecord(ctx->ev[3], s));
+    // ---- filters, colour, pack
+    std::vector<uint8_t*> final_dev(n, nullptr);
+    std::vector<size_t> final_bytes(n, 0);
+    for (size_t i = 0; i < n; ++i) {
+      Parsed& p = ps[i];
+      if (p.status != JXLB_OK) continue;
+      const FrameDev& f = frames[frame_of[i]];
+      OutputDesc od;
+      od.data = ctx->stage_out.p + p.stage_off;
+      od.stride_bytes = (uint32_t) p.stage_stride;
+      od.bits16 = p.out16;
+      od.alpha_channel = -1;
+      od.alpha_bits = 8;
+      od.color_bits = p.md.bits_per_sample;
+      int ai = p.md.alpha_channel();
+      if (ai >= 0) {
+        od.alpha_channel = (int32_t) (f.num_color_mod_channels + (uint32_t) ai);
+        od.alpha_bits = p.md.extra[ai].bits;
+      }
+      if (f.encoding == 0) {
+        int cur = LaunchFilters(f, s);
+        LaunchColor(f, p.cp, ctx->nt_dev, cur ? f.xyb1 : f.xyb0, od, s);
+      } else {
+        LaunchModularToRgba(f, od, s);
+      }
+      // ReformatColorConfig
+      PackParams pk;
+      pk.src = od.data;
+      pk.src_stride = od.stride_bytes;
+      pk.width = p.md.xsize;
+      pk.height = p.md.ysize;
+      pk.src16 = p.out16;
+      pk.depth = p.depth;
+      pk.format = (uint32_t) p.format;
+      pk.associate = (!p.alpha_premultiplied && p.has_alpha) ? 1 : 0;
+      pk.attenuate = !p.alpha_premultiplied ? 1 : 0;
+      pk.dst_stride = pk.width * FormatBytesPerPixel(pk.format);
+      final_bytes[i] = (size_t) pk.dst_stride * pk.height;
+      uint8_t* dst = nullptr;
+      CUDA_OK(cudaMalloc(&dst, final_bytes[i]));
+      final_dev[i] = dst;
+      pk.dst = dst;
+      LaunchPack(pk, s);
+    }
+    CUDA_OK(cudaEventRecord(ctx->ev[4], s));
+    // ---- statuses + results
+    {
+      uint32_t* sh = reinterpret_cast<uint32_t*>(ctx->status_host.p);
+      for (size_t i = 0; i < n; ++i) {
+        Parsed& p = ps[i];
+        if (p.status != JXLB_OK) continue;
+        CUDA_OK(cudaMemcpyAsync(sh + p.status_base, ctx->work_buf.p + p.work_off + p.plan.off_status, (size_t) p.plan.num_streams * 4,
+                                cudaMemcpyDeviceToHost, s));
+      }
+    }
+    std::vector<void*> host_out(n, nullptr);
+    if (output_device < 0) {
+      for (size_t i = 0; i < n; ++i) {
+        if (ps[i].status != JXLB_OK) continue;
+        host_out[i] = Pool().Get(final_bytes[i]);
+        if (!host_out[i]) {
+          Fail(&ps[i], JXLB_OOM, "Not enough memory to decode this image");
+          continue;
+        }
+        CUDA_OK(cudaMemcpyAsync(host_out[i], final_dev[i], final_bytes[i], cudaMemcpyDeviceToHost, s));
+      }
+    }
+    CUDA_OK(cudaEventRecord(ctx->ev[5], s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (timings) {
+      for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&timings->ms[k], ctx->ev[k], ctx->ev[k + 1]);
+      cudaEventElapsedTime(&timings->ms[5], ctx->ev[0], ctx->ev[5]);
+    }
+    // ---- per-image status from the stream statuses
+    const int32_t* sh = reinterpret_cast<const int32_t*>(ctx->status_host.p);
+    for (size_t i = 0; i < n; ++i) {
+      Parsed& p = ps[i];
+      if (p.status != JXLB_OK) {
+        if (final_dev[i]) cudaFree(final_dev[i]);
+        if (host_out[i]) Pool().Put(host_out[i]);
+        continue;
+      }
+      const FrameDev& f = p.plan.proto;
+      int worst = kOk;
+      auto check = [&](uint32_t slot) {
+        int v = sh[p.status_base + slot];
+        if (v == -1) v = kErrBadStream;  // never written
+        if (v != kOk && worst == kOk) worst = v;
+      };
+      if (f.single_section) {
+        check(f.num_lf_groups + f.num_groups);
+      } else {
+        if (f.encoding == 0)
+          for (uint32_t l = 0; l < f.num_lf_groups; ++l) check(l);
+        for (uint32_t g = 0; g < f.num_groups; ++g) check(f.num_lf_groups + g);
+      }
+      if (worst != kOk) {
+        if (worst == kErrUnsupported || worst == kErrScratch) Fail(&p, JXLB_UNSUPPORTED, "coding tool or stream size outside this build's coverage");
+        else Fail(&p, JXLB_INVALID_JXL, worst == kErrTruncated ? "truncated section" : "corrupt section");
+        if (final_dev[i]) cudaFree(final_dev[i]);
+        if (host_out[i]) Pool().Put(host_out[i]);
+        continue;
+      }
+      DecodedImage& d = (*out)[i];
+      d.width = p.md.xsize;
+      d.height = p.md.ysize;
+      d.stride_bytes = p.md.xsize * FormatBytesPerPixel((uint32_t) p.format);
+      d.format = p.format;
+      d.color_space = p.color_space;
+      d.premultiplied = p.has_alpha ? 1 : 0;
+      if (output_device < 0) {
+        d.data = host_out[i];
+        d.device = -1;
+        cudaFree(final_dev[i]);
+      } else {
+        d.data = final_dev[i];
+        d.device = ctx->device;
+      }
+    }
+  } catch (CudaError& e) {
+    for (auto& p : ps)
+      if (p.status == JXLB_OK) Fail(&p, JXLB_ERROR_NO_DEVICE, e.msg);
+    cudaGetLastError();
+  }
+  finish_errors();
+  return overall;
+}
+
+}  // namespace jxlb

@@ -148,6 +148,7 @@ struct FrameDev {
   uint8_t* cell_strategy;          // [h8][w8]: strategy | 0x80 if top-left cell of its block, 0xFF = uncovered
   uint16_t* cell_hfmul;            // [h8][w8]: hf_mul of the covering block
   uint8_t* cell_sharp;             // [h8][w8]
+  uint16_t* cell_off;              // [h8][w8]: (dy << 8) | dx offset of the cell from its block's top-left cell
   int16_t* coef;                   // [3][coef_h][coef_stride] quantised coefficients (X, Y, B), block-rectangle layout
   uint32_t coef_stride, coef_h;
   float* lf;                       // [3][h8][lf_stride] dequantised (X, Y, B)

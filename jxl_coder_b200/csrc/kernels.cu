@@ -1,0 +1,226 @@
+// CUDA kernels of the JPEG XL decode path (sm_100a).
+//
+// Stream kernels (entropy-coded sections): every section of a frame is an inherently serial bitstream (ANS state,
+// context depends on previously decoded symbols), so the unit of parallelism is the section: (image, LF group) and
+// (image, group).  This first version gives each section its own warp with one active lane running the shared
+// host/device section decoder; a batch of 64 4096x4096 images has 16 384 group sections + 256 LF-group sections in
+// flight.  Numeric kernels: LF dequant + smoothing per cell, dequant/CfL/LLF/inverse-VarDCT per 64x64 region in
+// shared memory (recon.h), per-pixel filters and colour conversion (pixel_stages.h).
+#include "kernels.h"
+
+#include <atomic>
+
+#include "recon.h"
+
+namespace jxlb {
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+
+constexpr int kStreamBlockThreads = 32;  // one warp per section, lane 0 decodes
+
+struct SyncThreads {
+  __device__ void operator()() const { __syncthreads(); }
+};
+
+__device__ StreamScratch CarveScratch(const ScratchLayout& s, uint32_t job, uint8_t** hf_arena, uint32_t** perm) {
+  uint8_t* p = s.base + (uint64_t) job * s.bytes_per_job;
+  StreamScratch sc;
+  sc.arena.Init(p, s.arena_bytes);
+  p += (s.arena_bytes + 255u) & ~255u;
+  sc.wp = reinterpret_cast<int32_t*>(p);
+  p += ((uint64_t) s.wp_ints * 4 + 255u) & ~(uint64_t) 255u;
+  sc.nzmap = p;
+  p += 3 * 1024;
+  sc.lz77 = nullptr;
+  sc.lz77_mask = 0;
+  if (hf_arena) *hf_arena = p;
+  p += (s.hf_arena_bytes + 255u) & ~255u;
+  if (perm) *perm = reinterpret_cast<uint32_t*>(p);
+  return sc;
+}
+
+__global__ void __launch_bounds__(kStreamBlockThreads) SingleSectionKernel(const FrameDev* frames, const StreamJob* jobs,
+                                                                           uint32_t njobs, NaturalOrders nat, ScratchLayout scratch) {
+  const uint32_t j = blockIdx.x;
+  if (j >= njobs || threadIdx.x != 0) return;
+  const StreamJob job = jobs[j];
+  const FrameDev& f = frames[job.frame];
+  uint8_t* hf_mem;
+  uint32_t* perm;
+  StreamScratch sc = CarveScratch(scratch, j, &hf_mem, &perm);
+  Arena hf;
+  hf.Init(hf_mem, scratch.hf_arena_bytes);
+  f.status[job.status_slot] = DecodeSingleSectionFrame(f, nat, sc, hf, perm, scratch.max_local_nodes);
+}
+
+__global__ void __launch_bounds__(kStreamBlockThreads) LfGroupKernel(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs,
+                                                                     ScratchLayout scratch) {
+  const uint32_t j = blockIdx.x;
+  if (j >= njobs || threadIdx.x != 0) return;
+  const StreamJob job = jobs[j];
+  const FrameDev& f = frames[job.frame];
+  StreamScratch sc = CarveScratch(scratch, j, nullptr, nullptr);
+  BitReader br;
+  const uint32_t sec = 1 + job.index;
+  br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);
+  f.status[job.status_slot] = DecodeLfGroupSection(br, f, job.index, sc, scratch.max_local_nodes);
+}
+
+__global__ void __launch_bounds__(kStreamBlockThreads) PassGroupKernel(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs,
+                                                                       NaturalOrders nat, ScratchLayout scratch) {
+  const uint32_t j = blockIdx.x;
+  if (j >= njobs || threadIdx.x != 0) return;
+  const StreamJob job = jobs[j];
+  const FrameDev& f = frames[job.frame];
+  StreamScratch sc = CarveScratch(scratch, j, nullptr, nullptr);
+  BitReader br;
+  const uint32_t sec = 1 + f.num_lf_groups + 1 + job.index;
+  br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);
+  int st = kOk;
+  if (f.encoding == 0) st = DecodeAcGroup(br, f, job.index, nat, sc);
+  if (st == kOk) st = DecodeModularGroup(br, f, job.index, sc, scratch.max_local_nodes);
+  f.status[job.status_slot] = st;
+}
+
+// ---- numeric ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) LfFinalKernel(const FrameDev f) {
+  const uint32_t cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y;
+  if (cx >= f.w8 || cy >= f.h8) return;
+  const LfMul m = MakeLfMul(f);
+  float v[3];
+  LfFinalCell(f, m, cx, cy, v);
+  const size_t plane = (size_t) f.h8 * f.lf_stride, o = (size_t) cy * f.lf_stride + cx;
+  f.lf[o] = v[0];
+  f.lf[plane + o] = v[1];
+  f.lf[2 * plane + o] = v[2];
+}
+
+constexpr int kReconThreads = 192;  // 3 channels x 64 columns/rows
+
+__global__ void __launch_bounds__(kReconThreads) ReconRegionKernel(const FrameDev f, const NumericTables* nt) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  RegionShared& sh = *reinterpret_cast<RegionShared*>(smem);
+  ReconRegion(f, *nt, blockIdx.x, blockIdx.y, sh, (int) threadIdx.x, (int) blockDim.x, SyncThreads());
+}
+
+// One CTA per 8x8 cell; only top-left cells of blocks that are not contained in a 64x64 region do work.
+__global__ void __launch_bounds__(256) ReconLargeKernel(const FrameDev f, const NumericTables* nt) {
+  const uint32_t bx = blockIdx.x, by = blockIdx.y;
+  const uint8_t s = f.cell_strategy[(size_t) by * f.w8 + bx];
+  if (!(s & 0x80) || s == 0xFF) return;
+  if (!BlockNeedsLargePath(s & 0x7Fu, bx, by)) return;
+  ReconLargeBlock(f, *nt, bx, by, (int) threadIdx.x, (int) blockDim.x, SyncThreads());
+}
+
+__global__ void __launch_bounds__(256) GaborishKernel(const FrameDev f, const float* src, float* dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= (int) f.width || y >= (int) f.height) return;
+  StageGaborish(f, src, dst, x, y);
+}
+
+__global__ void __launch_bounds__(256) EpfKernel(const FrameDev f, int stage, const float* src, float* dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= (int) f.width || y >= (int) f.height) return;
+  StageEpf(f, stage, src, dst, x, y);
+}
+
+__global__ void __launch_bounds__(256) ColorKernel(const FrameDev f, const ColorParams cp, const NumericTables* nt, const float* src,
+                                                   OutputDesc out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= (int) f.width || y >= (int) f.height) return;
+  StageColorToRgba(f, cp, *nt, src, out, x, y);
+}
+
+__global__ void __launch_bounds__(256) ModularToRgbaKernel(const FrameDev f, OutputDesc out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= (int) f.width || y >= (int) f.height) return;
+  if (!f.single_section) StageGlobalInverseRct(f, x, y);
+  StageModularToRgba(f, out, x, y);
+}
+
+__global__ void __launch_bounds__(256) PackKernel(const PackParams p) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= p.width || y >= p.height) return;
+  PackPixel(p, x, y);
+}
+
+dim3 PixelGrid(uint32_t w, uint32_t h, uint32_t bx) { return dim3((w + bx - 1) / bx, h, 1); }
+
+}  // namespace
+
+void LaunchPack(const PackParams& p, cudaStream_t stream) {
+  PackKernel<<<PixelGrid(p.width, p.height, 256), 256, 0, stream>>>(p);
+  ++g_launches;
+}
+
+uint64_t KernelLaunchCount() { return g_launches.load(); }
+
+void LaunchSingleSectionFrames(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat,
+                               ScratchLayout scratch, cudaStream_t stream) {
+  if (!njobs) return;
+  SingleSectionKernel<<<njobs, kStreamBlockThreads, 0, stream>>>(frames, jobs, njobs, nat, scratch);
+  ++g_launches;
+}
+void LaunchLfGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, ScratchLayout scratch, cudaStream_t stream) {
+  if (!njobs) return;
+  LfGroupKernel<<<njobs, kStreamBlockThreads, 0, stream>>>(frames, jobs, njobs, scratch);
+  ++g_launches;
+}
+void LaunchPassGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat, ScratchLayout scratch,
+                      cudaStream_t stream) {
+  if (!njobs) return;
+  PassGroupKernel<<<njobs, kStreamBlockThreads, 0, stream>>>(frames, jobs, njobs, nat, scratch);
+  ++g_launches;
+}
+
+void LaunchLfFinal(const FrameDev& f, cudaStream_t stream) {
+  LfFinalKernel<<<PixelGrid(f.w8, f.h8, 256), 256, 0, stream>>>(f);
+  ++g_launches;
+}
+
+void LaunchRecon(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(ReconRegionKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(RegionShared));
+    configured = true;
+  }
+  dim3 grid((f.w8 + kRegionCells - 1) / kRegionCells, (f.h8 + kRegionCells - 1) / kRegionCells, 1);
+  ReconRegionKernel<<<grid, kReconThreads, sizeof(RegionShared), stream>>>(f, nt_dev);
+  ReconLargeKernel<<<dim3(f.w8, f.h8, 1), 256, 0, stream>>>(f, nt_dev);
+  g_launches += 2;
+}
+
+int LaunchFilters(const FrameDev& f, cudaStream_t stream) {
+  float* buf[2] = {f.xyb0, f.xyb1};
+  int cur = 0;
+  const dim3 grid = PixelGrid(f.width, f.height, 256);
+  if (f.rf.gab) {
+    GaborishKernel<<<grid, 256, 0, stream>>>(f, buf[cur], buf[cur ^ 1]);
+    cur ^= 1;
+    ++g_launches;
+  }
+  const int iters = f.rf.epf_iters;
+  for (int stage = 0; stage < 3; ++stage) {
+    const bool run = (stage == 0 && iters == 3) || (stage == 1 && iters >= 1) || (stage == 2 && iters >= 2);
+    if (!run) continue;
+    EpfKernel<<<grid, 256, 0, stream>>>(f, stage, buf[cur], buf[cur ^ 1]);
+    cur ^= 1;
+    ++g_launches;
+  }
+  return cur;
+}
+
+void LaunchColor(const FrameDev& f, const ColorParams& cp, const NumericTables* nt_dev, const float* src, OutputDesc out,
+                 cudaStream_t stream) {
+  ColorKernel<<<PixelGrid(f.width, f.height, 256), 256, 0, stream>>>(f, cp, nt_dev, src, out);
+  ++g_launches;
+}
+
+void LaunchModularToRgba(const FrameDev& f, OutputDesc out, cudaStream_t stream) {
+  ModularToRgbaKernel<<<PixelGrid(f.width, f.height, 256), 256, 0, stream>>>(f, out);
+  ++g_launches;
+}
+
+}  // namespace jxlb

@@ -1,0 +1,51 @@
+// Launch wrappers of the CUDA kernels (kernels.cu).  All launches are asynchronous on the given stream.
+#pragma once
+#include <cuda_runtime.h>
+#include "frame.h"
+#include "numeric.h"
+#include "pack.h"
+#include "pixel_stages.h"
+#include "vardct_sections.h"
+
+namespace jxlb {
+
+// One serial bitstream section to decode: frame index in the batch + section-specific index.
+struct StreamJob {
+  uint32_t frame;
+  uint32_t index;        // LF group / group index
+  uint32_t status_slot;  // entry of FrameDev::status to write
+  uint32_t pad;
+};
+
+// Per-launch scratch: job j owns [j * bytes_per_job, (j + 1) * bytes_per_job) of `base`, carved into
+// arena | weighted-predictor state | non-zero map | HfGlobal arena + permutation scratch (single-section only).
+struct ScratchLayout {
+  uint8_t* base;
+  uint64_t bytes_per_job;
+  uint32_t arena_bytes;
+  uint32_t wp_ints;
+  uint32_t hf_arena_bytes;   // single-section frames only
+  uint32_t max_local_nodes;
+};
+
+void LaunchSingleSectionFrames(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat,
+                               ScratchLayout scratch, cudaStream_t stream);
+void LaunchLfGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, ScratchLayout scratch, cudaStream_t stream);
+void LaunchPassGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat, ScratchLayout scratch,
+                      cudaStream_t stream);
+
+// Numeric stages of one VarDCT frame (FrameDev passed by value).
+void LaunchLfFinal(const FrameDev& f, cudaStream_t stream);
+void LaunchRecon(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t stream);
+// Gaborish + EPF stages as configured; returns which buffer (0 = xyb0, 1 = xyb1) holds the result.
+int LaunchFilters(const FrameDev& f, cudaStream_t stream);
+void LaunchColor(const FrameDev& f, const ColorParams& cp, const NumericTables* nt_dev, const float* src, OutputDesc out,
+                 cudaStream_t stream);
+void LaunchModularToRgba(const FrameDev& f, OutputDesc out, cudaStream_t stream);
+// Alpha association + packing to the requested Bitmap format (pack.h).
+void LaunchPack(const PackParams& p, cudaStream_t stream);
+
+// Number of kernel launches issued by this module since process start (bench.py reports it as gpu_launches).
+uint64_t KernelLaunchCount();
+
+}  // namespace jxlb

@@ -1,0 +1,131 @@
+// Per-pixel stages after the inverse transforms, host + device: Gaborish, EPF stages, XYB -> RGBA (u8 dithered / u16),
+// modular (lossless) samples -> RGBA.  One call = one output pixel; the kernels map one thread per pixel.
+// Output matches what the reference asks libjxl for: interleaved RGBA, JxlPixelFormat{4, UINT8|UINT16, native, 0}
+// (/root/reference/jxlcoder/src/main/cpp/interop/JxlDecoding.cpp:63,96), alpha not premultiplied.
+#pragma once
+#include "numeric.h"
+
+namespace jxlb {
+
+struct OutputDesc {
+  uint8_t* data;           // RGBA interleaved
+  uint32_t stride_bytes;
+  uint32_t bits16;         // 0: uint8 samples, 1: uint16 samples
+  int32_t alpha_channel;   // index into the frame's modular image, or -1
+  uint32_t alpha_bits;     // bit depth of the alpha samples
+  uint32_t color_bits;     // bit depth of modular colour samples (modular frames)
+};
+
+JXLB_HD Planes3 ViewPlanes(const FrameDev& f, const float* base) {
+  Planes3 v;
+  const size_t plane = (size_t) f.plane_h * f.plane_stride;
+  v.p[0] = base;
+  v.p[1] = base + plane;
+  v.p[2] = base + 2 * plane;
+  v.w = (int) f.width;
+  v.h = (int) f.height;
+  v.stride = (int) f.plane_stride;
+  return v;
+}
+
+JXLB_HD void StageGaborish(const FrameDev& f, const float* src, float* dst, int x, int y) {
+  const Planes3 im = ViewPlanes(f, src);
+  const size_t plane = (size_t) f.plane_h * f.plane_stride, o = (size_t) y * f.plane_stride + x;
+  for (int c = 0; c < 3; ++c) dst[c * plane + o] = GaborishSample(im, c, x, y, f.rf.gab_w1[c], f.rf.gab_w2[c]);
+}
+
+JXLB_HD void StageEpf(const FrameDev& f, int stage, const float* src, float* dst, int x, int y) {
+  const Planes3 im = ViewPlanes(f, src);
+  const size_t plane = (size_t) f.plane_h * f.plane_stride, o = (size_t) y * f.plane_stride + x;
+  const size_t ci = (size_t) (y >> 3) * f.w8 + (x >> 3);
+  const float inv_sigma = EpfInvSigma(f, f.cell_hfmul[ci], f.cell_sharp[ci]);
+  float out[3];
+  EpfPixel(im, f.rf, stage, x, y, inv_sigma, out);
+  dst[o] = out[0];
+  dst[plane + o] = out[1];
+  dst[2 * plane + o] = out[2];
+}
+
+JXLB_HD uint32_t ScaleSample(int32_t v, uint32_t bits, uint32_t maxout) {
+  const uint32_t maxin = (1u << bits) - 1;
+  if (v < 0) v = 0;
+  if ((uint32_t) v > maxin) v = (int32_t) maxin;
+  if (maxin == maxout) return (uint32_t) v;
+  const float fv = (float) v * (1.0f / (float) maxin) * (float) maxout;
+  return (uint32_t) rintf(fv);
+}
+
+JXLB_HD void StoreRgba(const OutputDesc& out, int x, int y, uint32_t r, uint32_t g, uint32_t b, uint32_t a) {
+  if (out.bits16) {
+    uint16_t* p = reinterpret_cast<uint16_t*>(out.data + (size_t) y * out.stride_bytes) + 4 * (size_t) x;
+    p[0] = (uint16_t) r;
+    p[1] = (uint16_t) g;
+    p[2] = (uint16_t) b;
+    p[3] = (uint16_t) a;
+  } else {
+    uint8_t* p = out.data + (size_t) y * out.stride_bytes + 4 * (size_t) x;
+    p[0] = (uint8_t) r;
+    p[1] = (uint8_t) g;
+    p[2] = (uint8_t) b;
+    p[3] = (uint8_t) a;
+  }
+}
+
+JXLB_HD uint32_t AlphaAt(const FrameDev& f, const OutputDesc& out, int x, int y) {
+  const uint32_t maxout = out.bits16 ? 65535u : 255u;
+  if (out.alpha_channel < 0) return maxout;
+  const int32_t a = f.mod[(size_t) out.alpha_channel * f.height * f.mod_stride + (size_t) y * f.mod_stride + x];
+  return ScaleSample(a, out.alpha_bits, maxout);
+}
+
+JXLB_HD void StageColorToRgba(const FrameDev& f, const ColorParams& cp, const NumericTables& nt, const float* src,
+                              const OutputDesc& out, int x, int y) {
+  const size_t plane = (size_t) f.plane_h * f.plane_stride, o = (size_t) y * f.plane_stride + x;
+  float rgb[3];
+  XybToEncodedRgb(src[o], src[plane + o], src[2 * plane + o], cp, rgb);
+  uint32_t v[3];
+  if (out.bits16) {
+    for (int c = 0; c < 3; ++c) {
+      float s = rgb[c] * 65535.0f;
+      s = s < 0.0f ? 0.0f : s > 65535.0f ? 65535.0f : s;
+      v[c] = (uint32_t) rintf(s);
+    }
+  } else {
+    const float d = nt.dither[(y & 31) * 32 + (x & 31)];
+    for (int c = 0; c < 3; ++c) v[c] = ToU8Dithered(rgb[c], d);
+  }
+  if (cp.grey) v[0] = v[2] = v[1];
+  StoreRgba(out, x, y, v[0], v[1], v[2], AlphaAt(f, out, x, y));
+}
+
+// Modular (non-XYB) frames: integer samples straight to the output depth.
+JXLB_HD void StageModularToRgba(const FrameDev& f, const OutputDesc& out, int x, int y) {
+  const uint32_t maxout = out.bits16 ? 65535u : 255u;
+  const size_t plane = (size_t) f.height * f.mod_stride, o = (size_t) y * f.mod_stride + x;
+  uint32_t v[3];
+  if (f.num_color_mod_channels == 1) {
+    v[0] = v[1] = v[2] = ScaleSample(f.mod[o], out.color_bits, maxout);
+  } else {
+    for (int c = 0; c < 3; ++c) v[c] = ScaleSample(f.mod[c * plane + o], out.color_bits, maxout);
+  }
+  StoreRgba(out, x, y, v[0], v[1], v[2], AlphaAt(f, out, x, y));
+}
+
+// Frame-level inverse RCTs of a multi-section modular frame, one pixel (the per-group ones are undone in the group
+// decoder).  Applied in reverse transform order.
+JXLB_HD void StageGlobalInverseRct(const FrameDev& f, int x, int y) {
+  const size_t plane = (size_t) f.height * f.mod_stride, o = (size_t) y * f.mod_stride + x;
+  for (int t = (int) f.global_nb_transforms - 1; t >= 0; --t) {
+    const ModTransform& tr = f.global_tr[t];
+    if (tr.id != 0 || tr.begin_c + 3 > f.num_mod_channels) continue;
+    int32_t a = f.mod[(tr.begin_c) * plane + o], b = f.mod[(tr.begin_c + 1) * plane + o], c = f.mod[(tr.begin_c + 2) * plane + o];
+    InverseRctPixel(tr.rct_type, a, b, c);
+    uint32_t perm[3];
+    RctPermutation(tr.rct_type, perm);
+    f.mod[(tr.begin_c + perm[0]) * plane + o] = a;
+    f.mod[(tr.begin_c + perm[1]) * plane + o] = b;
+    f.mod[(tr.begin_c + perm[2]) * plane + o] = c;
+  }
+}
+
+}  // namespace jxlb

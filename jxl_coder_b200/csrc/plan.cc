@@ -104,6 +104,7 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
     p.off_cell_strategy = take((size_t) f.h8 * f.w8);
     p.off_cell_hfmul = take((size_t) f.h8 * f.w8 * 2);
     p.off_cell_sharp = take((size_t) f.h8 * f.w8);
+    p.off_cell_off = take((size_t) f.h8 * f.w8 * 2);
     p.coef_bytes = (size_t) 3 * f.coef_h * f.coef_stride * 2;
     p.off_coef = take(p.coef_bytes);
     p.off_lf = take((size_t) 3 * f.h8 * f.lf_stride * 4);
@@ -157,6 +158,7 @@ FrameDev BindFrameDev(const FramePlan& p, const uint8_t* cb, uint8_t* wb) {
     f.cell_strategy = wb + p.off_cell_strategy;
     f.cell_hfmul = reinterpret_cast<uint16_t*>(wb + p.off_cell_hfmul);
     f.cell_sharp = wb + p.off_cell_sharp;
+    f.cell_off = reinterpret_cast<uint16_t*>(wb + p.off_cell_off);
     f.coef = reinterpret_cast<int16_t*>(wb + p.off_coef);
     f.lf = reinterpret_cast<float*>(wb + p.off_lf);
     f.xyb0 = reinterpret_cast<float*>(wb + p.off_xyb0);

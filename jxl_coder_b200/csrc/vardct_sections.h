@@ -15,9 +15,7 @@ struct NaturalOrders {
   uint32_t offset[kNumOrders];
   uint32_t size[kNumOrders];
 };
-#ifndef __CUDA_ARCH__
-const NaturalOrders& NaturalOrderPoolHost();  // defined in natural_orders.cc
-#endif
+const NaturalOrders& NaturalOrderPoolHost();  // host only; defined in natural_orders.cc
 
 static constexpr uint32_t kOrderInFramePool = 0x80000000u;
 
@@ -241,10 +239,12 @@ JXLB_HD_NOINLINE int DecodeLfGroupSection(BitReader& br, const FrameDev& f, uint
       for (uint32_t yy = 0; yy < by; ++yy) {
         uint8_t* r = f.cell_strategy + (size_t) (cy0 + y + yy) * f.w8 + cx0 + x;
         uint16_t* rq = f.cell_hfmul + (size_t) (cy0 + y + yy) * f.w8 + cx0 + x;
+        uint16_t* ro = f.cell_off + (size_t) (cy0 + y + yy) * f.w8 + cx0 + x;
         for (uint32_t xx = 0; xx < bx; ++xx) {
           if (r[xx] != 0xFF) return kErrBadStream;
           r[xx] = (uint8_t) t;
           rq[xx] = (uint16_t) q;
+          ro[xx] = (uint16_t) ((yy << 8) | xx);
         }
       }
       *cell = (uint8_t) (t | 0x80);
@@ -299,7 +299,9 @@ JXLB_HD_NOINLINE int DecodeAcGroup(BitReader& br, const FrameDev& f, uint32_t g,
       const uint32_t size = 64 * covered;
       const uint32_t ord = StrategyOrder(t);
       const uint32_t kc_log = 3 + (uint32_t) FloorLog2(cx > cy ? cx : cy);  // log2 of the coefficient array's columns
-      const bool tall = cy > cx;
+      // Square and tall blocks keep their coefficient array transposed in the plane, so that for every block the
+      // plane holds F[v][u] (v = vertical, u = horizontal frequency) at (row v, col u) of the block's rectangle.
+      const bool tall = cy >= cx;
       uint32_t lf_idx = 0;
       if (has_lf_thr) {
         // bucket = (bx * (nB+1) + bb) * (nY+1) + by over the quantised LF values (planes stored Y, X, B)

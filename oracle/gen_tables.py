@@ -17,10 +17,17 @@ from oracle import refjxl  # noqa: E402
 OUT = os.path.join(HERE, '..', 'jxl_coder_b200', 'csrc', 'tables')
 
 
+def _lit(v):
+    s = '%.9g' % v
+    if '.' not in s and 'e' not in s and 'n' not in s:
+        s += '.0'
+    return s + 'f'
+
+
 def fmt(vals, per_line=8):
     lines = []
     for i in range(0, len(vals), per_line):
-        lines.append(', '.join('%.9gf' % v for v in vals[i:i + per_line]) + ',')
+        lines.append(', '.join(_lit(v) for v in vals[i:i + per_line]) + ',')
     return '\n'.join(lines) + '\n'
 
 

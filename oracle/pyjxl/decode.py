@@ -193,7 +193,8 @@ def _decode_group_modular(pbr, fh, md, mchans, global_done, mimg, gtree, gcode, 
 
 def coefficient_planes(fh, hfo, strategy, first, coef_list, W, H):
     """int planes [3][H8*8, W8*8] (c: 0=X 1=Y 2=B) in the layout DESIGN.md defines for the GPU path: every varblock's
-    pixel rectangle holds its quantised coefficient array; tall blocks store it transposed."""
+    pixel rectangle holds its quantised coefficient array; square and tall blocks store it transposed, so the plane
+    holds F[v][u] (vertical, horizontal frequency) at (row v, col u) for every block."""
     h8, w8 = strategy.shape
     planes = np.zeros((3, h8 * 8, w8 * 8), np.int32)
     orders = hfo['orders']
@@ -203,7 +204,7 @@ def coefficient_planes(fh, hfo, strategy, first, coef_list, W, H):
         kc = 8 * max(cx, cy)
         pos = orders[(vd.ORDER_ID[t], c)][k]
         r, col = pos // kc, pos % kc
-        if cy > cx:
+        if cy >= cx:
             r, col = col, r
         planes[c, by * 8 + r, bx * 8 + col] += v
     return planes

@@ -11,6 +11,10 @@
 #include "../../jxl_coder_b200/csrc/frame_parser.h"
 #include "../../jxl_coder_b200/csrc/plan.h"
 #include "../../jxl_coder_b200/csrc/vardct_sections.h"
+#include "../../jxl_coder_b200/csrc/color_params.h"
+#include "../../jxl_coder_b200/csrc/numeric_tables.h"
+#include "../../jxl_coder_b200/csrc/pixel_stages.h"
+#include "../../jxl_coder_b200/csrc/recon.h"
 
 using namespace jxlb;
 
@@ -138,6 +142,76 @@ const uint16_t* emu_cell_hfmul(void* h) { return static_cast<Emu*>(h)->f.cell_hf
 const uint8_t* emu_cell_sharp(void* h) { return static_cast<Emu*>(h)->f.cell_sharp; }
 const int16_t* emu_coef(void* h) { return static_cast<Emu*>(h)->f.coef; }
 const int32_t* emu_mod(void* h) { return static_cast<Emu*>(h)->f.mod; }
+
+// Runs the numeric stages (the same host/device functions the kernels call) and writes RGBA8 / RGBA16.
+// also exposes the XYB planes after the inverse transforms (stage = 0) and after the filters (stage = 1).
+int emu_render(void* h, uint8_t* out, uint32_t stride_bytes, int bits16, float* xyb_idct, float* xyb_final) {
+  Emu* e = static_cast<Emu*>(h);
+  FrameDev& f = e->f;
+  const NumericTables& nt = GetHostNumericTables().tables;
+  OutputDesc od;
+  od.data = out;
+  od.stride_bytes = stride_bytes;
+  od.bits16 = (uint32_t) bits16;
+  od.alpha_channel = -1;
+  od.alpha_bits = 8;
+  od.color_bits = e->md.bits_per_sample;
+  int ai = e->md.alpha_channel();
+  if (ai >= 0) {
+    od.alpha_channel = (int32_t) (f.num_color_mod_channels + (uint32_t) ai);
+    od.alpha_bits = e->md.extra[ai].bits;
+  }
+  auto nosync = [] {};
+  if (f.encoding == 0) {
+    ColorParams cp;
+    std::string err;
+    if (MakeColorParams(e->md, &cp, &err)) return 3;
+    const LfMul m = MakeLfMul(f);
+    const size_t lfplane = (size_t) f.h8 * f.lf_stride;
+    for (uint32_t cy = 0; cy < f.h8; ++cy)
+      for (uint32_t cx = 0; cx < f.w8; ++cx) {
+        float v[3];
+        LfFinalCell(f, m, cx, cy, v);
+        for (int c = 0; c < 3; ++c) f.lf[c * lfplane + (size_t) cy * f.lf_stride + cx] = v[c];
+      }
+    static RegionShared sh;
+    for (uint32_t ry = 0; ry < (f.h8 + 7) / 8; ++ry)
+      for (uint32_t rx = 0; rx < (f.w8 + 7) / 8; ++rx) ReconRegion(f, nt, rx, ry, sh, 0, 1, nosync);
+    for (uint32_t cy = 0; cy < f.h8; ++cy)
+      for (uint32_t cx = 0; cx < f.w8; ++cx) {
+        uint8_t s = f.cell_strategy[(size_t) cy * f.w8 + cx];
+        if ((s & 0x80) && s != 0xFF && BlockNeedsLargePath(s & 0x7F, cx, cy)) ReconLargeBlock(f, nt, cx, cy, 0, 1, nosync);
+      }
+    const size_t plane = (size_t) f.plane_h * f.plane_stride;
+    if (xyb_idct) memcpy(xyb_idct, f.xyb0, 3 * plane * sizeof(float));
+    float* src = f.xyb0;
+    float* dst = f.xyb1;
+    auto run = [&](auto fn) {
+      for (uint32_t y = 0; y < f.height; ++y)
+        for (uint32_t x = 0; x < f.width; ++x) fn((int) x, (int) y);
+      float* t = src;
+      src = dst;
+      dst = t;
+    };
+    if (f.rf.gab) run([&](int x, int y) { StageGaborish(f, src, dst, x, y); });
+    if (f.rf.epf_iters == 3) run([&](int x, int y) { StageEpf(f, 0, src, dst, x, y); });
+    if (f.rf.epf_iters >= 1) run([&](int x, int y) { StageEpf(f, 1, src, dst, x, y); });
+    if (f.rf.epf_iters >= 2) run([&](int x, int y) { StageEpf(f, 2, src, dst, x, y); });
+    if (xyb_final) memcpy(xyb_final, src, 3 * plane * sizeof(float));
+    for (uint32_t y = 0; y < f.height; ++y)
+      for (uint32_t x = 0; x < f.width; ++x) StageColorToRgba(f, cp, nt, src, od, (int) x, (int) y);
+  } else {
+    if (e->md.xyb_encoded) return 3;
+    for (uint32_t y = 0; y < f.height; ++y)
+      for (uint32_t x = 0; x < f.width; ++x) {
+        if (!f.single_section) StageGlobalInverseRct(f, (int) x, (int) y);
+        StageModularToRgba(f, od, (int) x, (int) y);
+      }
+  }
+  return 0;
+}
+uint32_t emu_plane_stride(void* h) { return static_cast<Emu*>(h)->f.plane_stride; }
+uint32_t emu_plane_h(void* h) { return static_cast<Emu*>(h)->f.plane_h; }
 
 // Unit hooks for table checks.
 uint32_t emu_freq_ctx(uint32_t k) { return ZeroDensityFreqCtx(k); }

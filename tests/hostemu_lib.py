@@ -7,7 +7,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = ["tests/hostemu/hostemu.cc", "jxl_coder_b200/csrc/frame_parser.cc", "jxl_coder_b200/csrc/plan.cc",
-       "jxl_coder_b200/csrc/natural_orders.cc"]
+       "jxl_coder_b200/csrc/natural_orders.cc", "jxl_coder_b200/csrc/numeric_tables.cc", "jxl_coder_b200/csrc/color_params.cc"]
 OUT = os.path.join(HERE, "hostemu", "_build", "libhostemu.so")
 _lib = None
 
@@ -18,7 +18,7 @@ def build():
                                                   os.listdir(os.path.join(ROOT, "jxl_coder_b200/csrc")) if h.endswith(".h")]
     if os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", OUT] + SRC, cwd=ROOT)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", OUT] + SRC, cwd=ROOT)
     return OUT
 
 
@@ -35,6 +35,9 @@ def lib():
                      ("emu_cell_hfmul", C.c_uint16), ("emu_cell_sharp", C.c_uint8), ("emu_coef", C.c_int16), ("emu_mod", C.c_int32)):
             getattr(L, n).restype = C.POINTER(t)
             getattr(L, n).argtypes = [C.c_void_p]
+        L.emu_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+        L.emu_plane_stride.argtypes = [C.c_void_p]
+        L.emu_plane_h.argtypes = [C.c_void_p]
         L.emu_logcount.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.emu_natural_order.argtypes = [C.c_uint32, C.c_void_p]
         _lib = L
@@ -86,6 +89,23 @@ class Decoded:
     def mod(self):
         i = self.info
         return self._arr("emu_mod", (i["num_mod_channels"], i["height"], i["mod_stride"]))[:, :, :i["width"]]
+
+    def render(self, bits16=False, want_planes=False):
+        """RGBA [h, w, 4] through the numeric host/device functions (+ XYB planes after IDCT / after filters)."""
+        i = self.info
+        L = lib()
+        dt = np.uint16 if bits16 else np.uint8
+        out = np.zeros((i["height"], i["width"], 4), dt)
+        ps, ph = L.emu_plane_stride(self.h), L.emu_plane_h(self.h)
+        a = np.zeros((3, ph, ps), np.float32) if want_planes else None
+        b = np.zeros((3, ph, ps), np.float32) if want_planes else None
+        rc = L.emu_render(self.h, out.ctypes.data, out.strides[0], int(bits16), a.ctypes.data if want_planes else None,
+                          b.ctypes.data if want_planes else None)
+        if rc:
+            raise RuntimeError("emu_render rc=%d" % rc)
+        if want_planes:
+            return out, a[:, :i["height"], :i["width"]], b[:, :i["height"], :i["width"]]
+        return out
 
     def close(self):
         if self.h:
