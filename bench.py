@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""Benchmark of the JXL -> RGBA8 decode path (BASELINE.json: "Mpixels/s decoded (JXL->RGBA8)"; workload = configs[1]:
+batch of 64 synthetic 4096x4096 lossy VarDCT (q=90) images -> RGBA_8888 per GPU).
+
+    python bench.py --gpus N --steps K --warmup W                 # our CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W # the reference's own CPU path (oracle/_ref), rank 0 only
+
+A step = one pass of the whole hot path over one batch.  `value` times the kernels with the codestreams + parsed tables
+already resident in HBM (jxlb_batch_prepare once, jxlb_batch_run per step); `e2e` times jxlb_decode_batch on host
+buffers, i.e. header parsing, pinned staging, H2D, all kernels and the D2H of every decoded pixel.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZE = 4096
+BATCH = 64
+DISTINCT = 8
+MPIX_PER_IMAGE = SIZE * SIZE / 1e6
+# algorithmic bytes per pixel of the inverse-transform kernel (SURVEY.md §8d "if split: K_idct"):
+# 3 x int16 coefficients read (6 B) + per-cell metadata and LF (0.25 B) + 3 x f32 XYB samples written (12 B)
+IDCT_BYTES_PER_PIXEL = 18.25
+
+
+def load_inputs(batch=BATCH, distinct=DISTINCT, size=SIZE):
+    """`distinct` different synthetic images (seeds 12345+i, oracle/synth.py) encoded with the reference's encoder
+    settings and cached under bench_data/; the batch cycles through them."""
+    from oracle import gen_inputs
+    datas = [gen_inputs.c2_image(i, size) for i in range(distinct)]
+    return [datas[i % distinct] for i in range(batch)]
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.samples.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(k)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_reference(datas, threads, seconds_budget, per_thread_images):
+    """Times the reference's DecodeJpegXlOneShot (oracle/_ref: its own sources + prebuilt libjxl 0.12.0) on host cores:
+    `threads` concurrent decodes (each creating libjxl's resizable thread pool exactly as the reference does)."""
+    from oracle import refjxl
+    refjxl.lib()
+    refjxl.decode_discard(datas[0])  # warm up
+    done = [0] * threads
+
+    def work(t):
+        for i in range(per_thread_images):
+            refjxl.decode_discard(datas[(t + i) % len(datas)])
+            done[t] += 1
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.time()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.time() - t0
+    return sum(done) * MPIX_PER_IMAGE / dt, dt, sum(done)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import refjxl
+    if not refjxl.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference once)"}))
+        return
+    datas = load_inputs()
+    cores = os.cpu_count() or 1
+    # one step = a bounded sample of the 64-image workload: `cores` concurrent decodes x 1 image each
+    sample_images = max(cores, 8)
+    vals = []
+    for i in range(args.warmup):
+        cpu_reference(datas, cores, 0, 1)
+    t0 = time.time()
+    for i in range(args.steps):
+        v, dt, nimg = cpu_reference(datas, cores, 0, max(1, sample_images // cores))
+        vals.append(v)
+    total = time.time() - t0
+    value = sum(vals) / len(vals)
+    out = {
+        "impl": "reference", "metric": "Mpixels/s decoded (JXL->RGBA8)", "value": round(value, 2), "unit": "MP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "batch of 64 synthetic 4096x4096 lossy VarDCT (q=90) JXL -> RGBA8 (configs[1]); reference arm decodes a bounded sample per step",
+                   "sample_images_per_step": sample_images},
+        "cpu_baseline": {"value": round(value, 2), "unit": "MP/s", "cores": cores, "kind": "reference",
+                         "sample": "%d concurrent DecodeJpegXlOneShot calls (libjxl 0.12.0 prebuilt x86_64, SSE2 build, own thread pool per call) on %d 4096x4096 images per step" % (cores, sample_images)},
+        "e2e": {"value": round(value, 2), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the decode path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import jxl_coder_b200 as J
+    J.load_library()
+    datas = load_inputs()
+    h2d = sum(len(d) for d in datas)
+    d2h = BATCH * SIZE * SIZE * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident measurement
+    batch = J.PreparedBatch(datas, config=J.PreferredColorConfig.RGBA_8888, device=local)
+    assert all(s == 0 for s in batch.status), batch.status
+    launches0 = J.kernel_launches()
+    for _ in range(args.warmup):
+        assert batch.run() == 0
+    launches_per_step = (J.kernel_launches() - launches0) // max(1, args.warmup)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    stage_acc = {}
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        assert batch.run() == 0
+        ms = batch.stage_ms()
+        dev_ms += ms["all_kernels"]
+        for k, v in ms.items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    barrier()
+    wall = time.perf_counter() - t0
+    # correctness spot check of what was just timed (against the reference when it is present on this box)
+    parity = None
+    try:
+        from oracle import refjxl
+        if rank == 0 and refjxl.available():
+            import numpy as np
+            got = batch.fetch(0).as_array()
+            want = refjxl.decode_sampled(datas[0], cfg=2)["pixels"].reshape(got.shape)
+            d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+            parity = {"exact": round(float((d == 0).mean()), 4), "max_abs_diff": int(d.max())}
+    except Exception as e:  # the check is informative only
+        parity = {"error": str(e)}
+    batch.free()
+    # device time (CUDA events on the decode stream), max over ranks
+    t_dev = torch.tensor([dev_ms / 1e3], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    dev_s = float(t_dev.item())
+    value = world * BATCH * MPIX_PER_IMAGE * args.steps / dev_s
+
+    # ---- end to end through the public batch call: host buffers in, host pixels out
+    for _ in range(min(args.warmup, 2)):
+        for b in J.decode_batch(datas, config=2, device=local, keep_native=True):
+            b.free()
+    barrier()
+    t1 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        res = J.decode_batch(datas, config=2, device=local, keep_native=True)
+        for b in res:
+            b.free()
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    t_e2e = torch.tensor([e2e_wall], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * MPIX_PER_IMAGE * e2e_steps / float(t_e2e.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        return
+    steps = args.steps
+    stages = {k: round(v / steps, 3) for k, v in stage_acc.items()}
+    idct_ms = stages["inverse_transforms"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = IDCT_BYTES_PER_PIXEL * BATCH * SIZE * SIZE / (idct_ms * 1e-3) / 1e9 if idct_ms > 0 else 0.0
+    out = {
+        "metric": "Mpixels/s decoded (JXL->RGBA8)", "value": round(value, 1), "unit": "MP/s", "n_gpus": world, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * dev_s / steps, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "batch of 64 synthetic 4096x4096 lossy VarDCT (q=90, effort 7) JXL -> RGBA_8888 per GPU (configs[1]); %d distinct images cycled" % DISTINCT,
+                   "images_per_gpu": BATCH, "l2": "inputs_larger_than_L2 (each step touches > 30 GB of planes)",
+                   "value_is": "kernels only, codestreams + host-parsed tables resident in HBM (jxlb_batch_run)",
+                   "roofline_kernel": "ReconRegionKernel + ReconLargeKernel (dequant + CfL + LLF + inverse VarDCT -> XYB f32 planes)",
+                   "wall_ms_per_step": round(1e3 * wall / steps, 2)},
+        "e2e": {"value": round(e2e_value, 1), "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "gpu_launches": int(launches_per_step * steps),
+        "stages_ms_per_step": stages,
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                     "algorithmic_bytes_per_pixel": IDCT_BYTES_PER_PIXEL},
+        "clocks": sampler.summary(),
+        "parity_spot_check": parity,
+    }
+    # bounded CPU baseline on this box (rank 0, N=1 only)
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import refjxl
+            if refjxl.available():
+                cores = os.cpu_count() or 1
+                v, dt, nimg = cpu_reference(datas, cores, 0, 1)
+                out["cpu_baseline"] = {"value": round(v, 2), "unit": "MP/s", "cores": cores, "kind": "reference",
+                                       "sample": "%d concurrent DecodeJpegXlOneShot calls (reference's prebuilt libjxl 0.12.0, SSE2) on %d of the 4096x4096 images, %.1f s" % (cores, nimg, dt)}
+            else:
+                out["cpu_baseline"] = {"value": None, "unit": "MP/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not present on this box"}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "unit": "MP/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -116,6 +116,21 @@ JXLB_API int jxlb_get_size(const uint8_t* data, size_t len, uint32_t* width, uin
 
 JXLB_API void jxlb_image_free(jxlb_image* img);
 
+/* Prepared batches (throughput interface).  jxlb_batch_prepare parses the requests on the CPU and uploads the
+   codestreams + tables, so the inputs are resident in HBM; jxlb_batch_run executes every kernel (entropy decode ->
+   packed pixels) and leaves the results in HBM; it can be called repeatedly.  jxlb_batch_fetch copies one result to
+   pinned host memory.  status (may be NULL) receives one jxlb_status per request. */
+typedef struct jxlb_batch jxlb_batch;
+JXLB_API jxlb_batch* jxlb_batch_prepare(const jxlb_request* reqs, size_t n, const jxlb_batch_opts* opts, int32_t* status);
+JXLB_API int jxlb_batch_run(jxlb_batch* b);
+JXLB_API int jxlb_batch_fetch(jxlb_batch* b, size_t index, jxlb_image* out);
+/* Device pointer + size of result `index` after jxlb_batch_run (valid until the next run / free). */
+JXLB_API const void* jxlb_batch_device_pixels(const jxlb_batch* b, size_t index, size_t* bytes);
+/* Device time (ms, CUDA events on the decode stream) of the last run: [0] upload, [1] LF sections, [2] group sections,
+   [3] LF dequant + smoothing, [4] dequant + inverse transforms, [5] filters + colour + pack, [6] download, [7] all kernels. */
+JXLB_API void jxlb_batch_stage_ms(const jxlb_batch* b, float* ms8);
+JXLB_API void jxlb_batch_free(jxlb_batch* b);
+
 /* JxlAnimatedImage */
 typedef struct jxlb_anim jxlb_anim;
 JXLB_API jxlb_anim* jxlb_anim_open(const uint8_t* data, size_t len, int32_t color_config, int32_t scale_mode, int32_t filter,

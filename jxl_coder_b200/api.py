@@ -103,6 +103,14 @@ def load_library():
     L.jxlb_anim_close.restype = None
     L.jxlb_anim_frame_duration_ms.argtypes = [C.c_void_p, C.c_int32]
     L.jxlb_anim_get_frame.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_Image)]
+    L.jxlb_batch_prepare.restype = C.c_void_p
+    L.jxlb_batch_prepare.argtypes = [C.POINTER(_Request), C.c_size_t, C.POINTER(_BatchOpts), C.POINTER(C.c_int32)]
+    L.jxlb_batch_run.argtypes = [C.c_void_p]
+    L.jxlb_batch_fetch.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(_Image)]
+    L.jxlb_batch_device_pixels.restype = C.c_void_p
+    L.jxlb_batch_device_pixels.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.jxlb_batch_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.jxlb_batch_free.argtypes = [C.c_void_p]
     L.jxlb_kernel_launches.restype = C.c_uint64
     L.jxlb_last_batch_timings.argtypes = [C.POINTER(C.c_float)]
     L.jxlb_version.restype = C.c_char_p
@@ -276,3 +284,50 @@ def last_batch_timings():
     buf = (C.c_float * 6)()
     load_library().jxlb_last_batch_timings(buf)
     return dict(zip(("upload", "entropy", "recon", "filters_color_pack", "download", "total"), [float(v) for v in buf]))
+
+
+class PreparedBatch:
+    """Throughput interface: parse + upload once (inputs resident in HBM), run the kernels repeatedly, results stay in HBM."""
+
+    STAGES = ("upload", "lf_sections", "group_sections", "lf_final", "inverse_transforms", "filters_color_pack", "download", "all_kernels")
+
+    def __init__(self, datas, width=-1, height=-1, config=PreferredColorConfig.RGBA_8888, scale_mode=ScaleMode.FIT,
+                 filt=JxlResizeFilter.MITCHELL_NETRAVALI, api_level=34, device=-1):
+        L = load_library()
+        n = len(datas)
+        self._bufs = [_as_buffer(d) for d in datas]
+        reqs = (_Request * n)()
+        for i, (b, ln) in enumerate(self._bufs):
+            reqs[i] = _Request(C.cast(b, C.c_void_p), ln, width, height, int(config), int(scale_mode), int(filt))
+        st = (C.c_int32 * n)()
+        opts = _BatchOpts(api_level, -1, device, 0)
+        self._h = L.jxlb_batch_prepare(reqs, n, C.byref(opts), st)
+        self.status = list(st)
+        self.n = n
+        if not self._h:
+            raise JxlCoderError(5, "jxlb_batch_prepare failed")
+
+    def run(self):
+        return load_library().jxlb_batch_run(self._h)
+
+    def fetch(self, i):
+        img = _Image()
+        st = load_library().jxlb_batch_fetch(self._h, i, C.byref(img))
+        if st != 0:
+            _raise(st, img.message.decode(errors="replace"))
+        return Bitmap(img)
+
+    def device_pixels(self, i):
+        n = C.c_size_t()
+        p = load_library().jxlb_batch_device_pixels(self._h, i, C.byref(n))
+        return p, n.value
+
+    def stage_ms(self):
+        buf = (C.c_float * 8)()
+        load_library().jxlb_batch_stage_ms(self._h, buf)
+        return dict(zip(self.STAGES, [float(v) for v in buf]))
+
+    def free(self):
+        if self._h:
+            load_library().jxlb_batch_free(self._h)
+            self._h = None

@@ -91,6 +91,40 @@ void jxlb_image_free(jxlb_image* img) {
   img->data = nullptr;
 }
 
+// ---- prepared batches ----
+struct jxlb_batch {
+  jxlb::Batch* b;
+};
+
+jxlb_batch* jxlb_batch_prepare(const jxlb_request* reqs, size_t n, const jxlb_batch_opts* opts, int32_t* status) {
+  if (!reqs || !n) return nullptr;
+  jxlb_batch_opts o{0, -1, -1, 0};
+  if (opts) o = *opts;
+  std::vector<int> st;
+  jxlb::Batch* b = PrepareBatch(reqs, n, o.api_level, o.device, &st);
+  if (status)
+    for (size_t i = 0; i < n; ++i) status[i] = st[i];
+  jxlb_batch* h = new jxlb_batch{b};
+  return h;
+}
+int jxlb_batch_run(jxlb_batch* b) { return b ? RunBatch(b->b, true) : JXLB_BAD_ARG; }
+int jxlb_batch_fetch(jxlb_batch* b, size_t index, jxlb_image* out) {
+  if (!b || !out) return JXLB_BAD_ARG;
+  DecodedImage d;
+  int rc = FetchBatchImage(b->b, index, &d);
+  FillImage(d, out);
+  return rc;
+}
+const void* jxlb_batch_device_pixels(const jxlb_batch* b, size_t index, size_t* bytes) {
+  return b ? BatchDevicePixels(b->b, index, bytes) : nullptr;
+}
+void jxlb_batch_stage_ms(const jxlb_batch* b, float* ms8) { BatchStageMs(b ? b->b : nullptr, ms8); }
+void jxlb_batch_free(jxlb_batch* b) {
+  if (!b) return;
+  FreeBatch(b->b);
+  delete b;
+}
+
 // ---- animated images: implemented in anim.cu ----
 
 uint64_t jxlb_kernel_launches(void) { return KernelLaunchCount(); }

@@ -339,64 +339,67 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p) {
   MakeFramePlan(md, fh, p->g, p->cs.size(), &p->plan);
 }
 
-struct JobLists {
-  std::vector<StreamJob> single, lf, groups;
-};
-
 }  // namespace
 
-void FreeImageMemory(void* data, int device) {
-  if (!data) return;
-  if (device < 0) {
-    if (!Pool().Put(data)) cudaFreeHost(data);
-  } else {
-    int cur = 0;
-    cudaGetDevice(&cur);
-    cudaSetDevice(device);
-    cudaFree(data);
-    cudaSetDevice(cur);
-  }
-}
+// ---- batch object ---------------------------------------------------------------------------------------------------
+struct BatchBuffers {
+  DevBuffer const_buf, work_buf, scratch_buf, meta_buf, stage_out, final_out;
+  PinnedBuffer staging, status_host;
+};
 
-int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device, std::vector<DecodedImage>* out,
-                BatchTimings* timings) {
-  out->assign(n, DecodedImage());
-  if (api_level <= 0) api_level = 34;
-  std::vector<Parsed> ps(n);
-  for (size_t i = 0; i < n; ++i) ParseRequest(reqs[i], api_level, &ps[i]);
-  int overall = JXLB_OK;
-  auto finish_errors = [&]() {
-    for (size_t i = 0; i < n; ++i) {
-      (*out)[i].status = ps[i].status;
-      (*out)[i].message = ps[i].message;
-      if (ps[i].status != JXLB_OK) overall = ps[i].status;
-    }
-  };
-  bool any = false;
-  for (auto& p : ps) any |= p.status == JXLB_OK;
-  if (!any) {
-    finish_errors();
-    return overall;
-  }
+struct Batch {
   DeviceContext* ctx = nullptr;
-  try {
-    ctx = GetContext(device);
-  } catch (CudaError& e) {
-    for (auto& p : ps)
-      if (p.status == JXLB_OK) Fail(&p, JXLB_ERROR_NO_DEVICE, e.msg);
-    finish_errors();
-    return overall;
+  int api_level = 34;
+  size_t n = 0;
+  std::vector<Parsed> ps;
+  std::vector<uint32_t> frame_of;
+  std::vector<FrameDev> frames;
+  std::vector<StreamJob> jobs_single, jobs_lf, jobs_groups;
+  ScratchLayout sl_single{}, sl_lf{}, sl_grp{};
+  size_t const_total = 0, work_total = 0, stage_total = 0, final_total = 0, meta_total = 0;
+  uint32_t nframes = 0, status_total = 0;
+  std::vector<size_t> final_off, final_bytes;
+  const FrameDev* frames_d = nullptr;
+  const StreamJob* jobs_single_d = nullptr;
+  const StreamJob* jobs_lf_d = nullptr;
+  const StreamJob* jobs_groups_d = nullptr;
+  BatchBuffers own;           // buffers owned by this batch
+  BatchBuffers* buf = nullptr;
+  cudaEvent_t ev[10]{};
+  bool events = false;
+  bool uploaded = false, ran = false;
+  BatchTimings tm;
+
+  ~Batch() {
+    if (events)
+      for (auto& e : ev) cudaEventDestroy(e);
+    auto freed = [](DevBuffer& b) {
+      if (b.p) cudaFree(b.p);
+      b.p = nullptr;
+    };
+    auto freeh = [](PinnedBuffer& b) {
+      if (b.p) cudaFreeHost(b.p);
+      b.p = nullptr;
+    };
+    freed(own.const_buf);
+    freed(own.work_buf);
+    freed(own.scratch_buf);
+    freed(own.meta_buf);
+    freed(own.stage_out);
+    freed(own.final_out);
+    freeh(own.staging);
+    freeh(own.status_host);
   }
-  std::lock_guard<std::mutex> lock(ctx->mu);
-  try {
-    CUDA_OK(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
-    // ---- plan the batch buffers
-    size_t const_total = 0, work_total = 0, stage_total = 0;
-    uint32_t nframes = 0;
-    JobLists jobs;
-    std::vector<uint32_t> frame_of(n, 0);
-    size_t lf_scratch = 0, grp_scratch = 0;
+
+  // Host side: parse every request, lay out the batch.  No CUDA calls.
+  void Parse(const jxlb_request* reqs, size_t count, int api) {
+    n = count;
+    api_level = api <= 0 ? 34 : api;
+    ps.assign(n, Parsed());
+    for (size_t i = 0; i < n; ++i) ParseRequest(reqs[i], api_level, &ps[i]);
+    frame_of.assign(n, 0);
+    final_off.assign(n, 0);
+    final_bytes.assign(n, 0);
     for (size_t i = 0; i < n; ++i) {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
@@ -407,20 +410,24 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
       p.stage_stride = Align256((size_t) p.md.xsize * 4 * (p.out16 ? 2 : 1));
       p.stage_off = stage_total;
       stage_total += Align256(p.stage_stride * p.md.ysize);
+      final_bytes[i] = (size_t) p.md.xsize * FormatBytesPerPixel((uint32_t) p.format) * p.md.ysize;
+      final_off[i] = final_total;
+      final_total += Align256(final_bytes[i]);
       frame_of[i] = nframes++;
+      p.status_base = status_total;
+      status_total += p.plan.num_streams;
       const FrameDev& f = p.plan.proto;
       if (f.single_section) {
-        jobs.single.push_back(StreamJob{frame_of[i], 0, f.num_lf_groups + f.num_groups, 0});
+        jobs_single.push_back(StreamJob{frame_of[i], 0, f.num_lf_groups + f.num_groups, 0});
       } else {
         if (f.encoding == 0)
-          for (uint32_t l = 0; l < f.num_lf_groups; ++l) jobs.lf.push_back(StreamJob{frame_of[i], l, l, 0});
-        for (uint32_t g = 0; g < f.num_groups; ++g) jobs.groups.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, 0});
+          for (uint32_t l = 0; l < f.num_lf_groups; ++l) jobs_lf.push_back(StreamJob{frame_of[i], l, l, 0});
+        for (uint32_t g = 0; g < f.num_groups; ++g) jobs_groups.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, 0});
       }
     }
-    // scratch layouts
-    ScratchLayout sl_single{}, sl_lf{}, sl_grp{};
     auto job_bytes = [](const ScratchLayout& l) {
-      return Align256(l.arena_bytes) + Align256((size_t) l.wp_ints * 4) + 3 * 1024 + Align256(l.hf_arena_bytes) + (l.hf_arena_bytes ? 2 * 65536 * 4 : 0);
+      return Align256(l.arena_bytes) + Align256((size_t) l.wp_ints * 4) + 3 * 1024 + Align256(l.hf_arena_bytes) +
+             (l.hf_arena_bytes ? (size_t) 2 * 65536 * 4 : 0);
     };
     sl_single.arena_bytes = 1536u << 10;
     sl_single.wp_ints = WPState::ScratchInts(1024 + 8);
@@ -446,91 +453,105 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
     sl_grp.wp_ints = grp_modular ? WPState::ScratchInts(grp_dim + 8) : 0;
     sl_grp.max_local_nodes = 2048;
     sl_grp.bytes_per_job = Align256(job_bytes(sl_grp));
-    lf_scratch = sl_lf.bytes_per_job * jobs.lf.size();
-    grp_scratch = sl_grp.bytes_per_job * jobs.groups.size();
-    const size_t single_scratch = sl_single.bytes_per_job * jobs.single.size();
-    const size_t scratch_total = Align256(lf_scratch) + Align256(grp_scratch) + Align256(single_scratch);
-    const size_t njobs = jobs.single.size() + jobs.lf.size() + jobs.groups.size();
-    const size_t meta_total = Align256(nframes * sizeof(FrameDev)) + Align256(njobs * sizeof(StreamJob));
+    const size_t njobs = jobs_single.size() + jobs_lf.size() + jobs_groups.size();
+    meta_total = Align256(nframes * sizeof(FrameDev)) + Align256(njobs * sizeof(StreamJob));
+  }
 
-    ctx->const_buf.Ensure(const_total);
-    ctx->work_buf.Ensure(work_total);
-    ctx->scratch_buf.Ensure(scratch_total);
-    ctx->meta_buf.Ensure(meta_total);
-    ctx->stage_out.Ensure(stage_total);
-    ctx->staging.Ensure(const_total + meta_total);
-    uint32_t status_total = 0;
-    for (size_t i = 0; i < n; ++i)
-      if (ps[i].status == JXLB_OK) {
-        ps[i].status_base = status_total;
-        status_total += ps[i].plan.num_streams;
-      }
-    ctx->status_host.Ensure((size_t) status_total * 4 + 256);
+  bool AnyOk() const {
+    for (auto& p : ps)
+      if (p.status == JXLB_OK) return true;
+    return false;
+  }
 
-    CUDA_OK(cudaEventRecord(ctx->ev[0], s));
-    // ---- stage + upload
-    uint8_t* stg = ctx->staging.p;
-    std::vector<FrameDev> frames(nframes);
+  // Allocates (or reuses) device buffers, stages the const regions and uploads them.
+  void Upload(BatchBuffers* use) {
+    buf = use ? use : &own;
+    CUDA_OK(cudaSetDevice(ctx->device));
+    if (!events) {
+      for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+      events = true;
+    }
+    cudaStream_t s = ctx->stream;
+    const size_t lf_scratch = Align256(sl_lf.bytes_per_job * jobs_lf.size());
+    const size_t grp_scratch = Align256(sl_grp.bytes_per_job * jobs_groups.size());
+    const size_t single_scratch = Align256(sl_single.bytes_per_job * jobs_single.size());
+    buf->const_buf.Ensure(const_total);
+    buf->work_buf.Ensure(work_total);
+    buf->scratch_buf.Ensure(lf_scratch + grp_scratch + single_scratch);
+    buf->meta_buf.Ensure(meta_total);
+    buf->stage_out.Ensure(stage_total);
+    buf->final_out.Ensure(final_total);
+    buf->staging.Ensure(const_total + meta_total);
+    buf->status_host.Ensure((size_t) status_total * 4 + 256);
+    sl_lf.base = buf->scratch_buf.p;
+    sl_grp.base = buf->scratch_buf.p + lf_scratch;
+    sl_single.base = buf->scratch_buf.p + lf_scratch + grp_scratch;
+    CUDA_OK(cudaEventRecord(ev[0], s));
+    uint8_t* stg = buf->staging.p;
+    frames.assign(nframes, FrameDev());
     for (size_t i = 0; i < n; ++i) {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
       FillConstRegion(p.plan, p.cs.data(), p.fh, p.g, stg + p.const_off);
-      frames[frame_of[i]] = BindFrameDev(p.plan, ctx->const_buf.p + p.const_off, ctx->work_buf.p + p.work_off);
+      frames[frame_of[i]] = BindFrameDev(p.plan, buf->const_buf.p + p.const_off, buf->work_buf.p + p.work_off);
     }
     uint8_t* meta_h = stg + const_total;
     memcpy(meta_h, frames.data(), nframes * sizeof(FrameDev));
     StreamJob* jobs_h = reinterpret_cast<StreamJob*>(meta_h + Align256(nframes * sizeof(FrameDev)));
     size_t jo = 0;
-    memcpy(jobs_h + jo, jobs.single.data(), jobs.single.size() * sizeof(StreamJob));
-    const size_t single_o = jo;
-    jo += jobs.single.size();
-    memcpy(jobs_h + jo, jobs.lf.data(), jobs.lf.size() * sizeof(StreamJob));
-    const size_t lf_o = jo;
-    jo += jobs.lf.size();
-    memcpy(jobs_h + jo, jobs.groups.data(), jobs.groups.size() * sizeof(StreamJob));
-    const size_t grp_o = jo;
-    CUDA_OK(cudaMemcpyAsync(ctx->const_buf.p, stg, const_total, cudaMemcpyHostToDevice, s));
-    CUDA_OK(cudaMemcpyAsync(ctx->meta_buf.p, meta_h, meta_total, cudaMemcpyHostToDevice, s));
-    const FrameDev* frames_d = reinterpret_cast<const FrameDev*>(ctx->meta_buf.p);
-    const StreamJob* jobs_d = reinterpret_cast<const StreamJob*>(ctx->meta_buf.p + Align256(nframes * sizeof(FrameDev)));
-    // zero: coefficient planes (the AC decoder scatters only non-zeros) and the status words
+    auto put = [&](const std::vector<StreamJob>& v) {
+      size_t o = jo;
+      if (!v.empty()) memcpy(jobs_h + jo, v.data(), v.size() * sizeof(StreamJob));
+      jo += v.size();
+      return o;
+    };
+    const size_t so = put(jobs_single), lo = put(jobs_lf), go = put(jobs_groups);
+    CUDA_OK(cudaMemcpyAsync(buf->const_buf.p, stg, const_total, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(buf->meta_buf.p, meta_h, meta_total, cudaMemcpyHostToDevice, s));
+    frames_d = reinterpret_cast<const FrameDev*>(buf->meta_buf.p);
+    const StreamJob* jd = reinterpret_cast<const StreamJob*>(buf->meta_buf.p + Align256(nframes * sizeof(FrameDev)));
+    jobs_single_d = jd + so;
+    jobs_lf_d = jd + lo;
+    jobs_groups_d = jd + go;
+    CUDA_OK(cudaEventRecord(ev[1], s));
+    uploaded = true;
+  }
+
+  // All kernels, from the uploaded codestreams to packed pixels in HBM.  Asynchronous on ctx->stream.
+  void Run() {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    CUDA_OK(cudaEventRecord(ev[2], s));
     for (size_t i = 0; i < n; ++i) {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
-      uint8_t* wb = ctx->work_buf.p + p.work_off;
+      uint8_t* wb = buf->work_buf.p + p.work_off;
       CUDA_OK(cudaMemsetAsync(wb + p.plan.off_status, 0xFF, (size_t) p.plan.num_streams * 4, s));
       if (p.plan.coef_bytes) CUDA_OK(cudaMemsetAsync(wb + p.plan.off_coef, 0, p.plan.coef_bytes, s));
     }
-    CUDA_OK(cudaEventRecord(ctx->ev[1], s));
-    // ---- entropy-coded sections
-    uint8_t* sc = ctx->scratch_buf.p;
-    sl_lf.base = sc;
-    sl_grp.base = sc + Align256(lf_scratch);
-    sl_single.base = sc + Align256(lf_scratch) + Align256(grp_scratch);
-    LaunchSingleSectionFrames(frames_d, jobs_d + single_o, (uint32_t) jobs.single.size(), ctx->nat_dev, sl_single, s);
-    LaunchLfGroups(frames_d, jobs_d + lf_o, (uint32_t) jobs.lf.size(), sl_lf, s);
-    LaunchPassGroups(frames_d, jobs_d + grp_o, (uint32_t) jobs.groups.size(), ctx->nat_dev, sl_grp, s);
-    CUDA_OK(cudaEventRecord(ctx->ev[2], s));
-    // ---- reconstruction
+    LaunchSingleSectionFrames(frames_d, jobs_single_d, (uint32_t) jobs_single.size(), ctx->nat_dev, sl_single, s);
+    LaunchLfGroups(frames_d, jobs_lf_d, (uint32_t) jobs_lf.size(), sl_lf, s);
+    CUDA_OK(cudaEventRecord(ev[3], s));
+    LaunchPassGroups(frames_d, jobs_groups_d, (uint32_t) jobs_groups.size(), ctx->nat_dev, sl_grp, s);
+    CUDA_OK(cudaEventRecord(ev[4], s));
     for (size_t i = 0; i < n; ++i) {
-      Parsed& p = ps[i];
-      if (p.status != JXLB_OK) continue;
+      if (ps[i].status != JXLB_OK) continue;
       const FrameDev& f = frames[frame_of[i]];
-      if (f.encoding == 0) {
-        LaunchLfFinal(f, s);
-        LaunchRecon(f, ctx->nt_dev, s);
-      }
+      if (f.encoding == 0) LaunchLfFinal(f, s);
     }
-    CUDA_OK(cudaEventRecord(ctx->ev[3], s));
-    // ---- filters, colour, pack
-    std::vector<uint8_t*> final_dev(n, nullptr);
-    std::vector<size_t> final_bytes(n, 0);
+    CUDA_OK(cudaEventRecord(ev[5], s));
+    for (size_t i = 0; i < n; ++i) {
+      if (ps[i].status != JXLB_OK) continue;
+      const FrameDev& f = frames[frame_of[i]];
+      if (f.encoding == 0) LaunchRecon(f, ctx->nt_dev, s);
+    }
+    CUDA_OK(cudaEventRecord(ev[6], s));
     for (size_t i = 0; i < n; ++i) {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
       const FrameDev& f = frames[frame_of[i]];
       OutputDesc od;
-      od.data = ctx->stage_out.p + p.stage_off;
+      od.data = buf->stage_out.p + p.stage_off;
       od.stride_bytes = (uint32_t) p.stage_stride;
       od.bits16 = p.out16;
       od.alpha_channel = -1;
@@ -547,8 +568,7 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
       } else {
         LaunchModularToRgba(f, od, s);
       }
-      // ReformatColorConfig
-      PackParams pk;
+      PackParams pk;  // ReformatColorConfig
       pk.src = od.data;
       pk.src_stride = od.stride_bytes;
       pk.width = p.md.xsize;
@@ -559,55 +579,83 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
       pk.associate = (!p.alpha_premultiplied && p.has_alpha) ? 1 : 0;
       pk.attenuate = !p.alpha_premultiplied ? 1 : 0;
       pk.dst_stride = pk.width * FormatBytesPerPixel(pk.format);
-      final_bytes[i] = (size_t) pk.dst_stride * pk.height;
-      uint8_t* dst = nullptr;
-      CUDA_OK(cudaMalloc(&dst, final_bytes[i]));
-      final_dev[i] = dst;
-      pk.dst = dst;
+      pk.dst = buf->final_out.p + final_off[i];
       LaunchPack(pk, s);
     }
-    CUDA_OK(cudaEventRecord(ctx->ev[4], s));
-    // ---- statuses + results
-    {
-      uint32_t* sh = reinterpret_cast<uint32_t*>(ctx->status_host.p);
-      for (size_t i = 0; i < n; ++i) {
-        Parsed& p = ps[i];
-        if (p.status != JXLB_OK) continue;
-        CUDA_OK(cudaMemcpyAsync(sh + p.status_base, ctx->work_buf.p + p.work_off + p.plan.off_status, (size_t) p.plan.num_streams * 4,
-                                cudaMemcpyDeviceToHost, s));
-      }
+    CUDA_OK(cudaEventRecord(ev[7], s));
+    ran = true;
+  }
+
+  // Downloads the per-stream statuses (and, if host_out, the pixels), synchronises and resolves per-image status.
+  void Finish(bool to_host, int output_device, std::vector<DecodedImage>* out) {
+    cudaStream_t s = ctx->stream;
+    uint32_t* sh = reinterpret_cast<uint32_t*>(buf->status_host.p);
+    for (size_t i = 0; i < n; ++i) {
+      Parsed& p = ps[i];
+      if (p.status != JXLB_OK) continue;
+      CUDA_OK(cudaMemcpyAsync(sh + p.status_base, buf->work_buf.p + p.work_off + p.plan.off_status, (size_t) p.plan.num_streams * 4,
+                              cudaMemcpyDeviceToHost, s));
     }
-    std::vector<void*> host_out(n, nullptr);
-    if (output_device < 0) {
-      for (size_t i = 0; i < n; ++i) {
-        if (ps[i].status != JXLB_OK) continue;
-        host_out[i] = Pool().Get(final_bytes[i]);
-        if (!host_out[i]) {
+    std::vector<void*> result(n, nullptr);
+    for (size_t i = 0; i < n && out; ++i) {
+      if (ps[i].status != JXLB_OK) continue;
+      if (to_host) {
+        result[i] = Pool().Get(final_bytes[i]);
+        if (!result[i]) {
           Fail(&ps[i], JXLB_OOM, "Not enough memory to decode this image");
           continue;
         }
-        CUDA_OK(cudaMemcpyAsync(host_out[i], final_dev[i], final_bytes[i], cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaMemcpyAsync(result[i], buf->final_out.p + final_off[i], final_bytes[i], cudaMemcpyDeviceToHost, s));
+      } else {
+        void* d = nullptr;
+        if (cudaMalloc(&d, final_bytes[i]) != cudaSuccess) {
+          Fail(&ps[i], JXLB_OOM, "Not enough memory to decode this image");
+          cudaGetLastError();
+          continue;
+        }
+        result[i] = d;
+        CUDA_OK(cudaMemcpyAsync(d, buf->final_out.p + final_off[i], final_bytes[i], cudaMemcpyDeviceToDevice, s));
       }
     }
-    CUDA_OK(cudaEventRecord(ctx->ev[5], s));
+    CUDA_OK(cudaEventRecord(ev[8], s));
     CUDA_OK(cudaStreamSynchronize(s));
-    if (timings) {
-      for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&timings->ms[k], ctx->ev[k], ctx->ev[k + 1]);
-      cudaEventElapsedTime(&timings->ms[5], ctx->ev[0], ctx->ev[5]);
-    }
-    // ---- per-image status from the stream statuses
-    const int32_t* sh = reinterpret_cast<const int32_t*>(ctx->status_host.p);
+    // ms: [0] upload, [1] LF sections, [2] group sections, [3] LF final, [4] inverse transforms, [5] filters+colour+pack, [6] download
+    auto el = [&](int a, int b) {
+      float v = 0;
+      cudaEventElapsedTime(&v, ev[a], ev[b]);
+      return v;
+    };
+    tm.ms[0] = el(0, 1);
+    tm.ms[1] = el(2, 4);
+    tm.ms[2] = el(4, 6);
+    tm.ms[3] = el(6, 7);
+    tm.ms[4] = el(7, 8);
+    tm.ms[5] = el(2, 8);
+    stage_ms[0] = el(0, 1);
+    stage_ms[1] = el(2, 3);
+    stage_ms[2] = el(3, 4);
+    stage_ms[3] = el(4, 5);
+    stage_ms[4] = el(5, 6);
+    stage_ms[5] = el(6, 7);
+    stage_ms[6] = el(7, 8);
+    stage_ms[7] = el(2, 7);
+    const int32_t* shs = reinterpret_cast<const int32_t*>(buf->status_host.p);
     for (size_t i = 0; i < n; ++i) {
       Parsed& p = ps[i];
+      auto drop = [&]() {
+        if (!result[i]) return;
+        if (to_host) Pool().Put(result[i]);
+        else cudaFree(result[i]);
+        result[i] = nullptr;
+      };
       if (p.status != JXLB_OK) {
-        if (final_dev[i]) cudaFree(final_dev[i]);
-        if (host_out[i]) Pool().Put(host_out[i]);
+        drop();
         continue;
       }
       const FrameDev& f = p.plan.proto;
       int worst = kOk;
       auto check = [&](uint32_t slot) {
-        int v = sh[p.status_base + slot];
+        int v = shs[p.status_base + slot];
         if (v == -1) v = kErrBadStream;  // never written
         if (v != kOk && worst == kOk) worst = v;
       };
@@ -619,12 +667,14 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
         for (uint32_t g = 0; g < f.num_groups; ++g) check(f.num_lf_groups + g);
       }
       if (worst != kOk) {
-        if (worst == kErrUnsupported || worst == kErrScratch) Fail(&p, JXLB_UNSUPPORTED, "coding tool or stream size outside this build's coverage");
-        else Fail(&p, JXLB_INVALID_JXL, worst == kErrTruncated ? "truncated section" : "corrupt section");
-        if (final_dev[i]) cudaFree(final_dev[i]);
-        if (host_out[i]) Pool().Put(host_out[i]);
+        if (worst == kErrUnsupported || worst == kErrScratch)
+          Fail(&p, JXLB_UNSUPPORTED, "coding tool or stream size outside this build's coverage");
+        else
+          Fail(&p, JXLB_INVALID_JXL, worst == kErrTruncated ? "truncated section" : "corrupt section");
+        drop();
         continue;
       }
+      if (!out) continue;
       DecodedImage& d = (*out)[i];
       d.width = p.md.xsize;
       d.height = p.md.ysize;
@@ -632,22 +682,148 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
       d.format = p.format;
       d.color_space = p.color_space;
       d.premultiplied = p.has_alpha ? 1 : 0;
-      if (output_device < 0) {
-        d.data = host_out[i];
-        d.device = -1;
-        cudaFree(final_dev[i]);
-      } else {
-        d.data = final_dev[i];
-        d.device = ctx->device;
-      }
+      d.data = result[i];
+      d.device = to_host ? -1 : ctx->device;
+      (void) output_device;
     }
+  }
+
+  float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+void FreeImageMemory(void* data, int device) {
+  if (!data) return;
+  if (device < 0) {
+    if (!Pool().Put(data)) cudaFreeHost(data);
+  } else {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    cudaFree(data);
+    cudaSetDevice(cur);
+  }
+}
+
+namespace {
+BatchBuffers* SpareBuffers(DeviceContext* ctx) {
+  static std::map<DeviceContext*, std::unique_ptr<BatchBuffers>> spare;
+  auto& b = spare[ctx];
+  if (!b) b.reset(new BatchBuffers());
+  return b.get();
+}
+void CopyStatuses(const Batch& b, std::vector<DecodedImage>* out, int* overall) {
+  for (size_t i = 0; i < b.n; ++i) {
+    (*out)[i].status = b.ps[i].status;
+    (*out)[i].message = b.ps[i].message;
+    if (b.ps[i].status != JXLB_OK) *overall = b.ps[i].status;
+  }
+}
+}  // namespace
+
+int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device, std::vector<DecodedImage>* out,
+                BatchTimings* timings) {
+  out->assign(n, DecodedImage());
+  Batch b;
+  b.Parse(reqs, n, api_level);
+  int overall = JXLB_OK;
+  if (!b.AnyOk()) {
+    CopyStatuses(b, out, &overall);
+    return overall;
+  }
+  try {
+    b.ctx = GetContext(device);
   } catch (CudaError& e) {
-    for (auto& p : ps)
+    for (auto& p : b.ps)
+      if (p.status == JXLB_OK) Fail(&p, JXLB_ERROR_NO_DEVICE, e.msg);
+    CopyStatuses(b, out, &overall);
+    return overall;
+  }
+  std::lock_guard<std::mutex> lock(b.ctx->mu);
+  try {
+    b.Upload(SpareBuffers(b.ctx));
+    b.Run();
+    b.Finish(output_device < 0, output_device, out);
+    if (timings) *timings = b.tm;
+  } catch (CudaError& e) {
+    for (auto& p : b.ps)
       if (p.status == JXLB_OK) Fail(&p, JXLB_ERROR_NO_DEVICE, e.msg);
     cudaGetLastError();
   }
-  finish_errors();
+  CopyStatuses(b, out, &overall);
   return overall;
 }
+
+// ---- prepared batches (throughput interface: inputs resident in HBM, results left in HBM) --------------------------------
+Batch* PrepareBatch(const jxlb_request* reqs, size_t n, int api_level, int device, std::vector<int>* status) {
+  std::unique_ptr<Batch> b(new Batch());
+  b->Parse(reqs, n, api_level);
+  status->assign(n, 0);
+  try {
+    b->ctx = GetContext(device);
+    std::lock_guard<std::mutex> lock(b->ctx->mu);
+    if (b->AnyOk()) {
+      b->Upload(nullptr);
+      CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+    }
+  } catch (CudaError& e) {
+    for (auto& p : b->ps)
+      if (p.status == JXLB_OK) Fail(&p, JXLB_ERROR_NO_DEVICE, e.msg);
+    cudaGetLastError();
+  }
+  for (size_t i = 0; i < n; ++i) (*status)[i] = b->ps[i].status;
+  return b.release();
+}
+
+int RunBatch(Batch* b, bool sync) {
+  if (!b || !b->uploaded) return JXLB_ERROR;
+  std::lock_guard<std::mutex> lock(b->ctx->mu);
+  try {
+    b->Run();
+    if (sync) b->Finish(false, 0, nullptr);
+  } catch (CudaError& e) {
+    cudaGetLastError();
+    return JXLB_ERROR_NO_DEVICE;
+  }
+  for (auto& p : b->ps)
+    if (p.status != JXLB_OK) return p.status;
+  return JXLB_OK;
+}
+
+int FetchBatchImage(Batch* b, size_t i, DecodedImage* out) {
+  if (!b || i >= b->n || !b->ran) return JXLB_BAD_ARG;
+  const Parsed& p = b->ps[i];
+  out->status = p.status;
+  out->message = p.message;
+  if (p.status != JXLB_OK) return p.status;
+  std::lock_guard<std::mutex> lock(b->ctx->mu);
+  void* h = Pool().Get(b->final_bytes[i]);
+  if (!h) return JXLB_OOM;
+  cudaSetDevice(b->ctx->device);
+  if (cudaMemcpyAsync(h, b->buf->final_out.p + b->final_off[i], b->final_bytes[i], cudaMemcpyDeviceToHost, b->ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(b->ctx->stream) != cudaSuccess) {
+    Pool().Put(h);
+    return JXLB_ERROR_NO_DEVICE;
+  }
+  out->data = h;
+  out->device = -1;
+  out->width = p.md.xsize;
+  out->height = p.md.ysize;
+  out->stride_bytes = p.md.xsize * FormatBytesPerPixel((uint32_t) p.format);
+  out->format = p.format;
+  out->color_space = p.color_space;
+  out->premultiplied = p.has_alpha ? 1 : 0;
+  return JXLB_OK;
+}
+
+void BatchStageMs(const Batch* b, float* ms8) {
+  for (int i = 0; i < 8; ++i) ms8[i] = b ? b->stage_ms[i] : 0.f;
+}
+const void* BatchDevicePixels(const Batch* b, size_t i, size_t* bytes) {
+  if (!b || i >= b->n || b->ps[i].status != JXLB_OK) return nullptr;
+  if (bytes) *bytes = b->final_bytes[i];
+  return b->buf->final_out.p + b->final_off[i];
+}
+cudaStream_t BatchStream(const Batch* b) { return b->ctx->stream; }
+void FreeBatch(Batch* b) { delete b; }
 
 }  // namespace jxlb

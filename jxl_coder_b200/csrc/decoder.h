@@ -30,3 +30,19 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
 void FreeImageMemory(void* data, int device);
 
 }  // namespace jxlb
+
+// ---- prepared batches: parse + upload once ("inputs resident in HBM"), then run the kernels any number of times with
+// the results left in HBM.  Used by the benchmark's device-resident measurement and by callers that keep pixels on the GPU.
+#include <cuda_runtime.h>
+namespace jxlb {
+struct Batch;
+Batch* PrepareBatch(const jxlb_request* reqs, size_t n, int api_level, int device, std::vector<int>* status);
+int RunBatch(Batch* b, bool sync);
+int FetchBatchImage(Batch* b, size_t i, DecodedImage* out);
+// ms8: [0] upload, [1] LF sections, [2] group sections, [3] LF dequant+smoothing, [4] dequant+inverse transforms,
+//      [5] filters+colour+pack, [6] download, [7] all kernels
+void BatchStageMs(const Batch* b, float* ms8);
+const void* BatchDevicePixels(const Batch* b, size_t i, size_t* bytes);
+cudaStream_t BatchStream(const Batch* b);
+void FreeBatch(Batch* b);
+}  // namespace jxlb
