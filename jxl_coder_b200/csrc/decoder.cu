@@ -38,6 +38,7 @@ struct CudaError {
 };
 
 size_t Align256(size_t v) { return (v + 255) & ~(size_t) 255; }
+constexpr uint32_t kMaxAcSmemCode = 208u << 10;  // AC code blobs up to this size are staged in shared memory
 
 struct DevBuffer {
   uint8_t* p = nullptr;
@@ -354,7 +355,10 @@ struct Batch {
   std::vector<Parsed> ps;
   std::vector<uint32_t> frame_of;
   std::vector<FrameDev> frames;
-  std::vector<StreamJob> jobs_single, jobs_lf, jobs_groups;
+  std::vector<StreamJob> jobs_single, jobs_lf, jobs_groups;   // jobs_groups: groups decoded by the one-warp-per-section kernel
+  std::vector<StreamJob> jobs_lane_groups, jobs_lane_mod;     // groups taken by the lane-parallel AC kernel (+ their modular tails)
+  std::vector<AcCtaJob> jobs_ac_cta;
+  uint32_t ac_smem_code_bytes = 0;
   ScratchLayout sl_single{}, sl_lf{}, sl_grp{};
   size_t const_total = 0, work_total = 0, stage_total = 0, final_total = 0, meta_total = 0;
   uint32_t nframes = 0, status_total = 0;
@@ -363,6 +367,9 @@ struct Batch {
   const StreamJob* jobs_single_d = nullptr;
   const StreamJob* jobs_lf_d = nullptr;
   const StreamJob* jobs_groups_d = nullptr;
+  const StreamJob* jobs_lane_groups_d = nullptr;
+  const StreamJob* jobs_lane_mod_d = nullptr;
+  const AcCtaJob* jobs_ac_cta_d = nullptr;
   BatchBuffers own;           // buffers owned by this batch
   BatchBuffers* buf = nullptr;
   cudaEvent_t ev[10]{};
@@ -422,7 +429,22 @@ struct Batch {
       } else {
         if (f.encoding == 0)
           for (uint32_t l = 0; l < f.num_lf_groups; ++l) jobs_lf.push_back(StreamJob{frame_of[i], l, l, 0});
-        for (uint32_t g = 0; g < f.num_groups; ++g) jobs_groups.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, 0});
+        // lane-parallel AC decode unless the AC code needs an LZ77 window or does not fit shared memory
+        bool lane = false;
+        if (f.encoding == 0 && !p.g.ac_code.empty()) {
+          const CodeHeader* chh = reinterpret_cast<const CodeHeader*>(p.g.ac_code.data());
+          lane = !chh->lz77 && chh->total_bytes <= kMaxAcSmemCode && getenv("JXLB_NO_LANE_AC") == nullptr;
+          if (lane) ac_smem_code_bytes = std::max(ac_smem_code_bytes, chh->total_bytes);
+        }
+        if (lane) {
+          for (uint32_t g = 0; g < f.num_groups; ++g) jobs_lane_groups.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, 0});
+          for (uint32_t g0 = 0; g0 < f.num_groups; g0 += 128)
+            jobs_ac_cta.push_back(AcCtaJob{frame_of[i], g0, std::min(128u, f.num_groups - g0), 0});
+          if (f.num_mod_channels > f.global_mod_decoded)
+            for (uint32_t g = 0; g < f.num_groups; ++g) jobs_lane_mod.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, 0});
+        } else {
+          for (uint32_t g = 0; g < f.num_groups; ++g) jobs_groups.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, 0});
+        }
       }
     }
     auto job_bytes = [](const ScratchLayout& l) {
@@ -430,12 +452,12 @@ struct Batch {
              (l.hf_arena_bytes ? (size_t) 2 * 65536 * 4 : 0);
     };
     sl_single.arena_bytes = 1536u << 10;
-    sl_single.wp_ints = WPState::ScratchInts(1024 + 8);
+    sl_single.wp_ints = ModFastScratch::Ints(1024 + 8);
     sl_single.hf_arena_bytes = 2048u << 10;
     sl_single.max_local_nodes = 32768;
     sl_single.bytes_per_job = Align256(job_bytes(sl_single));
     sl_lf.arena_bytes = 1536u << 10;
-    sl_lf.wp_ints = WPState::ScratchInts(kLfGroupCells + 8);
+    sl_lf.wp_ints = ModFastScratch::Ints(kLfGroupCells * kLfGroupCells + 8);  // BlockInfo channel: up to one entry per cell
     sl_lf.max_local_nodes = 32768;
     sl_lf.bytes_per_job = Align256(job_bytes(sl_lf));
     bool grp_modular = false, grp_local_tree = false;
@@ -450,10 +472,11 @@ struct Batch {
       }
     }
     sl_grp.arena_bytes = grp_modular ? (grp_local_tree ? (192u << 10) : (16u << 10)) : 0;
-    sl_grp.wp_ints = grp_modular ? WPState::ScratchInts(grp_dim + 8) : 0;
+    sl_grp.wp_ints = grp_modular ? ModFastScratch::Ints(grp_dim + 8) : 0;
     sl_grp.max_local_nodes = 2048;
     sl_grp.bytes_per_job = Align256(job_bytes(sl_grp));
-    const size_t njobs = jobs_single.size() + jobs_lf.size() + jobs_groups.size();
+    const size_t njobs = jobs_single.size() + jobs_lf.size() + jobs_groups.size() + jobs_lane_groups.size() + jobs_lane_mod.size() +
+                         jobs_ac_cta.size();  // AcCtaJob has the same size as StreamJob
     meta_total = Align256(nframes * sizeof(FrameDev)) + Align256(njobs * sizeof(StreamJob));
   }
 
@@ -473,7 +496,7 @@ struct Batch {
     }
     cudaStream_t s = ctx->stream;
     const size_t lf_scratch = Align256(sl_lf.bytes_per_job * jobs_lf.size());
-    const size_t grp_scratch = Align256(sl_grp.bytes_per_job * jobs_groups.size());
+    const size_t grp_scratch = Align256(sl_grp.bytes_per_job * std::max(jobs_groups.size(), jobs_lane_mod.size()));
     const size_t single_scratch = Align256(sl_single.bytes_per_job * jobs_single.size());
     buf->const_buf.Ensure(const_total);
     buf->work_buf.Ensure(work_total);
@@ -505,7 +528,10 @@ struct Batch {
       jo += v.size();
       return o;
     };
-    const size_t so = put(jobs_single), lo = put(jobs_lf), go = put(jobs_groups);
+    const size_t so = put(jobs_single), lo = put(jobs_lf), go = put(jobs_groups), lgo = put(jobs_lane_groups), lmo = put(jobs_lane_mod);
+    const size_t aco = jo;
+    if (!jobs_ac_cta.empty()) memcpy(jobs_h + jo, jobs_ac_cta.data(), jobs_ac_cta.size() * sizeof(AcCtaJob));
+    jo += jobs_ac_cta.size();
     CUDA_OK(cudaMemcpyAsync(buf->const_buf.p, stg, const_total, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(buf->meta_buf.p, meta_h, meta_total, cudaMemcpyHostToDevice, s));
     frames_d = reinterpret_cast<const FrameDev*>(buf->meta_buf.p);
@@ -513,6 +539,9 @@ struct Batch {
     jobs_single_d = jd + so;
     jobs_lf_d = jd + lo;
     jobs_groups_d = jd + go;
+    jobs_lane_groups_d = jd + lgo;
+    jobs_lane_mod_d = jd + lmo;
+    jobs_ac_cta_d = reinterpret_cast<const AcCtaJob*>(jd + aco);
     CUDA_OK(cudaEventRecord(ev[1], s));
     uploaded = true;
   }
@@ -533,6 +562,9 @@ struct Batch {
     LaunchLfGroups(frames_d, jobs_lf_d, (uint32_t) jobs_lf.size(), sl_lf, s);
     CUDA_OK(cudaEventRecord(ev[3], s));
     LaunchPassGroups(frames_d, jobs_groups_d, (uint32_t) jobs_groups.size(), ctx->nat_dev, sl_grp, s);
+    LaunchBuildGroupBlocks(frames_d, jobs_lane_groups_d, (uint32_t) jobs_lane_groups.size(), s);
+    LaunchAcLanes(frames_d, jobs_ac_cta_d, (uint32_t) jobs_ac_cta.size(), ctx->nat_dev, ac_smem_code_bytes, s);
+    LaunchGroupModular(frames_d, jobs_lane_mod_d, (uint32_t) jobs_lane_mod.size(), sl_grp, s);
     CUDA_OK(cudaEventRecord(ev[4], s));
     for (size_t i = 0; i < n; ++i) {
       if (ps[i].status != JXLB_OK) continue;

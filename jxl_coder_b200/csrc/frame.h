@@ -149,6 +149,10 @@ struct FrameDev {
   uint16_t* cell_hfmul;            // [h8][w8]: hf_mul of the covering block
   uint8_t* cell_sharp;             // [h8][w8]
   uint16_t* cell_off;              // [h8][w8]: (dy << 8) | dx offset of the cell from its block's top-left cell
+  uint32_t* group_blocks;          // [num_groups][1024]: blocks of each group in raster order of their top-left cell:
+                                   //   bx | by << 5 | strategy << 10 | (hf_mul - 1) << 16   (bx, by relative to the group)
+  uint32_t* group_nblocks;         // [num_groups]
+  uint64_t* group_ac_end_bit;      // [num_groups]: bit position after the AC data (start of the group's modular data)
   int16_t* coef;                   // [3][coef_h][coef_stride] quantised coefficients (X, Y, B), block-rectangle layout
   uint32_t coef_stride, coef_h;
   float* lf;                       // [3][h8][lf_stride] dequantised (X, Y, B)

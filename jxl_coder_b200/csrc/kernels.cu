@@ -105,13 +105,27 @@ __global__ void __launch_bounds__(kReconThreads) ReconRegionKernel(const FrameDe
   ReconRegion(f, *nt, blockIdx.x, blockIdx.y, sh, (int) threadIdx.x, (int) blockDim.x, SyncThreads());
 }
 
-// One CTA per 8x8 cell; only top-left cells of blocks that are not contained in a 64x64 region do work.
+// One CTA per 64x64 region; it reconstructs the blocks whose top-left cell lies in the region but which are not
+// contained in it (larger than 64 pixels, or straddling a region border) -- rare, so most CTAs exit after the scan.
 __global__ void __launch_bounds__(256) ReconLargeKernel(const FrameDev f, const NumericTables* nt) {
-  const uint32_t bx = blockIdx.x, by = blockIdx.y;
-  const uint8_t s = f.cell_strategy[(size_t) by * f.w8 + bx];
-  if (!(s & 0x80) || s == 0xFF) return;
-  if (!BlockNeedsLargePath(s & 0x7Fu, bx, by)) return;
-  ReconLargeBlock(f, *nt, bx, by, (int) threadIdx.x, (int) blockDim.x, SyncThreads());
+  __shared__ uint32_t todo[64];
+  __shared__ uint32_t ntodo;
+  if (threadIdx.x == 0) ntodo = 0;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const uint32_t bx = blockIdx.x * kRegionCells + (threadIdx.x & 7), by = blockIdx.y * kRegionCells + (threadIdx.x >> 3);
+    if (bx < f.w8 && by < f.h8) {
+      const uint8_t s = f.cell_strategy[(size_t) by * f.w8 + bx];
+      if ((s & 0x80) && s != 0xFF && BlockNeedsLargePath(s & 0x7Fu, bx, by)) todo[atomicAdd(&ntodo, 1u)] = bx | (by << 16);
+    }
+  }
+  __syncthreads();
+  const uint32_t n = ntodo;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t e = todo[i];
+    ReconLargeBlock(f, *nt, e & 0xFFFF, e >> 16, (int) threadIdx.x, (int) blockDim.x, SyncThreads());
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(256) GaborishKernel(const FrameDev f, const float* src, float* dst) {
@@ -155,7 +169,8 @@ void LaunchPack(const PackParams& p, cudaStream_t stream) {
   ++g_launches;
 }
 
-uint64_t KernelLaunchCount() { return g_launches.load(); }
+extern std::atomic<uint64_t> g_launches_ac;
+uint64_t KernelLaunchCount() { return g_launches.load() + g_launches_ac.load(); }
 
 void LaunchSingleSectionFrames(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat,
                                ScratchLayout scratch, cudaStream_t stream) {
@@ -188,7 +203,7 @@ void LaunchRecon(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t st
   }
   dim3 grid((f.w8 + kRegionCells - 1) / kRegionCells, (f.h8 + kRegionCells - 1) / kRegionCells, 1);
   ReconRegionKernel<<<grid, kReconThreads, sizeof(RegionShared), stream>>>(f, nt_dev);
-  ReconLargeKernel<<<dim3(f.w8, f.h8, 1), 256, 0, stream>>>(f, nt_dev);
+  ReconLargeKernel<<<grid, 256, 0, stream>>>(f, nt_dev);
   g_launches += 2;
 }
 

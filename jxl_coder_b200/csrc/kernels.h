@@ -34,6 +34,19 @@ void LaunchLfGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njob
 void LaunchPassGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat, ScratchLayout scratch,
                       cudaStream_t stream);
 
+// Lane-parallel AC decode (kernels_ac.cu): a CTA of 128 lanes decodes up to 128 groups of ONE frame.
+struct AcCtaJob {
+  uint32_t frame;
+  uint32_t first_group;
+  uint32_t ngroups;
+  uint32_t pad;
+};
+void LaunchBuildGroupBlocks(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, cudaStream_t stream);
+uint32_t AcLaneSmemBytes(uint32_t code_bytes);
+void LaunchAcLanes(const FrameDev* frames, const AcCtaJob* jobs, uint32_t njobs, NaturalOrders nat, uint32_t smem_code_bytes,
+                   cudaStream_t stream);
+void LaunchGroupModular(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, ScratchLayout scratch, cudaStream_t stream);
+
 // Numeric stages of one VarDCT frame (FrameDev passed by value).
 void LaunchLfFinal(const FrameDev& f, cudaStream_t stream);
 void LaunchRecon(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t stream);

@@ -105,6 +105,9 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
     p.off_cell_hfmul = take((size_t) f.h8 * f.w8 * 2);
     p.off_cell_sharp = take((size_t) f.h8 * f.w8);
     p.off_cell_off = take((size_t) f.h8 * f.w8 * 2);
+    p.off_group_blocks = take((size_t) fh.num_groups * 1024 * 4);
+    p.off_group_nblocks = take((size_t) fh.num_groups * 4);
+    p.off_group_ac_end = take((size_t) fh.num_groups * 8);
     p.coef_bytes = (size_t) 3 * f.coef_h * f.coef_stride * 2;
     p.off_coef = take(p.coef_bytes);
     p.off_lf = take((size_t) 3 * f.h8 * f.lf_stride * 4);
@@ -159,6 +162,9 @@ FrameDev BindFrameDev(const FramePlan& p, const uint8_t* cb, uint8_t* wb) {
     f.cell_hfmul = reinterpret_cast<uint16_t*>(wb + p.off_cell_hfmul);
     f.cell_sharp = wb + p.off_cell_sharp;
     f.cell_off = reinterpret_cast<uint16_t*>(wb + p.off_cell_off);
+    f.group_blocks = reinterpret_cast<uint32_t*>(wb + p.off_group_blocks);
+    f.group_nblocks = reinterpret_cast<uint32_t*>(wb + p.off_group_nblocks);
+    f.group_ac_end_bit = reinterpret_cast<uint64_t*>(wb + p.off_group_ac_end);
     f.coef = reinterpret_cast<int16_t*>(wb + p.off_coef);
     f.lf = reinterpret_cast<float*>(wb + p.off_lf);
     f.xyb0 = reinterpret_cast<float*>(wb + p.off_xyb0);

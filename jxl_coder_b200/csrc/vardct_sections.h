@@ -6,6 +6,7 @@
 // (/root/reference/jxlcoder/src/main/cpp/interop/JxlDecoding.cpp:74-175).  Format digest: SURVEY.md App. B.5-B.7.
 #pragma once
 #include "frame.h"
+#include "modular_fast.h"
 
 namespace jxlb {
 
@@ -88,7 +89,7 @@ JXLB_HD_NOINLINE int ParseHfGlobal(BitReader& br, uint32_t num_groups, uint32_t 
 // ---- helpers shared by the section decoders ---------------------------------------------------------------------------
 struct StreamScratch {
   Arena arena;             // local trees / codes
-  int32_t* wp;             // WPState::ScratchInts(max channel width) ints
+  int32_t* wp;             // ModFastScratch::Ints(max channel width) ints
   uint32_t* lz77;          // optional LZ77 window (power-of-two entries) or nullptr
   uint32_t lz77_mask;
   uint8_t* nzmap;          // 3 * 32 * 32 bytes for the AC non-zero context map
@@ -182,7 +183,7 @@ JXLB_HD_NOINLINE int DecodeLfGroupSection(BitReader& br, const FrameDev& f, uint
     ch[c].h = h8;
     ch[c].stride = f.lf_stride;
   }
-  st = DecodeModularChannels(br, mc, mh.wp, ch, 3, 1 + lfg, s.wp, s.lz77, s.lz77_mask);
+  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, 3, 1 + lfg, s.wp, s.lz77, s.lz77_mask);
   if (st != kOk) return st;
   ApplyInverseRcts(mh, ch, 3);
   s.arena.used = arena_mark;
@@ -209,7 +210,7 @@ JXLB_HD_NOINLINE int DecodeLfGroupSection(BitReader& br, const FrameDev& f, uint
   ch[3].w = w8;
   ch[3].h = h8;
   ch[3].stride = f.lf_stride;
-  st = DecodeModularChannels(br, mc, mh.wp, ch, 4, 1 + 2 * nlf + lfg, s.wp, s.lz77, s.lz77_mask);
+  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, 4, 1 + 2 * nlf + lfg, s.wp, s.lz77, s.lz77_mask);
   if (st != kOk) return st;
   if (mh.nb_transforms) return kErrUnsupported;
   s.arena.used = arena_mark;
@@ -269,7 +270,8 @@ JXLB_HD uint32_t BlockContext(const FrameDev& f, uint32_t order, uint32_t hf_mul
 // AC part of a PassGroup section (App. B.7).  Writes the non-zero quantised coefficients of group g into the frame's
 // coefficient planes (pre-zeroed), each block's coefficient array occupying the block's pixel rectangle, transposed
 // for tall blocks (DESIGN.md "coefficient planes").
-JXLB_HD_NOINLINE int DecodeAcGroup(BitReader& br, const FrameDev& f, uint32_t g, const NaturalOrders& nat, StreamScratch& s) {
+JXLB_HD_NOINLINE int DecodeAcGroup(BitReader& br_io, const FrameDev& f, uint32_t g, const NaturalOrders& nat, StreamScratch& s) {
+  BitReader br = br_io;  // register copy: the coefficient stores below must not force reloads of the reader state
   const uint32_t gx = g % f.ngx, gy = g / f.ngx;
   const uint32_t bx0 = gx * kGroupCells, by0 = gy * kGroupCells;
   const uint32_t bw = f.w8 - bx0 < kGroupCells ? f.w8 - bx0 : kGroupCells;
@@ -361,6 +363,7 @@ JXLB_HD_NOINLINE int DecodeAcGroup(BitReader& br, const FrameDev& f, uint32_t g,
   }
   if (!sr.FinalStateOk()) return kErrBadStream;
   if (br.Overrun()) return kErrTruncated;
+  br_io = br;
   return kOk;
 }
 
@@ -389,7 +392,7 @@ JXLB_HD_NOINLINE int DecodeModularGroup(BitReader& br, const FrameDev& f, uint32
   int st = BeginModularStream(br, f, s, max_local_nodes, &mh, &mc);
   if (st != kOk) return st;
   const uint32_t stream_id = 1 + 3 * f.num_lf_groups + 17 + g;
-  st = DecodeModularChannels(br, mc, mh.wp, ch, nch, stream_id, s.wp, s.lz77, s.lz77_mask);
+  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, nch, stream_id, s.wp, s.lz77, s.lz77_mask);
   if (st != kOk) return st;
   ApplyInverseRcts(mh, ch, nch);
   s.arena.used = arena_mark;
@@ -414,7 +417,7 @@ JXLB_HD_NOINLINE int DecodeGlobalModular(BitReader& br, const FrameDev& f, Strea
   uint32_t arena_mark = s.arena.used;
   int st = BeginModularStream(br, f, s, max_local_nodes, &mh, &mc);
   if (st != kOk) return st;
-  st = DecodeModularChannels(br, mc, mh.wp, ch, nch, 0, s.wp, s.lz77, s.lz77_mask);
+  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, nch, 0, s.wp, s.lz77, s.lz77_mask);
   if (st != kOk) return st;
   if (nch == f.num_mod_channels) ApplyInverseRcts(mh, ch, nch);
   s.arena.used = arena_mark;

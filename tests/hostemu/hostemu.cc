@@ -83,7 +83,7 @@ void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, si
   const FrameDev& f = e->f;
   // scratch
   std::vector<uint8_t> arena_mem(8u << 20), hf_mem(8u << 20);
-  std::vector<int32_t> wp(WPState::ScratchInts(4096 + 64));
+  std::vector<int32_t> wp(ModFastScratch::Ints(65536 + 64));
   std::vector<uint32_t> lz(1u << 20), perm(2 * 65536);
   std::vector<uint8_t> nz(3 * 1024);
   StreamScratch s;
