@@ -594,10 +594,11 @@ struct Batch {
         od.alpha_channel = (int32_t) (f.num_color_mod_channels + (uint32_t) ai);
         od.alpha_bits = p.md.extra[ai].bits;
       }
-      if (f.encoding == 0) {
+      const bool fused = f.encoding == 0 && getenv("JXLB_SIMPLE_FILTERS") == nullptr;
+      if (f.encoding == 0 && !fused) {
         int cur = LaunchFilters(f, s);
         LaunchColor(f, p.cp, ctx->nt_dev, cur ? f.xyb1 : f.xyb0, od, s);
-      } else {
+      } else if (f.encoding != 0) {
         LaunchModularToRgba(f, od, s);
       }
       PackParams pk;  // ReformatColorConfig
@@ -612,7 +613,8 @@ struct Batch {
       pk.attenuate = !p.alpha_premultiplied ? 1 : 0;
       pk.dst_stride = pk.width * FormatBytesPerPixel(pk.format);
       pk.dst = buf->final_out.p + final_off[i];
-      LaunchPack(pk, s);
+      if (fused) LaunchFilterColorPack(f, p.cp, ctx->nt_dev, od, pk, s);
+      else LaunchPack(pk, s);
     }
     CUDA_OK(cudaEventRecord(ev[7], s));
     ran = true;

@@ -19,6 +19,9 @@ namespace {
 std::atomic<uint64_t> g_launches{0};
 
 constexpr int kStreamBlockThreads = 32;  // one warp per section, lane 0 decodes
+// shared memory of an LF-group stream: its entropy code (context map + alias tables) and the modular decoder's rows
+constexpr uint32_t kLfFastCodeBytes = 88u << 10;
+constexpr uint32_t kLfFastInts = 4352;  // ModFastScratch::Ints(288)
 
 struct SyncThreads {
   __device__ void operator()() const { __syncthreads(); }
@@ -62,6 +65,10 @@ __global__ void __launch_bounds__(kStreamBlockThreads) LfGroupKernel(const Frame
   const StreamJob job = jobs[j];
   const FrameDev& f = frames[job.frame];
   StreamScratch sc = CarveScratch(scratch, j, nullptr, nullptr);
+  extern __shared__ __align__(16) uint8_t lf_smem[];
+  sc.fast = lf_smem;
+  sc.fast_code_bytes = kLfFastCodeBytes;
+  sc.fast_ints = kLfFastInts;
   BitReader br;
   const uint32_t sec = 1 + job.index;
   br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);
@@ -180,7 +187,13 @@ void LaunchSingleSectionFrames(const FrameDev* frames, const StreamJob* jobs, ui
 }
 void LaunchLfGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, ScratchLayout scratch, cudaStream_t stream) {
   if (!njobs) return;
-  LfGroupKernel<<<njobs, kStreamBlockThreads, 0, stream>>>(frames, jobs, njobs, scratch);
+  const int smem = (int) (kLfFastCodeBytes + kLfFastInts * 4);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(LfGroupKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  LfGroupKernel<<<njobs, kStreamBlockThreads, smem, stream>>>(frames, jobs, njobs, scratch);
   ++g_launches;
 }
 void LaunchPassGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat, ScratchLayout scratch,

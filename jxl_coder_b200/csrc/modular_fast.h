@@ -31,9 +31,11 @@ struct WPRegs {
 
 // One weighted-predictor step: prediction (<<3 domain handled inside), returns the prediction and the max-error
 // property; `pe_ne` / `err_ne`: values of the row above at x+1 (or x at the right edge).
+// (32-bit arithmetic: sample magnitudes up to 2^18 keep every intermediate below 2^31; only the final
+// multiplication by the 24-bit reciprocal needs 64 bits.)
 struct WPOut {
-  int64_t pred;           // clamped weighted prediction, <<3
-  int64_t sub[4];         // the four sub-predictions, <<3
+  int32_t pred;           // clamped weighted prediction, <<3
+  int32_t sub[4];         // the four sub-predictions, <<3
   int32_t prop;           // property 15
 };
 
@@ -47,11 +49,11 @@ JXLB_HD void WPStep(const WPRegs& r, const int32_t pe_ne[4], int32_t err_ne, con
     if (shift < 0) shift = 0;
     w[i] = 4 + (((uint32_t) h.w[i] * divtab[e >> shift]) >> shift);
   }
-  const int64_t N = (int64_t) N_ * 8, W = (int64_t) W_ * 8, NE = (int64_t) NE_ * 8, NW = (int64_t) NW_ * 8, NN = (int64_t) NN_ * 8;
-  const int64_t teW = r.err_w, teN = r.err_n, teNW = r.err_nw, teNE = err_ne;
-  const int64_t sumWN = teN + teW;
-  int64_t p = teW;
-  int64_t ap = p < 0 ? -p : p;
+  const int32_t N = N_ * 8, W = W_ * 8, NE = NE_ * 8, NW = NW_ * 8, NN = NN_ * 8;
+  const int32_t teW = r.err_w, teN = r.err_n, teNW = r.err_nw, teNE = err_ne;
+  const int32_t sumWN = teN + teW;
+  int32_t p = teW;
+  int32_t ap = p < 0 ? -p : p;
   if ((teN < 0 ? -teN : teN) > ap) { p = teN; ap = p < 0 ? -p : p; }
   if ((teNW < 0 ? -teNW : teNW) > ap) { p = teNW; ap = p < 0 ? -p : p; }
   if ((teNE < 0 ? -teNE : teNE) > ap) { p = teNE; }
@@ -65,14 +67,14 @@ JXLB_HD void WPStep(const WPRegs& r, const int32_t pe_ne[4], int32_t err_ne, con
 #pragma unroll
   for (int i = 0; i < 4; ++i) w[i] >>= (lw - 4);
   ws = w[0] + w[1] + w[2] + w[3];
-  int64_t sum = (int64_t) (ws >> 1) - 1;
+  int32_t sum = (int32_t) (ws >> 1) - 1;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) sum += o->sub[i] * (int64_t) w[i];
-  int64_t pred = (sum * (int64_t) divtab[ws - 1]) >> 24;
+  for (int i = 0; i < 4; ++i) sum += o->sub[i] * (int32_t) w[i];
+  int32_t pred = (int32_t) (((int64_t) sum * (int64_t) divtab[ws - 1]) >> 24);
   if (((teN ^ teW) | (teN ^ teNW)) <= 0) {
-    int64_t mx = W > NE ? W : NE;
+    int32_t mx = W > NE ? W : NE;
     if (N > mx) mx = N;
-    int64_t mn = W < NE ? W : NE;
+    int32_t mn = W < NE ? W : NE;
     if (N < mn) mn = N;
     if (pred > mx) pred = mx;
     if (pred < mn) pred = mn;
@@ -154,7 +156,7 @@ JXLB_HD int64_t PredictNoWp(uint32_t predictor, int32_t W, int32_t N, int32_t NW
 
 JXLB_HD_NOINLINE int DecodeModularChannelsFast(BitReader& br_io, const ModularContext& mc, const WPHeader& wph, const ModChannel* ch,
                                                uint32_t nch, uint32_t stream_id, int32_t* scratch, uint32_t* lz77_window,
-                                               uint32_t lz77_mask) {
+                                               uint32_t lz77_mask, int32_t* fast_scratch = nullptr, uint32_t fast_ints = 0) {
   BitReader br = br_io;       // register copies; written back on exit
   const CodeView code = mc.code;
   SymbolReader sr;
@@ -167,19 +169,21 @@ JXLB_HD_NOINLINE int DecodeModularChannelsFast(BitReader& br_io, const ModularCo
   if (code.lz77 && lz77_window == nullptr) return kErrUnsupported;
   sr.Begin(code, br, lz77_window, lz77_mask);
   const TreeNode* tree = mc.tree;
-  // scratch carve-up
-  uint32_t* divtab = reinterpret_cast<uint32_t*>(scratch);
-  uint16_t* lut = reinterpret_cast<uint16_t*>(scratch + 64);
-  int32_t* rows = scratch + 64 + ModFastScratch::kLutEntries / 2;
-  int32_t* wpmem = rows + 3 * (maxw + 8);
-  for (uint32_t k = 0; k < 64; ++k) divtab[k] = (1u << 24) / (k + 1);
   int status = kOk;
+  (void) maxw;
   for (uint32_t ci = 0; ci < nch && status == kOk; ++ci) {
     const ModChannel c = ch[ci];
     if (!c.w || !c.h) continue;
     const SubtreeInfo info = AnalyseSubtree(tree, mc.num_nodes, ci, stream_id);
     const uint32_t xs = c.w;
-    int32_t* rbuf[3] = {rows, rows + (maxw + 8), rows + 2 * (maxw + 8)};  // rotating: [0] current, [1] N row, [2] NN row
+    // scratch carve-up for this channel: the fast (shared-memory) region when the channel is narrow enough
+    int32_t* base = (fast_scratch && ModFastScratch::Ints(xs) <= fast_ints) ? fast_scratch : scratch;
+    uint32_t* divtab = reinterpret_cast<uint32_t*>(base);
+    uint16_t* lut = reinterpret_cast<uint16_t*>(base + 64);
+    int32_t* rows = base + 64 + ModFastScratch::kLutEntries / 2;
+    int32_t* wpmem = rows + 3 * (xs + 8);
+    for (uint32_t k = 0; k < 64; ++k) divtab[k] = (1u << 24) / (k + 1);
+    int32_t* rbuf[3] = {rows, rows + (xs + 8), rows + 2 * (xs + 8)};  // rotating: [0] current, [1] N row, [2] NN row
     // weighted-predictor rows: err[2][xs+2], pe[4][2][xs+2]
     int32_t* err_rows = wpmem;
     int32_t* pe_rows = wpmem + 2 * (xs + 2);
@@ -198,6 +202,8 @@ JXLB_HD_NOINLINE int DecodeModularChannelsFast(BitReader& br_io, const ModularCo
       }
     }
     const TreeNode root_node = tree[info.root];
+    // NN feeds WP sub-predictor 3 only through p3[3], and otherwise only general trees (property 13 / predictor 13)
+    const bool need_nn = !info.wp_only || wph.p3[3] != 0;
     for (uint32_t y = 0; y < c.h; ++y) {
       int32_t* out_row = c.data + (size_t) y * c.stride;
       int32_t* cur = rbuf[0];
@@ -224,7 +230,7 @@ JXLB_HD_NOINLINE int DecodeModularChannelsFast(BitReader& br_io, const ModularCo
       int32_t prev9 = 0;
       for (uint32_t x = 0; x < xs; ++x) {
         const int32_t NE = (x + 1 < xs && y > 0) ? rN[x + 1] : N;
-        const int32_t NN = y > 1 ? rNN[x] : N;
+        const int32_t NN = (need_nn && y > 1) ? rNN[x] : N;
         WPOut wo;
         int32_t pe_ne[4];
         int32_t err_ne = 0;
@@ -313,14 +319,14 @@ JXLB_HD_NOINLINE int DecodeModularChannelsFast(BitReader& br_io, const ModularCo
         cur[x] = val;
         out_row[x] = val;
         if (info.uses_wp) {
-          const int64_t v8 = (int64_t) val * 8;
-          const int32_t e_cur = (int32_t) (wo.pred - v8);
+          const int32_t v8 = val * 8;
+          const int32_t e_cur = wo.pred - v8;
           err_rows[cur_o + x] = e_cur;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            int64_t d = wo.sub[i] - v8;
+            int32_t d = wo.sub[i] - v8;
             if (d < 0) d = -d;
-            const int32_t e = (int32_t) ((d + 3) >> 3);
+            const int32_t e = (d + 3) >> 3;
             pe_rows[(size_t) i * 2 * (xs + 2) + cur_o + x] = e;
             wr.pe_nw[i] = wr.pe_n[i];
             wr.pe_n[i] = pe_ne[i] + e;  // the row above at x+1, plus this sample's "+= e"

@@ -303,7 +303,8 @@ struct Planes3 {
 };
 
 // Gaborish: 3x3 smoothing-undo kernel (App. B.7), one output sample.
-JXLB_HD float GaborishSample(const Planes3& im, int c, int x, int y, float w1, float w2) {
+template <class Img>
+JXLB_HD float GaborishSample(const Img& im, int c, int x, int y, float w1, float w2) {
   const float centre = im.at(c, x, y);
   const float cross = im.at(c, x, y - 1) + im.at(c, x, y + 1) + im.at(c, x - 1, y) + im.at(c, x + 1, y);
   const float diag = im.at(c, x - 1, y - 1) + im.at(c, x + 1, y - 1) + im.at(c, x - 1, y + 1) + im.at(c, x + 1, y + 1);
@@ -320,8 +321,11 @@ JXLB_HD float EpfInvSigma(const FrameDev& f, uint32_t hf_mul, uint32_t sharp) {
   return 1.0f / sigma;
 }
 
-// One EPF output pixel for stage 0 / 1 / 2 (App. B.7).
-JXLB_HD void EpfPixel(const Planes3& im, const RestorationFilter& rf, int stage, int x, int y, float inv_sigma, float out[3]) {
+// One EPF output pixel for stage kStage = 0 / 1 / 2 (App. B.7).  Neighbour lists are compile-time constants so that the
+// loops unroll completely and every tap becomes a fixed-offset load.
+// (px, py) = image coordinates deciding the 8x8-border weighting; (x, y) = coordinates inside `im`.
+template <int kStage, class Img>
+JXLB_HD void EpfPixelT(const Img& im, const RestorationFilter& rf, int x, int y, int px, int py, float inv_sigma, float out[3]) {
   const float c0 = im.at(0, x, y), c1 = im.at(1, x, y), c2 = im.at(2, x, y);
   if (inv_sigma < kEpfSkipThreshold) {
     out[0] = c0;
@@ -330,43 +334,68 @@ JXLB_HD void EpfPixel(const Planes3& im, const RestorationFilter& rf, int stage,
     return;
   }
   float sm = 1.65f;
-  if (stage == 0) sm *= rf.epf_pass0_sigma_scale;
-  if (stage == 2) sm *= rf.epf_pass2_sigma_scale;
-  const int xm = x & 7, ym = y & 7;
+  if (kStage == 0) sm *= rf.epf_pass0_sigma_scale;
+  if (kStage == 2) sm *= rf.epf_pass2_sigma_scale;
+  const int xm = px & 7, ym = py & 7;
   if (xm == 0 || xm == 7 || ym == 0 || ym == 7) sm *= rf.epf_border_sad_mul;
   const float isg = inv_sigma * sm;
   float wsum = 1.0f, a0 = c0, a1 = c1, a2 = c2;
-  const int n = stage == 0 ? 12 : 4;
-  const int8_t n12[12][2] = {{0, -2}, {-1, -1}, {0, -1}, {1, -1}, {-2, 0}, {-1, 0}, {1, 0}, {2, 0}, {-1, 1}, {0, 1}, {1, 1}, {0, 2}};
-  const int8_t n4[4][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}};
-  for (int i = 0; i < n; ++i) {
-    const int dx = stage == 0 ? n12[i][0] : n4[i][0];
-    const int dy = stage == 0 ? n12[i][1] : n4[i][1];
+  constexpr int kN = kStage == 0 ? 12 : 4;
+  constexpr int kDx[12] = {0, -1, 0, 1, -2, -1, 1, 2, -1, 0, 1, 0};
+  constexpr int kDy[12] = {-2, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 2};
+  constexpr int kDx4[4] = {0, 0, -1, 1};
+  constexpr int kDy4[4] = {-1, 1, 0, 0};
+  // centre plus-shape, reused by every neighbour
+  float cc[3][5];
+  if (kStage != 2) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      cc[c][0] = c == 0 ? c0 : c == 1 ? c1 : c2;
+      cc[c][1] = im.at(c, x, y - 1);
+      cc[c][2] = im.at(c, x, y + 1);
+      cc[c][3] = im.at(c, x - 1, y);
+      cc[c][4] = im.at(c, x + 1, y);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kN; ++i) {
+    const int dx = kStage == 0 ? kDx[i] : kDx4[i];
+    const int dy = kStage == 0 ? kDy[i] : kDy4[i];
     float sad = 0.0f;
+    float nv[3];
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float sc = rf.epf_channel_scale[c];
-      if (stage == 2) {
-        sad += fabsf(im.at(c, x + dx, y + dy) - im.at(c, x, y)) * sc;
+      nv[c] = im.at(c, x + dx, y + dy);
+      if (kStage == 2) {
+        sad += fabsf(nv[c] - (c == 0 ? c0 : c == 1 ? c1 : c2)) * sc;
       } else {
-        float s = fabsf(im.at(c, x + dx, y + dy) - im.at(c, x, y));
-        s += fabsf(im.at(c, x + dx, y + dy - 1) - im.at(c, x, y - 1));
-        s += fabsf(im.at(c, x + dx, y + dy + 1) - im.at(c, x, y + 1));
-        s += fabsf(im.at(c, x + dx - 1, y + dy) - im.at(c, x - 1, y));
-        s += fabsf(im.at(c, x + dx + 1, y + dy) - im.at(c, x + 1, y));
+        float s = fabsf(nv[c] - cc[c][0]);
+        s += fabsf(im.at(c, x + dx, y + dy - 1) - cc[c][1]);
+        s += fabsf(im.at(c, x + dx, y + dy + 1) - cc[c][2]);
+        s += fabsf(im.at(c, x + dx - 1, y + dy) - cc[c][3]);
+        s += fabsf(im.at(c, x + dx + 1, y + dy) - cc[c][4]);
         sad += s * sc;
       }
     }
     float w = 1.0f + sad * isg;
     if (w < 0.0f) w = 0.0f;
     wsum += w;
-    a0 += w * im.at(0, x + dx, y + dy);
-    a1 += w * im.at(1, x + dx, y + dy);
-    a2 += w * im.at(2, x + dx, y + dy);
+    a0 += w * nv[0];
+    a1 += w * nv[1];
+    a2 += w * nv[2];
   }
   const float inv = 1.0f / wsum;
   out[0] = a0 * inv;
   out[1] = a1 * inv;
   out[2] = a2 * inv;
+}
+
+template <class Img>
+JXLB_HD void EpfPixel(const Img& im, const RestorationFilter& rf, int stage, int x, int y, int px, int py, float inv_sigma, float out[3]) {
+  if (stage == 0) EpfPixelT<0>(im, rf, x, y, px, py, inv_sigma, out);
+  else if (stage == 1) EpfPixelT<1>(im, rf, x, y, px, py, inv_sigma, out);
+  else EpfPixelT<2>(im, rf, x, y, px, py, inv_sigma, out);
 }
 
 // ---- colour ------------------------------------------------------------------------------------------------------------

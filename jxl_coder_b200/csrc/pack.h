@@ -58,14 +58,9 @@ JXLB_HD uint16_t FloatToHalfBits(float f) {
 #endif
 }
 
-JXLB_HD void PackPixel(const PackParams& p, uint32_t x, uint32_t y) {
-  uint32_t r, g, b, a;
+// Packs one decoded pixel (r, g, b, a at the decode stage's depth: 8-bit, or 16-bit when p.src16) into the output.
+JXLB_HD void PackRgba(const PackParams& p, uint32_t x, uint32_t y, uint32_t r, uint32_t g, uint32_t b, uint32_t a) {
   if (p.src16) {
-    const uint16_t* s = reinterpret_cast<const uint16_t*>(p.src + (size_t) y * p.src_stride) + 4 * (size_t) x;
-    r = s[0];
-    g = s[1];
-    b = s[2];
-    a = s[3];
     if (p.associate) {
       const uint32_t maxc = (1u << p.depth) - 1;
       r = r * a / maxc;
@@ -105,11 +100,6 @@ JXLB_HD void PackPixel(const PackParams& p, uint32_t x, uint32_t y) {
     }
     return;
   }
-  const uint8_t* s = p.src + (size_t) y * p.src_stride + 4 * (size_t) x;
-  r = s[0];
-  g = s[1];
-  b = s[2];
-  a = s[3];
   if (p.associate) {
     r = r * a / 255u;
     g = g * a / 255u;
@@ -117,11 +107,7 @@ JXLB_HD void PackPixel(const PackParams& p, uint32_t x, uint32_t y) {
   }
   uint8_t* drow = p.dst + (size_t) y * p.dst_stride;
   if (p.format == 0) {
-    uint8_t* o = drow + 4 * (size_t) x;
-    o[0] = (uint8_t) r;
-    o[1] = (uint8_t) g;
-    o[2] = (uint8_t) b;
-    o[3] = (uint8_t) a;
+    reinterpret_cast<uint32_t*>(drow)[x] = (r & 0xFFu) | ((g & 0xFFu) << 8) | ((b & 0xFFu) << 16) | ((a & 0xFFu) << 24);  // R,G,B,A bytes
     return;
   }
   if (p.attenuate) {  // the converters premultiply again (reference quirk)
@@ -140,6 +126,16 @@ JXLB_HD void PackPixel(const PackParams& p, uint32_t x, uint32_t y) {
     reinterpret_cast<uint16_t*>(drow)[x] = (uint16_t) (((r >> 3) << 11) | ((g >> 2) << 5) | (b >> 3));
   } else {
     reinterpret_cast<uint32_t*>(drow)[x] = ((a >> 6) << 30) | ((b << 2) << 20) | ((g << 2) << 10) | (r << 2);
+  }
+}
+
+JXLB_HD void PackPixel(const PackParams& p, uint32_t x, uint32_t y) {
+  if (p.src16) {
+    const uint16_t* s = reinterpret_cast<const uint16_t*>(p.src + (size_t) y * p.src_stride) + 4 * (size_t) x;
+    PackRgba(p, x, y, s[0], s[1], s[2], s[3]);
+  } else {
+    const uint8_t* s = p.src + (size_t) y * p.src_stride + 4 * (size_t) x;
+    PackRgba(p, x, y, s[0], s[1], s[2], s[3]);
   }
 }
 

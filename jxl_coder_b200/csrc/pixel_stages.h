@@ -40,7 +40,7 @@ JXLB_HD void StageEpf(const FrameDev& f, int stage, const float* src, float* dst
   const size_t ci = (size_t) (y >> 3) * f.w8 + (x >> 3);
   const float inv_sigma = EpfInvSigma(f, f.cell_hfmul[ci], f.cell_sharp[ci]);
   float out[3];
-  EpfPixel(im, f.rf, stage, x, y, inv_sigma, out);
+  EpfPixel(im, f.rf, stage, x, y, x, y, inv_sigma, out);
   dst[o] = out[0];
   dst[plane + o] = out[1];
   dst[2 * plane + o] = out[2];

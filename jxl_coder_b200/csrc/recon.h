@@ -80,10 +80,13 @@ static constexpr int kTileFloats = kRegionDim * kTileStride;  // one channel
 
 struct RegionCell {
   uint8_t strategy;   // 0..26, 0xFF = outside the frame
-  uint8_t flags;      // bit 0: this block is fully inside the region, bit 1: special 8x8 transform
+  uint8_t flags;      // bit 0: this block is fully inside the region, bit 1: special 8x8 transform, bit 2: transposed layout
   int8_t ox, oy;      // block origin in region cell coordinates (may be negative when not contained)
+  uint8_t kcols_log;  // log2 of the coefficient array's column count
   uint16_t hf_mul;
-  uint16_t pad;
+  uint32_t dq_off[3]; // offsets of the block's dequant matrices (X, Y, B) in the pool
+  float scale;        // 65536 / global_scale / hf_mul
+  float kx, kb;       // chroma-from-luma factors of the block
 };
 
 struct RegionShared {
@@ -126,7 +129,9 @@ JXLB_HD void ReconRegion(const FrameDev& f, const NumericTables& nt, uint32_t rx
     rc.flags = 0;
     rc.ox = rc.oy = 0;
     rc.hf_mul = 1;
-    rc.pad = 0;
+    rc.kcols_log = 3;
+    rc.dq_off[0] = rc.dq_off[1] = rc.dq_off[2] = 0;
+    rc.scale = rc.kx = rc.kb = 0.0f;
     const uint32_t gx = cx0 + ix, gy = cy0 + iy;
     if (gx < f.w8 && gy < f.h8) {
       const size_t ci = (size_t) gy * f.w8 + gx;
@@ -139,13 +144,22 @@ JXLB_HD void ReconRegion(const FrameDev& f, const NumericTables& nt, uint32_t rx
       rc.oy = (int8_t) ((int) iy - dy);
       const int bx = (int) StrategyCellsX(t), by = (int) StrategyCellsY(t);
       const bool contained = rc.ox >= 0 && rc.oy >= 0 && rc.ox + bx <= kRegionCells && rc.oy + by <= kRegionCells;
-      rc.flags = (uint8_t) ((contained ? 1 : 0) | (IsSpecial8x8(t) ? 2 : 0));
+      rc.flags = (uint8_t) ((contained ? 1 : 0) | (IsSpecial8x8(t) ? 2 : 0) | (by >= bx ? 4 : 0));
+      rc.kcols_log = (uint8_t) (3 + FloorLog2((uint32_t) (bx > by ? bx : by)));
+      const uint32_t qt = StrategyQuantTable(t);
+      for (int c = 0; c < 3; ++c) rc.dq_off[c] = nt.dequant_off[qt][c];
+      rc.scale = 65536.0f / (float) f.global_scale / (float) rc.hf_mul;
+      if (contained) {
+        // CfL factors come from the 64x64 tile of the block's top-left corner
+        const uint32_t tx = (cx0 + (uint32_t) rc.ox) / 8, ty = (cy0 + (uint32_t) rc.oy) / 8;
+        rc.kx = f.cfl.base_x + (float) f.xfromy[(size_t) ty * f.w64 + tx] / (float) f.cfl.colour_factor;
+        rc.kb = f.cfl.base_b + (float) f.bfromy[(size_t) ty * f.w64 + tx] / (float) f.cfl.colour_factor;
+      }
     }
     sh.cell[i] = rc;
   }
   sync();
   // P1: dequantise + chroma-from-luma into the three tiles (rows are coalesced int16 loads)
-  const float inv_gs = 65536.0f / (float) f.global_scale;
   const float xqm = QmScale(f.x_qm_scale), bqm = QmScale(f.b_qm_scale);
   const size_t cplane = (size_t) f.coef_h * f.coef_stride;
   for (int i = tid; i < kRegionDim * kRegionDim; i += nthreads) {
@@ -156,15 +170,11 @@ JXLB_HD void ReconRegion(const FrameDev& f, const NumericTables& nt, uint32_t rx
       const uint32_t pr = row - (uint32_t) rc.oy * 8, pc = col - (uint32_t) rc.ox * 8;
       const size_t gi = (size_t) (cy0 * 8 + row) * f.coef_stride + cx0 * 8 + col;
       const int qx = f.coef[gi], qy = f.coef[cplane + gi], qb = f.coef[2 * cplane + gi];
-      const float scale = inv_gs / (float) rc.hf_mul;
-      const uint32_t t = rc.strategy;
-      vy = DequantAt(f, nt, t, 1, qy, pr, pc, scale);
-      // CfL factors come from the 64x64 tile of the block's top-left corner
-      const uint32_t tx = (cx0 + (uint32_t) rc.ox) / 8, ty = (cy0 + (uint32_t) rc.oy) / 8;
-      const float kx = f.cfl.base_x + (float) f.xfromy[(size_t) ty * f.w64 + tx] / (float) f.cfl.colour_factor;
-      const float kb = f.cfl.base_b + (float) f.bfromy[(size_t) ty * f.w64 + tx] / (float) f.cfl.colour_factor;
-      vx = DequantAt(f, nt, t, 0, qx, pr, pc, scale * xqm) + kx * vy;
-      vb = DequantAt(f, nt, t, 2, qb, pr, pc, scale * bqm) + kb * vy;
+      // index into the block's dequant matrix (stored like the coefficient array: transposed for square / tall blocks)
+      const uint32_t ki = (rc.flags & 4) ? ((pc << rc.kcols_log) + pr) : ((pr << rc.kcols_log) + pc);
+      vy = qy ? AdjustQuantBias(qy, 1) * rc.scale * nt.dequant[rc.dq_off[1] + ki] : 0.0f;
+      vx = (qx ? AdjustQuantBias(qx, 0) * (rc.scale * xqm) * nt.dequant[rc.dq_off[0] + ki] : 0.0f) + rc.kx * vy;
+      vb = (qb ? AdjustQuantBias(qb, 2) * (rc.scale * bqm) * nt.dequant[rc.dq_off[2] + ki] : 0.0f) + rc.kb * vy;
     }
     const int ti = (int) row * kTileStride + (int) col;
     sh.tile[ti] = vx;

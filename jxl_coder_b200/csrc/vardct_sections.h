@@ -93,6 +93,9 @@ struct StreamScratch {
   uint32_t* lz77;          // optional LZ77 window (power-of-two entries) or nullptr
   uint32_t lz77_mask;
   uint8_t* nzmap;          // 3 * 32 * 32 bytes for the AC non-zero context map
+  uint8_t* fast = nullptr;      // optional low-latency memory (shared memory on the device): [code blob | modular scratch]
+  uint32_t fast_code_bytes = 0; // capacity of the code-blob part
+  uint32_t fast_ints = 0;       // capacity (int32) of the modular-scratch part
 };
 
 // Reads a modular sub-stream's GroupHeader and resolves its tree + code (global or local, built in scratch).
@@ -119,6 +122,16 @@ JXLB_HD_NOINLINE int BeginModularStream(BitReader& br, const FrameDev& f, Stream
     mc->uses_wp = wp;
     mc->max_property = maxp;
     mc->code.Bind(s.arena.base + coff);
+  }
+  // stage the code (context map + alias tables) in low-latency memory when it fits
+  if (s.fast) {
+    const CodeHeader* chh = reinterpret_cast<const CodeHeader*>(mc->code.blob);
+    if (chh->total_bytes <= s.fast_code_bytes) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(mc->code.blob);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(s.fast);
+      for (uint32_t i = 0; i < chh->total_bytes / 4; ++i) dst[i] = src[i];
+      mc->code.Bind(s.fast);
+    }
   }
   return kOk;
 }
@@ -183,7 +196,8 @@ JXLB_HD_NOINLINE int DecodeLfGroupSection(BitReader& br, const FrameDev& f, uint
     ch[c].h = h8;
     ch[c].stride = f.lf_stride;
   }
-  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, 3, 1 + lfg, s.wp, s.lz77, s.lz77_mask);
+  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, 3, 1 + lfg, s.wp, s.lz77, s.lz77_mask,
+                                 s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
   if (st != kOk) return st;
   ApplyInverseRcts(mh, ch, 3);
   s.arena.used = arena_mark;
@@ -210,7 +224,8 @@ JXLB_HD_NOINLINE int DecodeLfGroupSection(BitReader& br, const FrameDev& f, uint
   ch[3].w = w8;
   ch[3].h = h8;
   ch[3].stride = f.lf_stride;
-  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, 4, 1 + 2 * nlf + lfg, s.wp, s.lz77, s.lz77_mask);
+  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, 4, 1 + 2 * nlf + lfg, s.wp, s.lz77, s.lz77_mask,
+                                 s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
   if (st != kOk) return st;
   if (mh.nb_transforms) return kErrUnsupported;
   s.arena.used = arena_mark;
@@ -392,7 +407,8 @@ JXLB_HD_NOINLINE int DecodeModularGroup(BitReader& br, const FrameDev& f, uint32
   int st = BeginModularStream(br, f, s, max_local_nodes, &mh, &mc);
   if (st != kOk) return st;
   const uint32_t stream_id = 1 + 3 * f.num_lf_groups + 17 + g;
-  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, nch, stream_id, s.wp, s.lz77, s.lz77_mask);
+  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, nch, stream_id, s.wp, s.lz77, s.lz77_mask,
+                                 s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
   if (st != kOk) return st;
   ApplyInverseRcts(mh, ch, nch);
   s.arena.used = arena_mark;
@@ -417,7 +433,8 @@ JXLB_HD_NOINLINE int DecodeGlobalModular(BitReader& br, const FrameDev& f, Strea
   uint32_t arena_mark = s.arena.used;
   int st = BeginModularStream(br, f, s, max_local_nodes, &mh, &mc);
   if (st != kOk) return st;
-  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, nch, 0, s.wp, s.lz77, s.lz77_mask);
+  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, nch, 0, s.wp, s.lz77, s.lz77_mask,
+                                 s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
   if (st != kOk) return st;
   if (nch == f.num_mod_channels) ApplyInverseRcts(mh, ch, nch);
   s.arena.used = arena_mark;
