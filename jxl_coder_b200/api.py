@@ -136,10 +136,12 @@ class Bitmap:
         self.device_ptr = img.data if img.device >= 0 else None
         if img.device < 0:
             n = img.stride_bytes * img.height
-            raw = np.ctypeslib.as_array(C.cast(img.data, C.POINTER(C.c_uint8)), shape=(n,)).copy().reshape(img.height, img.stride_bytes)
-            self.pixels = raw  # uint8 view [h, stride]; see as_array()
-            if not keep_native:
+            raw = np.ctypeslib.as_array(C.cast(img.data, C.POINTER(C.c_uint8)), shape=(n,))
+            if not keep_native:  # own copy; the native buffer goes back to the pinned pool
+                raw = raw.copy()
                 load_library().jxlb_image_free(C.byref(img))
+            # keep_native: zero-copy view of the pinned result, valid until free()
+            self.pixels = raw.reshape(img.height, img.stride_bytes)  # uint8 [h, stride]; see as_array()
         else:
             self.pixels = None
 
@@ -160,7 +162,9 @@ class Bitmap:
 
 
 def _as_buffer(data):
-    if isinstance(data, (bytes, bytearray)):
+    if isinstance(data, bytes):  # immutable: hand the library the object's own storage (it copies what it keeps)
+        return C.c_char_p(data), len(data)
+    if isinstance(data, bytearray):
         return (C.c_char * len(data)).from_buffer_copy(data), len(data)
     b = bytes(data)
     return (C.c_char * len(b)).from_buffer_copy(b), len(b)

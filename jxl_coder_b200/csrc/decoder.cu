@@ -14,7 +14,9 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <atomic>
 #include <mutex>
+#include <thread>
 
 #include "color_params.h"
 #include "frame_parser.h"
@@ -38,6 +40,30 @@ struct CudaError {
 };
 
 size_t Align256(size_t v) { return (v + 255) & ~(size_t) 255; }
+
+// Runs fn(i) for i in [0, n) on up to hardware_concurrency host threads (header parsing and staging of a batch are
+// independent per image).
+template <class Fn>
+void ParallelFor(size_t n, Fn fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = std::min<size_t>(n, hw ? hw : 4);
+  if (nt <= 1) {
+    for (size_t i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> ths;
+  auto work = [&]() {
+    for (;;) {
+      size_t i = next.fetch_add(1);
+      if (i >= n) return;
+      fn(i);
+    }
+  };
+  for (size_t t = 1; t < nt; ++t) ths.emplace_back(work);
+  work();
+  for (auto& t : ths) t.join();
+}
 constexpr uint32_t kMaxAcSmemCode = 208u << 10;  // AC code blobs up to this size are staged in shared memory
 
 struct DevBuffer {
@@ -103,7 +129,7 @@ HostPool& Pool() {
 struct DeviceContext {
   int device = 0;
   std::mutex mu;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
   DevBuffer const_buf, work_buf, scratch_buf, meta_buf, stage_out;
   PinnedBuffer staging, status_host;
   NumericTables* nt_dev = nullptr;
@@ -115,6 +141,7 @@ struct DeviceContext {
     device = dev;
     CUDA_OK(cudaSetDevice(dev));
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
     // constant tables
     const HostNumericTables& h = GetHostNumericTables();
@@ -374,12 +401,20 @@ struct Batch {
   BatchBuffers* buf = nullptr;
   cudaEvent_t ev[10]{};
   bool events = false;
+  // e2e path: pinned host destinations; image i is copied out on the copy stream as soon as its last kernel is done,
+  // so the download of image i overlaps the reconstruction of image i + 1
+  std::vector<void*> host_dst;
+  std::vector<cudaEvent_t> img_ev;
   bool uploaded = false, ran = false;
   BatchTimings tm;
 
   ~Batch() {
     if (events)
       for (auto& e : ev) cudaEventDestroy(e);
+    for (auto& e : img_ev)
+      if (e) cudaEventDestroy(e);
+    for (void* h : host_dst)
+      if (h) Pool().Put(h);
     auto freed = [](DevBuffer& b) {
       if (b.p) cudaFree(b.p);
       b.p = nullptr;
@@ -403,7 +438,7 @@ struct Batch {
     n = count;
     api_level = api <= 0 ? 34 : api;
     ps.assign(n, Parsed());
-    for (size_t i = 0; i < n; ++i) ParseRequest(reqs[i], api_level, &ps[i]);
+    ParallelFor(n, [&](size_t i) { ParseRequest(reqs[i], api_level, &ps[i]); });
     frame_of.assign(n, 0);
     final_off.assign(n, 0);
     final_bytes.assign(n, 0);
@@ -512,12 +547,12 @@ struct Batch {
     CUDA_OK(cudaEventRecord(ev[0], s));
     uint8_t* stg = buf->staging.p;
     frames.assign(nframes, FrameDev());
-    for (size_t i = 0; i < n; ++i) {
+    ParallelFor(n, [&](size_t i) {
       Parsed& p = ps[i];
-      if (p.status != JXLB_OK) continue;
+      if (p.status != JXLB_OK) return;
       FillConstRegion(p.plan, p.cs.data(), p.fh, p.g, stg + p.const_off);
       frames[frame_of[i]] = BindFrameDev(p.plan, buf->const_buf.p + p.const_off, buf->work_buf.p + p.work_off);
-    }
+    });
     uint8_t* meta_h = stg + const_total;
     memcpy(meta_h, frames.data(), nframes * sizeof(FrameDev));
     StreamJob* jobs_h = reinterpret_cast<StreamJob*>(meta_h + Align256(nframes * sizeof(FrameDev)));
@@ -544,6 +579,18 @@ struct Batch {
     jobs_ac_cta_d = reinterpret_cast<const AcCtaJob*>(jd + aco);
     CUDA_OK(cudaEventRecord(ev[1], s));
     uploaded = true;
+  }
+
+  // Pinned host destinations for the overlapped download (e2e path).  Images that cannot get one fall back to the
+  // copy in Finish (which reports JXLB_OOM when that fails too).
+  void PrepareHostOutputs() {
+    host_dst.assign(n, nullptr);
+    img_ev.assign(n, nullptr);
+    for (size_t i = 0; i < n; ++i) {
+      if (ps[i].status != JXLB_OK) continue;
+      host_dst[i] = Pool().Get(final_bytes[i]);
+      CUDA_OK(cudaEventCreateWithFlags(&img_ev[i], cudaEventDisableTiming));
+    }
   }
 
   // All kernels, from the uploaded codestreams to packed pixels in HBM.  Asynchronous on ctx->stream.
@@ -615,6 +662,11 @@ struct Batch {
       pk.dst = buf->final_out.p + final_off[i];
       if (fused) LaunchFilterColorPack(f, p.cp, ctx->nt_dev, od, pk, s);
       else LaunchPack(pk, s);
+      if (i < host_dst.size() && host_dst[i]) {
+        CUDA_OK(cudaEventRecord(img_ev[i], s));
+        CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, img_ev[i], 0));
+        CUDA_OK(cudaMemcpyAsync(host_dst[i], buf->final_out.p + final_off[i], final_bytes[i], cudaMemcpyDeviceToHost, ctx->copy_stream));
+      }
     }
     CUDA_OK(cudaEventRecord(ev[7], s));
     ran = true;
@@ -633,7 +685,10 @@ struct Batch {
     std::vector<void*> result(n, nullptr);
     for (size_t i = 0; i < n && out; ++i) {
       if (ps[i].status != JXLB_OK) continue;
-      if (to_host) {
+      if (to_host && i < host_dst.size() && host_dst[i]) {
+        result[i] = host_dst[i];  // already in flight on the copy stream (see Run)
+        host_dst[i] = nullptr;
+      } else if (to_host) {
         result[i] = Pool().Get(final_bytes[i]);
         if (!result[i]) {
           Fail(&ps[i], JXLB_OOM, "Not enough memory to decode this image");
@@ -650,6 +705,10 @@ struct Batch {
         result[i] = d;
         CUDA_OK(cudaMemcpyAsync(d, buf->final_out.p + final_off[i], final_bytes[i], cudaMemcpyDeviceToDevice, s));
       }
+    }
+    if (to_host) {  // the decode stream's timeline ends when the copy stream has drained
+      CUDA_OK(cudaEventRecord(ev[9], ctx->copy_stream));
+      CUDA_OK(cudaStreamWaitEvent(s, ev[9], 0));
     }
     CUDA_OK(cudaEventRecord(ev[8], s));
     CUDA_OK(cudaStreamSynchronize(s));
@@ -775,6 +834,7 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
   std::lock_guard<std::mutex> lock(b.ctx->mu);
   try {
     b.Upload(SpareBuffers(b.ctx));
+    if (output_device < 0) b.PrepareHostOutputs();
     b.Run();
     b.Finish(output_device < 0, output_device, out);
     if (timings) *timings = b.tm;

@@ -6,7 +6,7 @@
 // (/root/reference/jxlcoder/src/main/cpp/interop/JxlDecoding.cpp:74-175).  Format digest: SURVEY.md App. B.5-B.7.
 #pragma once
 #include "frame.h"
-#include "modular_fast.h"
+#include "modular_tight.h"
 
 namespace jxlb {
 
@@ -196,7 +196,7 @@ JXLB_HD_NOINLINE int DecodeLfGroupSection(BitReader& br, const FrameDev& f, uint
     ch[c].h = h8;
     ch[c].stride = f.lf_stride;
   }
-  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, 3, 1 + lfg, s.wp, s.lz77, s.lz77_mask,
+  st = DecodeModularChannelsTight(br, mc, mh.wp, ch, 3, 1 + lfg, s.wp, s.lz77, s.lz77_mask,
                                  s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
   if (st != kOk) return st;
   ApplyInverseRcts(mh, ch, 3);
@@ -224,7 +224,7 @@ JXLB_HD_NOINLINE int DecodeLfGroupSection(BitReader& br, const FrameDev& f, uint
   ch[3].w = w8;
   ch[3].h = h8;
   ch[3].stride = f.lf_stride;
-  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, 4, 1 + 2 * nlf + lfg, s.wp, s.lz77, s.lz77_mask,
+  st = DecodeModularChannelsTight(br, mc, mh.wp, ch, 4, 1 + 2 * nlf + lfg, s.wp, s.lz77, s.lz77_mask,
                                  s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
   if (st != kOk) return st;
   if (mh.nb_transforms) return kErrUnsupported;
