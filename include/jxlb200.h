@@ -123,12 +123,25 @@ JXLB_API void jxlb_image_free(jxlb_image* img);
 typedef struct jxlb_batch jxlb_batch;
 JXLB_API jxlb_batch* jxlb_batch_prepare(const jxlb_request* reqs, size_t n, const jxlb_batch_opts* opts, int32_t* status);
 JXLB_API int jxlb_batch_run(jxlb_batch* b);
+/* Asynchronous form: jxlb_batch_run_async enqueues one run on the batch's own CUDA stream and returns; jxlb_batch_wait
+   waits for every run enqueued so far and returns the status.  Runs of DIFFERENT prepared batches overlap on the GPU
+   (the latency-bound LF-group stage of one hides under the throughput kernels of the other); runs of the same batch
+   execute in order. */
+JXLB_API int jxlb_batch_run_async(jxlb_batch* b);
+JXLB_API int jxlb_batch_wait(jxlb_batch* b);
 JXLB_API int jxlb_batch_fetch(jxlb_batch* b, size_t index, jxlb_image* out);
 /* Device pointer + size of result `index` after jxlb_batch_run (valid until the next run / free). */
 JXLB_API const void* jxlb_batch_device_pixels(const jxlb_batch* b, size_t index, size_t* bytes);
 /* Device time (ms, CUDA events on the decode stream) of the last run: [0] upload, [1] LF sections, [2] group sections,
    [3] LF dequant + smoothing, [4] dequant + inverse transforms, [5] filters + colour + pack, [6] download, [7] all kernels. */
 JXLB_API void jxlb_batch_stage_ms(const jxlb_batch* b, float* ms8);
+/* Same layout, averaged over every run of the batch waited for so far; *runs (may be NULL) = how many. */
+JXLB_API void jxlb_batch_stage_ms_mean(const jxlb_batch* b, float* ms8, int32_t* runs);
+/* Measurement helpers: jxlb_batch_reset_stats clears the stage-time averages and re-arms the span start;
+   jxlb_batch_span_ms = device time (CUDA events) from the start of `first`'s first run since its reset to the end of
+   `last`'s latest run (wait for both first) -- the timed region of a run that overlaps several prepared batches. */
+JXLB_API void jxlb_batch_reset_stats(jxlb_batch* b);
+JXLB_API float jxlb_batch_span_ms(const jxlb_batch* first, const jxlb_batch* last);
 JXLB_API void jxlb_batch_free(jxlb_batch* b);
 
 /* JxlAnimatedImage */

@@ -106,6 +106,12 @@ def load_library():
     L.jxlb_batch_prepare.restype = C.c_void_p
     L.jxlb_batch_prepare.argtypes = [C.POINTER(_Request), C.c_size_t, C.POINTER(_BatchOpts), C.POINTER(C.c_int32)]
     L.jxlb_batch_run.argtypes = [C.c_void_p]
+    L.jxlb_batch_run_async.argtypes = [C.c_void_p]
+    L.jxlb_batch_wait.argtypes = [C.c_void_p]
+    L.jxlb_batch_reset_stats.argtypes = [C.c_void_p]
+    L.jxlb_batch_span_ms.restype = C.c_float
+    L.jxlb_batch_span_ms.argtypes = [C.c_void_p, C.c_void_p]
+    L.jxlb_batch_stage_ms_mean.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     L.jxlb_batch_fetch.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(_Image)]
     L.jxlb_batch_device_pixels.restype = C.c_void_p
     L.jxlb_batch_device_pixels.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -326,10 +332,31 @@ class PreparedBatch:
         p = load_library().jxlb_batch_device_pixels(self._h, i, C.byref(n))
         return p, n.value
 
+    def run_async(self):
+        """Enqueues one run on this batch's own stream; runs of different PreparedBatch objects overlap on the GPU."""
+        return load_library().jxlb_batch_run_async(self._h)
+
+    def wait(self):
+        return load_library().jxlb_batch_wait(self._h)
+
     def stage_ms(self):
         buf = (C.c_float * 8)()
         load_library().jxlb_batch_stage_ms(self._h, buf)
         return dict(zip(self.STAGES, [float(v) for v in buf]))
+
+    def reset_stats(self):
+        load_library().jxlb_batch_reset_stats(self._h)
+
+    def span_ms(self, last=None):
+        """Device time from this batch's first run since reset_stats() to the end of `last`'s (default: this batch's) latest run."""
+        return float(load_library().jxlb_batch_span_ms(self._h, (last or self)._h))
+
+    def stage_ms_mean(self):
+        """(mean stage times over every run waited for so far, number of runs)"""
+        buf = (C.c_float * 8)()
+        n = C.c_int32(0)
+        load_library().jxlb_batch_stage_ms_mean(self._h, buf, C.byref(n))
+        return dict(zip(self.STAGES, [float(v) for v in buf])), int(n.value)
 
     def free(self):
         if self._h:

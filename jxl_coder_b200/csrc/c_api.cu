@@ -108,6 +108,8 @@ jxlb_batch* jxlb_batch_prepare(const jxlb_request* reqs, size_t n, const jxlb_ba
   return h;
 }
 int jxlb_batch_run(jxlb_batch* b) { return b ? RunBatch(b->b, true) : JXLB_BAD_ARG; }
+int jxlb_batch_run_async(jxlb_batch* b) { return b ? RunBatch(b->b, false) : JXLB_BAD_ARG; }
+int jxlb_batch_wait(jxlb_batch* b) { return b ? WaitBatch(b->b) : JXLB_BAD_ARG; }
 int jxlb_batch_fetch(jxlb_batch* b, size_t index, jxlb_image* out) {
   if (!b || !out) return JXLB_BAD_ARG;
   DecodedImage d;
@@ -119,6 +121,17 @@ const void* jxlb_batch_device_pixels(const jxlb_batch* b, size_t index, size_t* 
   return b ? BatchDevicePixels(b->b, index, bytes) : nullptr;
 }
 void jxlb_batch_stage_ms(const jxlb_batch* b, float* ms8) { BatchStageMs(b ? b->b : nullptr, ms8); }
+void jxlb_batch_stage_ms_mean(const jxlb_batch* b, float* ms8, int32_t* runs) {
+  int r = 0;
+  BatchStageMsMean(b ? b->b : nullptr, ms8, &r);
+  if (runs) *runs = r;
+}
+void jxlb_batch_reset_stats(jxlb_batch* b) {
+  if (b) ResetBatchStats(b->b);
+}
+float jxlb_batch_span_ms(const jxlb_batch* first, const jxlb_batch* last) {
+  return (first && last) ? BatchSpanMs(first->b, last->b) : -1.f;
+}
 void jxlb_batch_free(jxlb_batch* b) {
   if (!b) return;
   FreeBatch(b->b);

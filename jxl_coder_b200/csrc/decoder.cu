@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -126,23 +127,55 @@ HostPool& Pool() {
   return *pool;
 }
 
-struct DeviceContext {
-  int device = 0;
+struct BatchBuffers {
+  DevBuffer const_buf, work_buf, scratch_buf, meta_buf, stage_out, final_out;
+  PinnedBuffer staging, status_host;
+};
+
+// One decode "slot": a pair of streams plus recycled batch buffers.  Concurrent jxlb_decode_batch calls (the reference's
+// entry points are re-entrant and called from arbitrary app threads) take different slots, so the
+// latency-bound LF stage of one call overlaps the throughput kernels and the downloads of another.
+struct Slot {
   std::mutex mu;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
-  DevBuffer const_buf, work_buf, scratch_buf, meta_buf, stage_out;
-  PinnedBuffer staging, status_host;
+  BatchBuffers spare;
+};
+constexpr int kSlots = 4;
+
+struct DeviceContext {
+  int device = 0;
+  std::mutex mu;  // guards lazily created state below
+  Slot slots[kSlots];
+  std::atomic<uint32_t> next_slot{0};
+  // LF-stage tokens (JXLB_LF_TOKENS=n, default 0 = off).  The LF-group kernel is latency-bound (one lane per 2048x2048
+  // LF group) and leaves the GPU almost idle.  With n > 0 each Run() waits for the LF stage issued n launches earlier
+  // before starting its own, which STAGGERS the batches in flight on different streams (one runs its LF stage while the
+  // others run their throughput kernels).  Measured on B200 (profiles/r1c_overlap_notes.txt): the LF warps then lose
+  // ~45 % of their speed to issue-slot contention with the dense kernels sharing their SM sub-partitions, and the
+  // default -- several batches entering their LF stage together, then sharing the GPU for the dense stages -- wins.
+  static constexpr int kLfEvents = 32;
+  cudaEvent_t lf_ev[kLfEvents]{};
+  uint64_t lf_count = 0;
+  int lf_tokens = 0;
+  cudaEvent_t origin = nullptr;  // JXLB_TIMELINE=1: stage boundaries of every run are printed relative to this event
+  bool timeline = false;
   NumericTables* nt_dev = nullptr;
   NaturalOrders nat_dev{};
-  cudaEvent_t ev[8]{};
   bool ready = false;
 
   void Init(int dev) {
     device = dev;
     CUDA_OK(cudaSetDevice(dev));
-    CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+    for (Slot& sl : slots) {
+      CUDA_OK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+      CUDA_OK(cudaStreamCreateWithFlags(&sl.copy_stream, cudaStreamNonBlocking));
+    }
+    for (auto& e : lf_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (const char* e = getenv("JXLB_LF_TOKENS")) lf_tokens = std::max(0, atoi(e));  // 0 = no staggering
+    timeline = getenv("JXLB_TIMELINE") != nullptr;
+    CUDA_OK(cudaEventCreate(&origin));
+    CUDA_OK(cudaEventRecord(origin, slots[0].stream));
+    CUDA_OK(cudaEventSynchronize(origin));
     // constant tables
     const HostNumericTables& h = GetHostNumericTables();
     float* dq = nullptr;
@@ -370,11 +403,6 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p) {
 }  // namespace
 
 // ---- batch object ---------------------------------------------------------------------------------------------------
-struct BatchBuffers {
-  DevBuffer const_buf, work_buf, scratch_buf, meta_buf, stage_out, final_out;
-  PinnedBuffer staging, status_host;
-};
-
 struct Batch {
   DeviceContext* ctx = nullptr;
   int api_level = 34;
@@ -386,6 +414,7 @@ struct Batch {
   std::vector<StreamJob> jobs_lane_groups, jobs_lane_mod;     // groups taken by the lane-parallel AC kernel (+ their modular tails)
   std::vector<AcCtaJob> jobs_ac_cta;
   uint32_t ac_smem_code_bytes = 0;
+  bool ac_fast = true;        // every lane-decoded image has an alias-table (ANS) AC code
   ScratchLayout sl_single{}, sl_lf{}, sl_grp{};
   size_t const_total = 0, work_total = 0, stage_total = 0, final_total = 0, meta_total = 0;
   uint32_t nframes = 0, status_total = 0;
@@ -399,8 +428,22 @@ struct Batch {
   const AcCtaJob* jobs_ac_cta_d = nullptr;
   BatchBuffers own;           // buffers owned by this batch
   BatchBuffers* buf = nullptr;
-  cudaEvent_t ev[10]{};
-  bool events = false;
+  // streams: a slot's (one-shot decodes) or the batch's own (prepared batches, so that two prepared batches overlap)
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  bool own_streams = false;
+  std::mutex mu;              // serialises Run / Finish / Fetch on this batch
+  // Event sets: ev = the set of the current run.  Asynchronous runs (RunBatch(sync = false)) rotate through kEventSets
+  // sets so that the stage times of every run can still be read after the final wait.
+  static constexpr int kEventSets = 16;
+  cudaEvent_t ev_ring[kEventSets][10]{};
+  cudaEvent_t* ev = ev_ring[0];
+  int pending_runs = 0, run_index = 0;
+  double stage_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int stage_runs = 0;
+  cudaEvent_t span_start = nullptr, span_end = nullptr;  // first run start / last run end since ResetStats
+  bool span_armed = true;
+  bool events = false, upload_timed = false;
+  bool finished[kEventSets] = {};
   // e2e path: pinned host destinations; image i is copied out on the copy stream as soon as its last kernel is done,
   // so the download of image i overlaps the reconstruction of image i + 1
   std::vector<void*> host_dst;
@@ -410,7 +453,14 @@ struct Batch {
 
   ~Batch() {
     if (events)
-      for (auto& e : ev) cudaEventDestroy(e);
+      for (auto& set : ev_ring)
+        for (auto& e : set) cudaEventDestroy(e);
+    if (span_start) cudaEventDestroy(span_start);
+    if (span_end) cudaEventDestroy(span_end);
+    if (own_streams) {
+      if (stream) cudaStreamDestroy(stream);
+      if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
     for (auto& e : img_ev)
       if (e) cudaEventDestroy(e);
     for (void* h : host_dst)
@@ -451,7 +501,8 @@ struct Batch {
       work_total += Align256(p.plan.work_bytes);
       p.stage_stride = Align256((size_t) p.md.xsize * 4 * (p.out16 ? 2 : 1));
       p.stage_off = stage_total;
-      stage_total += Align256(p.stage_stride * p.md.ysize);
+      // the fused VarDCT kernel packs straight into final_out; only modular frames (and the unfused debug path) stage RGBA
+      if (p.plan.proto.encoding != 0 || UseUnfusedFilters()) stage_total += Align256(p.stage_stride * p.md.ysize);
       final_bytes[i] = (size_t) p.md.xsize * FormatBytesPerPixel((uint32_t) p.format) * p.md.ysize;
       final_off[i] = final_total;
       final_total += Align256(final_bytes[i]);
@@ -469,7 +520,10 @@ struct Batch {
         if (f.encoding == 0 && !p.g.ac_code.empty()) {
           const CodeHeader* chh = reinterpret_cast<const CodeHeader*>(p.g.ac_code.data());
           lane = !chh->lz77 && chh->total_bytes <= kMaxAcSmemCode && getenv("JXLB_NO_LANE_AC") == nullptr;
-          if (lane) ac_smem_code_bytes = std::max(ac_smem_code_bytes, chh->total_bytes);
+          if (lane) {
+            ac_smem_code_bytes = std::max(ac_smem_code_bytes, chh->total_bytes);
+            if (chh->use_prefix) ac_fast = false;
+          }
         }
         if (lane) {
           for (uint32_t g = 0; g < f.num_groups; ++g) jobs_lane_groups.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, 0});
@@ -526,10 +580,18 @@ struct Batch {
     buf = use ? use : &own;
     CUDA_OK(cudaSetDevice(ctx->device));
     if (!events) {
-      for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+      for (auto& set : ev_ring)
+        for (auto& e : set) CUDA_OK(cudaEventCreate(&e));
+      CUDA_OK(cudaEventCreate(&span_start));
+      CUDA_OK(cudaEventCreate(&span_end));
       events = true;
     }
-    cudaStream_t s = ctx->stream;
+    if (!stream) {
+      CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+      CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+      own_streams = true;
+    }
+    cudaStream_t s = stream;
     const size_t lf_scratch = Align256(sl_lf.bytes_per_job * jobs_lf.size());
     const size_t grp_scratch = Align256(sl_grp.bytes_per_job * std::max(jobs_groups.size(), jobs_lane_mod.size()));
     const size_t single_scratch = Align256(sl_single.bytes_per_job * jobs_single.size());
@@ -544,7 +606,7 @@ struct Batch {
     sl_lf.base = buf->scratch_buf.p;
     sl_grp.base = buf->scratch_buf.p + lf_scratch;
     sl_single.base = buf->scratch_buf.p + lf_scratch + grp_scratch;
-    CUDA_OK(cudaEventRecord(ev[0], s));
+    CUDA_OK(cudaEventRecord(ev_ring[0][0], s));
     uint8_t* stg = buf->staging.p;
     frames.assign(nframes, FrameDev());
     ParallelFor(n, [&](size_t i) {
@@ -577,7 +639,7 @@ struct Batch {
     jobs_lane_groups_d = jd + lgo;
     jobs_lane_mod_d = jd + lmo;
     jobs_ac_cta_d = reinterpret_cast<const AcCtaJob*>(jd + aco);
-    CUDA_OK(cudaEventRecord(ev[1], s));
+    CUDA_OK(cudaEventRecord(ev_ring[0][1], s));
     uploaded = true;
   }
 
@@ -593,10 +655,20 @@ struct Batch {
     }
   }
 
-  // All kernels, from the uploaded codestreams to packed pixels in HBM.  Asynchronous on ctx->stream.
+  // All kernels, from the uploaded codestreams to packed pixels in HBM.  Asynchronous on this batch's stream.
   void Run() {
     CUDA_OK(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = stream;
+    if (pending_runs >= kEventSets) CollectRuns();  // the ring is full: drain (synchronises)
+    if (pending_runs > 0) {                          // keep the upload events of set 0 readable from every set
+      run_index = (run_index + 1) % kEventSets;
+    }
+    ev = ev_ring[run_index];
+    ++pending_runs;
+    if (span_armed) {
+      CUDA_OK(cudaEventRecord(span_start, s));
+      span_armed = false;
+    }
     CUDA_OK(cudaEventRecord(ev[2], s));
     for (size_t i = 0; i < n; ++i) {
       Parsed& p = ps[i];
@@ -606,11 +678,20 @@ struct Batch {
       if (p.plan.coef_bytes) CUDA_OK(cudaMemsetAsync(wb + p.plan.off_coef, 0, p.plan.coef_bytes, s));
     }
     LaunchSingleSectionFrames(frames_d, jobs_single_d, (uint32_t) jobs_single.size(), ctx->nat_dev, sl_single, s);
-    LaunchLfGroups(frames_d, jobs_lf_d, (uint32_t) jobs_lf.size(), sl_lf, s);
+    if (!jobs_lf.empty() && ctx->lf_tokens > 0) {
+      std::lock_guard<std::mutex> l(ctx->mu);
+      const uint64_t k = ctx->lf_count++;
+      if (k >= (uint64_t) ctx->lf_tokens)
+        CUDA_OK(cudaStreamWaitEvent(s, ctx->lf_ev[(k - ctx->lf_tokens) % DeviceContext::kLfEvents], 0));
+      LaunchLfGroups(frames_d, jobs_lf_d, (uint32_t) jobs_lf.size(), sl_lf, s);
+      CUDA_OK(cudaEventRecord(ctx->lf_ev[k % DeviceContext::kLfEvents], s));
+    } else {
+      LaunchLfGroups(frames_d, jobs_lf_d, (uint32_t) jobs_lf.size(), sl_lf, s);
+    }
     CUDA_OK(cudaEventRecord(ev[3], s));
     LaunchPassGroups(frames_d, jobs_groups_d, (uint32_t) jobs_groups.size(), ctx->nat_dev, sl_grp, s);
     LaunchBuildGroupBlocks(frames_d, jobs_lane_groups_d, (uint32_t) jobs_lane_groups.size(), s);
-    LaunchAcLanes(frames_d, jobs_ac_cta_d, (uint32_t) jobs_ac_cta.size(), ctx->nat_dev, ac_smem_code_bytes, s);
+    LaunchAcLanes(frames_d, jobs_ac_cta_d, (uint32_t) jobs_ac_cta.size(), ctx->nat_dev, ac_smem_code_bytes, ac_fast, s);
     LaunchGroupModular(frames_d, jobs_lane_mod_d, (uint32_t) jobs_lane_mod.size(), sl_grp, s);
     CUDA_OK(cudaEventRecord(ev[4], s));
     for (size_t i = 0; i < n; ++i) {
@@ -641,7 +722,7 @@ struct Batch {
         od.alpha_channel = (int32_t) (f.num_color_mod_channels + (uint32_t) ai);
         od.alpha_bits = p.md.extra[ai].bits;
       }
-      const bool fused = f.encoding == 0 && getenv("JXLB_SIMPLE_FILTERS") == nullptr;
+      const bool fused = f.encoding == 0 && !UseUnfusedFilters();
       if (f.encoding == 0 && !fused) {
         int cur = LaunchFilters(f, s);
         LaunchColor(f, p.cp, ctx->nt_dev, cur ? f.xyb1 : f.xyb0, od, s);
@@ -664,17 +745,54 @@ struct Batch {
       else LaunchPack(pk, s);
       if (i < host_dst.size() && host_dst[i]) {
         CUDA_OK(cudaEventRecord(img_ev[i], s));
-        CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, img_ev[i], 0));
-        CUDA_OK(cudaMemcpyAsync(host_dst[i], buf->final_out.p + final_off[i], final_bytes[i], cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CUDA_OK(cudaStreamWaitEvent(copy_stream, img_ev[i], 0));
+        CUDA_OK(cudaMemcpyAsync(host_dst[i], buf->final_out.p + final_off[i], final_bytes[i], cudaMemcpyDeviceToHost, copy_stream));
       }
     }
     CUDA_OK(cudaEventRecord(ev[7], s));
+    CUDA_OK(cudaEventRecord(span_end, s));
     ran = true;
+  }
+
+  // Waits for every run issued so far and reads its stage times (stage_ms = the last run, stage_sum / stage_runs = all).
+  // ms: [0] upload, [1] LF sections, [2] group sections, [3] LF final, [4] inverse transforms, [5] filters+colour+pack,
+  //     [6] download, [7] all kernels
+  void CollectRuns() {
+    CUDA_OK(cudaStreamSynchronize(stream));
+    for (int k = pending_runs - 1; k >= 0; --k) {
+      const int set = ((run_index - k) % kEventSets + kEventSets) % kEventSets;
+      cudaEvent_t* e = ev_ring[set];
+      auto el = [&](cudaEvent_t a, cudaEvent_t b) {
+        float v = 0;
+        if (cudaEventElapsedTime(&v, a, b) != cudaSuccess) {
+          cudaGetLastError();
+          v = 0;
+        }
+        return v;
+      };
+      stage_ms[0] = upload_timed ? 0.f : el(ev_ring[0][0], ev_ring[0][1]);
+      upload_timed = true;
+      stage_ms[1] = el(e[2], e[3]);
+      stage_ms[2] = el(e[3], e[4]);
+      stage_ms[3] = el(e[4], e[5]);
+      stage_ms[4] = el(e[5], e[6]);
+      stage_ms[5] = el(e[6], e[7]);
+      stage_ms[6] = finished[set] ? el(e[7], e[8]) : 0.f;
+      stage_ms[7] = el(e[2], e[7]);
+      finished[set] = false;
+      if (ctx->timeline)
+        fprintf(stderr, "[timeline] batch %p run: start %.2f lf_done %.2f groups_done %.2f lf_final_done %.2f recon_done %.2f filter_done %.2f ms\n",
+                (void*) this, el(ctx->origin, e[2]), el(ctx->origin, e[3]), el(ctx->origin, e[4]), el(ctx->origin, e[5]),
+                el(ctx->origin, e[6]), el(ctx->origin, e[7]));
+      for (int i = 0; i < 8; ++i) stage_sum[i] += stage_ms[i];
+      ++stage_runs;
+    }
+    pending_runs = 0;
   }
 
   // Downloads the per-stream statuses (and, if host_out, the pixels), synchronises and resolves per-image status.
   void Finish(bool to_host, int output_device, std::vector<DecodedImage>* out) {
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = stream;
     uint32_t* sh = reinterpret_cast<uint32_t*>(buf->status_host.p);
     for (size_t i = 0; i < n; ++i) {
       Parsed& p = ps[i];
@@ -707,31 +825,18 @@ struct Batch {
       }
     }
     if (to_host) {  // the decode stream's timeline ends when the copy stream has drained
-      CUDA_OK(cudaEventRecord(ev[9], ctx->copy_stream));
+      CUDA_OK(cudaEventRecord(ev[9], copy_stream));
       CUDA_OK(cudaStreamWaitEvent(s, ev[9], 0));
     }
     CUDA_OK(cudaEventRecord(ev[8], s));
-    CUDA_OK(cudaStreamSynchronize(s));
-    // ms: [0] upload, [1] LF sections, [2] group sections, [3] LF final, [4] inverse transforms, [5] filters+colour+pack, [6] download
-    auto el = [&](int a, int b) {
-      float v = 0;
-      cudaEventElapsedTime(&v, ev[a], ev[b]);
-      return v;
-    };
-    tm.ms[0] = el(0, 1);
-    tm.ms[1] = el(2, 4);
-    tm.ms[2] = el(4, 6);
-    tm.ms[3] = el(6, 7);
-    tm.ms[4] = el(7, 8);
-    tm.ms[5] = el(2, 8);
-    stage_ms[0] = el(0, 1);
-    stage_ms[1] = el(2, 3);
-    stage_ms[2] = el(3, 4);
-    stage_ms[3] = el(4, 5);
-    stage_ms[4] = el(5, 6);
-    stage_ms[5] = el(6, 7);
-    stage_ms[6] = el(7, 8);
-    stage_ms[7] = el(2, 7);
+    finished[run_index] = true;
+    CollectRuns();
+    tm.ms[0] = stage_ms[0];
+    tm.ms[1] = stage_ms[1] + stage_ms[2];
+    tm.ms[2] = stage_ms[3] + stage_ms[4];
+    tm.ms[3] = stage_ms[5];
+    tm.ms[4] = stage_ms[6];
+    tm.ms[5] = stage_ms[7] + stage_ms[6];
     const int32_t* shs = reinterpret_cast<const int32_t*>(buf->status_host.p);
     for (size_t i = 0; i < n; ++i) {
       Parsed& p = ps[i];
@@ -798,11 +903,20 @@ void FreeImageMemory(void* data, int device) {
 }
 
 namespace {
-BatchBuffers* SpareBuffers(DeviceContext* ctx) {
-  static std::map<DeviceContext*, std::unique_ptr<BatchBuffers>> spare;
-  auto& b = spare[ctx];
-  if (!b) b.reset(new BatchBuffers());
-  return b.get();
+// Picks a decode slot: a free one if there is one, else waits for the next in round-robin order.
+Slot* AcquireSlot(DeviceContext* ctx, std::unique_lock<std::mutex>* lock) {
+  const uint32_t first = ctx->next_slot.fetch_add(1);
+  for (int k = 0; k < kSlots; ++k) {
+    Slot* sl = &ctx->slots[(first + k) % kSlots];
+    std::unique_lock<std::mutex> l(sl->mu, std::try_to_lock);
+    if (l.owns_lock()) {
+      *lock = std::move(l);
+      return sl;
+    }
+  }
+  Slot* sl = &ctx->slots[first % kSlots];
+  *lock = std::unique_lock<std::mutex>(sl->mu);
+  return sl;
 }
 void CopyStatuses(const Batch& b, std::vector<DecodedImage>* out, int* overall) {
   for (size_t i = 0; i < b.n; ++i) {
@@ -831,9 +945,12 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
     CopyStatuses(b, out, &overall);
     return overall;
   }
-  std::lock_guard<std::mutex> lock(b.ctx->mu);
+  std::unique_lock<std::mutex> lock;
+  Slot* slot = AcquireSlot(b.ctx, &lock);
+  b.stream = slot->stream;
+  b.copy_stream = slot->copy_stream;
   try {
-    b.Upload(SpareBuffers(b.ctx));
+    b.Upload(&slot->spare);
     if (output_device < 0) b.PrepareHostOutputs();
     b.Run();
     b.Finish(output_device < 0, output_device, out);
@@ -854,10 +971,9 @@ Batch* PrepareBatch(const jxlb_request* reqs, size_t n, int api_level, int devic
   status->assign(n, 0);
   try {
     b->ctx = GetContext(device);
-    std::lock_guard<std::mutex> lock(b->ctx->mu);
     if (b->AnyOk()) {
       b->Upload(nullptr);
-      CUDA_OK(cudaStreamSynchronize(b->ctx->stream));
+      CUDA_OK(cudaStreamSynchronize(b->stream));
     }
   } catch (CudaError& e) {
     for (auto& p : b->ps)
@@ -870,7 +986,7 @@ Batch* PrepareBatch(const jxlb_request* reqs, size_t n, int api_level, int devic
 
 int RunBatch(Batch* b, bool sync) {
   if (!b || !b->uploaded) return JXLB_ERROR;
-  std::lock_guard<std::mutex> lock(b->ctx->mu);
+  std::lock_guard<std::mutex> lock(b->mu);
   try {
     b->Run();
     if (sync) b->Finish(false, 0, nullptr);
@@ -889,12 +1005,12 @@ int FetchBatchImage(Batch* b, size_t i, DecodedImage* out) {
   out->status = p.status;
   out->message = p.message;
   if (p.status != JXLB_OK) return p.status;
-  std::lock_guard<std::mutex> lock(b->ctx->mu);
+  std::lock_guard<std::mutex> lock(b->mu);
   void* h = Pool().Get(b->final_bytes[i]);
   if (!h) return JXLB_OOM;
   cudaSetDevice(b->ctx->device);
-  if (cudaMemcpyAsync(h, b->buf->final_out.p + b->final_off[i], b->final_bytes[i], cudaMemcpyDeviceToHost, b->ctx->stream) != cudaSuccess ||
-      cudaStreamSynchronize(b->ctx->stream) != cudaSuccess) {
+  if (cudaMemcpyAsync(h, b->buf->final_out.p + b->final_off[i], b->final_bytes[i], cudaMemcpyDeviceToHost, b->stream) != cudaSuccess ||
+      cudaStreamSynchronize(b->stream) != cudaSuccess) {
     Pool().Put(h);
     return JXLB_ERROR_NO_DEVICE;
   }
@@ -917,7 +1033,44 @@ const void* BatchDevicePixels(const Batch* b, size_t i, size_t* bytes) {
   if (bytes) *bytes = b->final_bytes[i];
   return b->buf->final_out.p + b->final_off[i];
 }
-cudaStream_t BatchStream(const Batch* b) { return b->ctx->stream; }
+cudaStream_t BatchStream(const Batch* b) { return b->stream; }
+
+// Waits for every asynchronous run of the batch (RunBatch(b, false)) and resolves its status like a synchronous run.
+int WaitBatch(Batch* b) {
+  if (!b || !b->uploaded || !b->ran) return JXLB_ERROR;
+  std::lock_guard<std::mutex> lock(b->mu);
+  try {
+    b->Finish(false, 0, nullptr);
+  } catch (CudaError& e) {
+    cudaGetLastError();
+    return JXLB_ERROR_NO_DEVICE;
+  }
+  for (auto& p : b->ps)
+    if (p.status != JXLB_OK) return p.status;
+  return JXLB_OK;
+}
+void ResetBatchStats(Batch* b) {
+  if (!b) return;
+  std::lock_guard<std::mutex> lock(b->mu);
+  for (double& v : b->stage_sum) v = 0;
+  b->stage_runs = 0;
+  b->span_armed = true;
+}
+// Device time from the start of `first`'s first run since its last ResetBatchStats to the end of `last`'s latest run
+// (both must have completed: call WaitBatch on them first).  Negative on error.
+float BatchSpanMs(const Batch* first, const Batch* last) {
+  if (!first || !last || !first->span_start || !last->span_end) return -1.f;
+  float v = 0;
+  if (cudaEventElapsedTime(&v, first->span_start, last->span_end) != cudaSuccess) {
+    cudaGetLastError();
+    return -1.f;
+  }
+  return v;
+}
+void BatchStageMsMean(const Batch* b, float* ms8, int* runs) {
+  for (int i = 0; i < 8; ++i) ms8[i] = (b && b->stage_runs) ? (float) (b->stage_sum[i] / b->stage_runs) : 0.f;
+  if (runs) *runs = b ? b->stage_runs : 0;
+}
 void FreeBatch(Batch* b) { delete b; }
 
 }  // namespace jxlb

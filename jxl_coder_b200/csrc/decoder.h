@@ -23,7 +23,8 @@ struct BatchTimings {
   float ms[6] = {0, 0, 0, 0, 0, 0};
 };
 
-// Decodes n requests on CUDA device `device` (-1 = current).  Thread-safe (calls on the same device serialise).
+// Decodes n requests on CUDA device `device` (-1 = current).  Thread-safe; concurrent calls on the same device take
+// different decode slots (streams + buffers) and overlap on the GPU.
 int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device, std::vector<DecodedImage>* out,
                 BatchTimings* timings);
 
@@ -38,6 +39,12 @@ namespace jxlb {
 struct Batch;
 Batch* PrepareBatch(const jxlb_request* reqs, size_t n, int api_level, int device, std::vector<int>* status);
 int RunBatch(Batch* b, bool sync);
+// Waits for the asynchronous runs issued with RunBatch(b, false) and resolves statuses.
+int WaitBatch(Batch* b);
+// Mean stage times over every run collected so far (same layout as BatchStageMs).
+void BatchStageMsMean(const Batch* b, float* ms8, int* runs);
+void ResetBatchStats(Batch* b);
+float BatchSpanMs(const Batch* first, const Batch* last);
 int FetchBatchImage(Batch* b, size_t i, DecodedImage* out);
 // ms8: [0] upload, [1] LF sections, [2] group sections, [3] LF dequant+smoothing, [4] dequant+inverse transforms,
 //      [5] filters+colour+pack, [6] download, [7] all kernels

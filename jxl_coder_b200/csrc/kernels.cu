@@ -19,9 +19,11 @@ namespace {
 std::atomic<uint64_t> g_launches{0};
 
 constexpr int kStreamBlockThreads = 32;  // one warp per section, lane 0 decodes
-// shared memory of an LF-group stream: its entropy code (context map + alias tables) and the modular decoder's rows
-constexpr uint32_t kLfFastCodeBytes = 88u << 10;
-constexpr uint32_t kLfFastInts = 4352;  // ModFastScratch::Ints(288)
+// Shared memory of an LF-group stream: only the modular decoder's rows and LUTs (17 KB).  The stream's entropy code
+// (context map + alias tables, 15-50 KB) is read through L1 instead (an L1 hit costs the same ~30 cycles as LDS), so
+// that LF-group CTAs of one batch stay co-resident with the 180 KB AC CTAs and the reconstruction CTAs of another.
+constexpr uint32_t kLfFastCodeBytes = 0;
+constexpr uint32_t kLfFastInts = 3968;  // >= ModFastScratch::Ints(256) = 3948 (an LF group is at most 256 cells wide)
 
 struct SyncThreads {
   __device__ void operator()() const { __syncthreads(); }
@@ -114,7 +116,9 @@ __global__ void __launch_bounds__(kReconThreads) ReconRegionKernel(const FrameDe
 
 // One CTA per 64x64 region; it reconstructs the blocks whose top-left cell lies in the region but which are not
 // contained in it (larger than 64 pixels, or straddling a region border) -- rare, so most CTAs exit after the scan.
-__global__ void __launch_bounds__(256) ReconLargeKernel(const FrameDev f, const NumericTables* nt) {
+// 128 threads x <= 128 registers: a CTA must fit beside the LF-group CTAs of another batch that overlap it (a 256-thread
+// CTA at 254 registers needs a whole SM's register file and would stall its stream until an SM drains).
+__global__ void __launch_bounds__(128, 4) ReconLargeKernel(const FrameDev f, const NumericTables* nt) {
   __shared__ uint32_t todo[64];
   __shared__ uint32_t ntodo;
   if (threadIdx.x == 0) ntodo = 0;
@@ -191,6 +195,9 @@ void LaunchLfGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njob
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(LfGroupKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    // same (maximal) shared-memory carve-out for every long-running kernel: CTAs of kernels with different carve-outs
+    // cannot share an SM, which would serialise the batches that overlap on different streams
+    cudaFuncSetAttribute(LfGroupKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   LfGroupKernel<<<njobs, kStreamBlockThreads, smem, stream>>>(frames, jobs, njobs, scratch);
@@ -212,11 +219,20 @@ void LaunchRecon(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t st
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(ReconRegionKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(RegionShared));
+    // same (maximal) shared-memory carve-out for every long-running kernel: CTAs of kernels with different carve-outs
+    // cannot share an SM, which would serialise the batches that overlap on different streams
+    cudaFuncSetAttribute(ReconRegionKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   dim3 grid((f.w8 + kRegionCells - 1) / kRegionCells, (f.h8 + kRegionCells - 1) / kRegionCells, 1);
+  static bool large_configured = false;
+  if (!large_configured) {
+    cudaFuncSetAttribute(ReconLargeKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(LfFinalKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    large_configured = true;
+  }
   ReconRegionKernel<<<grid, kReconThreads, sizeof(RegionShared), stream>>>(f, nt_dev);
-  ReconLargeKernel<<<grid, 256, 0, stream>>>(f, nt_dev);
+  ReconLargeKernel<<<grid, 128, 0, stream>>>(f, nt_dev);
   g_launches += 2;
 }
 

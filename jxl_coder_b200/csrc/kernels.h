@@ -44,7 +44,7 @@ struct AcCtaJob {
 void LaunchBuildGroupBlocks(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, cudaStream_t stream);
 uint32_t AcLaneSmemBytes(uint32_t code_bytes);
 void LaunchAcLanes(const FrameDev* frames, const AcCtaJob* jobs, uint32_t njobs, NaturalOrders nat, uint32_t smem_code_bytes,
-                   cudaStream_t stream);
+                   bool fast, cudaStream_t stream);
 void LaunchGroupModular(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, ScratchLayout scratch, cudaStream_t stream);
 
 // Numeric stages of one VarDCT frame (FrameDev passed by value).

@@ -21,7 +21,7 @@ std::atomic<uint64_t> g_launches_ac{0};
 
 namespace {
 
-constexpr int kAcCtaThreads = 128;
+constexpr int kAcCtaGroups = 128;  // groups per CTA (all of the same image)
 constexpr uint32_t kTopBytesPerLane = 96;  // 3 channels x 32 columns of the non-zero context row
 
 __global__ void __launch_bounds__(128) BuildGroupBlocksKernel(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs) {
@@ -53,8 +53,78 @@ struct AcTables {
   uint8_t freq[64];
 };
 
-__global__ void __launch_bounds__(kAcCtaThreads) AcLaneKernel(const FrameDev* frames, const AcCtaJob* jobs, NaturalOrders nat,
-                                                              uint32_t smem_code_bytes) {
+// Bit reader of one lane: like BitReader, plus a one-word lookahead so that a refill never waits for memory (the load
+// issued by refill n is consumed by refill n + 1).  Lanes refill at different iterations; keeping the load off the
+// critical path is what stops one lane's L2 miss from stalling the other lanes of its warp.
+struct LaneBits {
+  const uint32_t* words;
+  uint64_t buf;
+  uint32_t nbits, widx, wend, nextw;
+  __device__ __forceinline__ void From(const BitReader& br) {
+    words = br.words;
+    buf = br.buf;
+    nbits = br.nbits;
+    widx = br.widx;
+    wend = br.wend;
+    nextw = widx < wend ? __ldg(words + widx) : 0u;
+  }
+  __device__ __forceinline__ uint64_t Position() const { return (uint64_t) widx * 32 - nbits; }
+  __device__ __forceinline__ void Refill() {
+    if (nbits <= 32) {
+      buf |= (uint64_t) nextw << nbits;
+      nbits += 32;
+      ++widx;
+      nextw = widx < wend ? __ldg(words + widx) : 0u;
+    }
+  }
+  __device__ __forceinline__ uint32_t Read(uint32_t n) {  // n <= 32
+    Refill();
+    const uint32_t v = (uint32_t) (buf & ((1ull << n) - 1));
+    buf >>= n;
+    nbits -= n;
+    return v;
+  }
+};
+
+// One hybrid integer of context `ctx` from an alias-table (ANS) code held in shared memory.
+__device__ __forceinline__ uint32_t LaneReadUint(LaneBits& lb, uint32_t& state, const uint8_t* ctx_map, const uint2* alias,
+                                                 const HybridCfg* cfgs, uint32_t log_alpha, uint32_t log_entry, uint32_t ctx) {
+  const uint32_t cluster = ctx_map[ctx];
+  const uint32_t res = state & (kAnsTabSize - 1);
+  const uint32_t bucket = res >> log_entry;
+  const uint32_t pos = res & ((1u << log_entry) - 1);
+  const uint2 e = alias[(cluster << log_alpha) + bucket];  // {cutoff | right << 8 | freq0 << 16, offset1 | freq1 << 16}
+  const HybridCfg cfg = cfgs[cluster];
+  const bool hi = pos >= (e.x & 0xFFu);
+  const uint32_t sym = hi ? ((e.x >> 8) & 0xFFu) : bucket;
+  const uint32_t off = hi ? (e.y & 0xFFFFu) + pos : pos;
+  const uint32_t freq = hi ? (e.y >> 16) : (e.x >> 16);
+  uint32_t st = freq * (state >> kAnsTabBits) + off;
+  if (st < (1u << 16)) {
+    lb.Refill();
+    st = (st << 16) | (uint32_t) (lb.buf & 0xFFFFu);
+    lb.buf >>= 16;
+    lb.nbits -= 16;
+  }
+  state = st;
+  const uint32_t split = 1u << cfg.split_exp;
+  if (sym < split) return sym;
+  const uint32_t in_token = (uint32_t) cfg.msb + cfg.lsb;
+  uint32_t nbits = cfg.split_exp - in_token + ((sym - split) >> in_token);
+  if (nbits > 31) nbits = 31;
+  const uint32_t low = sym & ((1u << cfg.lsb) - 1);
+  const uint32_t tok = sym >> cfg.lsb;
+  const uint32_t bits = lb.Read(nbits);
+  return ((((1u << cfg.msb) | (tok & ((1u << cfg.msb) - 1))) << nbits | bits) << cfg.lsb) | low;
+}
+
+// kLanes = groups per warp (the other lanes idle): fewer groups per warp means more warps per SM to hide the latency
+// of each lane's dependency chain, and fewer divergent paths to serialise inside a warp.
+// kFast: alias-table code staged in shared memory (the common case); otherwise the general symbol reader is used.
+template <int kLanes, bool kFast>
+__global__ void __launch_bounds__(kAcCtaGroups * 32 / kLanes) AcLaneKernel(const FrameDev* frames, const AcCtaJob* jobs, NaturalOrders nat,
+                                                                           uint32_t smem_code_bytes) {
+  constexpr int kThreads = kAcCtaGroups * 32 / kLanes;
   extern __shared__ uint4 smem4[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
   const AcCtaJob job = jobs[blockIdx.x];
@@ -66,19 +136,21 @@ __global__ void __launch_bounds__(kAcCtaThreads) AcLaneKernel(const FrameDev* fr
   const bool in_smem = blob_bytes <= smem_code_bytes;
   if (in_smem) {
     const uint4* src = reinterpret_cast<const uint4*>(f.ac_code);
-    for (uint32_t i = tid; i < blob_bytes / 16; i += kAcCtaThreads) smem4[i] = src[i];
+    for (uint32_t i = tid; i < blob_bytes / 16; i += kThreads) smem4[i] = src[i];
   }
   AcTables* tabs = reinterpret_cast<AcTables*>(smem + smem_code_bytes);
   if (tid < 64) {
     tabs->nnz[tid] = (uint8_t) ZeroDensityNnzCtx(tid);
     tabs->freq[tid] = (uint8_t) ZeroDensityFreqCtx(tid);
   }
-  uint8_t* top = smem + smem_code_bytes + sizeof(AcTables) + tid * kTopBytesPerLane;
   __syncthreads();
-  if (tid >= job.ngroups) return;
+  const uint32_t lane = tid & 31u, gi = (tid >> 5) * kLanes + lane;
+  if (lane >= (uint32_t) kLanes || gi >= job.ngroups) return;
+  uint8_t* top = smem + smem_code_bytes + sizeof(AcTables) + gi * kTopBytesPerLane;
   CodeView code;
-  code.Bind(in_smem ? smem : f.ac_code);
-  const uint32_t g = job.first_group + tid;
+  if (kFast) code.Bind(smem);  // the host only selects the fast kernel when every code of the batch fits (in_smem)
+  else code.Bind(in_smem ? smem : f.ac_code);
+  const uint32_t g = job.first_group + gi;
   const uint32_t gx = g % f.ngx, gy = g / f.ngx;
   const uint32_t gbx0 = gx * kGroupCells, gby0 = gy * kGroupCells;
   const uint32_t sec = 1 + f.num_lf_groups + 1 + g;
@@ -91,10 +163,19 @@ __global__ void __launch_bounds__(kAcCtaThreads) AcLaneKernel(const FrameDev* fr
   const uint32_t ctx_off = hfp * kContextsPerBlockCtx * nbc;
   SymbolReader sr;
   sr.Begin(code, br, nullptr, 0);
+  // fast path state: prefetching bit reader + the code's tables as shared-memory pointers
+  LaneBits lb;
+  lb.From(br);
+  uint32_t ans_state = sr.state;
+  const uint8_t* s_ctx_map = code.ctx_map;
+  const uint2* s_alias = reinterpret_cast<const uint2*>(code.alias);
+  const HybridCfg* s_cfg = code.cfg;
+  const uint32_t log_alpha = code.log_alpha, log_entry = code.log_entry;
   const uint32_t* blocks = f.group_blocks + (size_t) g * 1024;
   const uint32_t nblocks = status == kOk ? f.group_nblocks[g] : 0;
   const bool has_lf_thr = f.bctx.num_lf_ctx > 1;
-  const size_t cplane = (size_t) f.coef_h * f.coef_stride;
+  const uint32_t coef_stride = f.coef_stride;
+  const size_t cplane = (size_t) f.coef_h * coef_stride;
   // per-block state
   uint32_t bi = 0, ci = 0;
   uint32_t bx = 0, by = 0, t = 0, q = 1, cx = 1, covered = 1, l2 = 0, size = 64, ord = 0, kc_log = 3, lf_idx = 0;
@@ -107,6 +188,7 @@ __global__ void __launch_bounds__(kAcCtaThreads) AcLaneKernel(const FrameDev* fr
   while (bi < nblocks) {
     uint32_t ctx;
     uint8_t* tp = top + c * 32;
+    uint32_t pos_pref = 0;
     if (!in_coeffs) {
       if (ci == 0) {
         const uint32_t e = blocks[bi];
@@ -146,10 +228,16 @@ __global__ void __launch_bounds__(kAcCtaThreads) AcLaneKernel(const FrameDev* fr
       ctx = ctx_off + nzc * nbc + bc;
       h0 = ctx_off + nbc * kNonZeroBuckets + kZeroDensityContexts * bc;
     } else {
+      pos_pref = __ldg(order + k);  // used only if this coefficient is non-zero; issued early to hide its latency
       const uint32_t nl = (nz + covered - 1) >> l2;
       ctx = h0 + ((uint32_t) tabs->nnz[nl] + tabs->freq[k >> l2]) * 2 + prev;
     }
-    const uint32_t u = ReadHybridUint(code, sr, br, ctx);
+    uint32_t u;
+    if (kFast) {
+      u = LaneReadUint(lb, ans_state, s_ctx_map, s_alias, s_cfg, log_alpha, log_entry, ctx);
+    } else {
+      u = ReadHybridUint(code, sr, br, ctx);
+    }
     bool advance = false;
     if (!in_coeffs) {
       nz = u;
@@ -167,7 +255,7 @@ __global__ void __launch_bounds__(kAcCtaThreads) AcLaneKernel(const FrameDev* fr
         prev = nz > size / 16 ? 0 : 1;
         const uint32_t ooff = f.orders.offset[ord][c];
         order = (ooff & kOrderInFramePool) ? f.order_pool + (ooff & ~kOrderInFramePool) : nat.pool + ooff;
-        plane = f.coef + c * cplane + (size_t) (gby0 + by) * 8 * f.coef_stride + (gbx0 + bx) * 8;
+        plane = f.coef + c * cplane + (size_t) (gby0 + by) * 8 * coef_stride + (gbx0 + bx) * 8;
       }
     } else {
       if (u) {
@@ -176,14 +264,14 @@ __global__ void __launch_bounds__(kAcCtaThreads) AcLaneKernel(const FrameDev* fr
           status = kErrUnsupported;
           break;
         }
-        const uint32_t pos = order[k];
+        const uint32_t pos = pos_pref;
         uint32_t r = pos >> kc_log, col = pos & ((1u << kc_log) - 1);
         if (tall) {
           const uint32_t tmp = r;
           r = col;
           col = tmp;
         }
-        plane[(size_t) r * f.coef_stride + col] = (int16_t) v;
+        plane[(size_t) r * coef_stride + col] = (int16_t) v;
       }
       prev = u != 0 ? 1 : 0;
       nz -= prev;
@@ -203,9 +291,19 @@ __global__ void __launch_bounds__(kAcCtaThreads) AcLaneKernel(const FrameDev* fr
       }
     }
   }
-  if (status == kOk && !sr.FinalStateOk()) status = kErrBadStream;
-  if (status == kOk && br.Overrun()) status = kErrTruncated;
-  f.group_ac_end_bit[g] = br.Position();
+  uint64_t end_pos;
+  bool overrun;
+  if (kFast) {
+    if (status == kOk && ans_state != (kAnsSignature << 16)) status = kErrBadStream;
+    end_pos = lb.Position();
+    overrun = end_pos > br.end_bit;
+  } else {
+    if (status == kOk && !sr.FinalStateOk()) status = kErrBadStream;
+    end_pos = br.Position();
+    overrun = br.Overrun();
+  }
+  if (status == kOk && overrun) status = kErrTruncated;
+  f.group_ac_end_bit[g] = end_pos;
   f.status[f.num_lf_groups + g] = status;
 }
 
@@ -241,20 +339,46 @@ void LaunchBuildGroupBlocks(const FrameDev* frames, const StreamJob* jobs, uint3
 }
 
 uint32_t AcLaneSmemBytes(uint32_t code_bytes) {
-  return ((code_bytes + 15u) & ~15u) + (uint32_t) sizeof(AcTables) + kAcCtaThreads * kTopBytesPerLane;
+  return ((code_bytes + 15u) & ~15u) + (uint32_t) sizeof(AcTables) + kAcCtaGroups * kTopBytesPerLane;
 }
 
+namespace {
+template <int kLanes, bool kFast>
+void LaunchAcLanesT(const FrameDev* frames, const AcCtaJob* jobs, uint32_t njobs, NaturalOrders nat, uint32_t smem_code_bytes,
+                    uint32_t smem, cudaStream_t stream) {
+  static uint32_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(AcLaneKernel<kLanes, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    configured = smem;
+  }
+  AcLaneKernel<kLanes, kFast><<<njobs, kAcCtaGroups * 32 / kLanes, smem, stream>>>(frames, jobs, nat, smem_code_bytes);
+}
+int AcLanesPerWarp() {
+  static int v = [] {
+    const char* e = getenv("JXLB_AC_LANES");
+    const int n = e ? atoi(e) : 8;
+    return (n == 32 || n == 16 || n == 8 || n == 4) ? n : 8;
+  }();
+  return v;
+}
+}  // namespace
+
+// fast: every job's AC code is an alias-table (ANS) code that fits the shared-memory budget.
 void LaunchAcLanes(const FrameDev* frames, const AcCtaJob* jobs, uint32_t njobs, NaturalOrders nat, uint32_t smem_code_bytes,
-                   cudaStream_t stream) {
+                   bool fast, cudaStream_t stream) {
   if (!njobs) return;
   smem_code_bytes = (smem_code_bytes + 15u) & ~15u;
   const uint32_t smem = AcLaneSmemBytes(smem_code_bytes);
-  static uint32_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(AcLaneKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    configured = smem;
+  if (!fast) {
+    LaunchAcLanesT<32, false>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream);
+  } else {
+    switch (AcLanesPerWarp()) {
+      case 32: LaunchAcLanesT<32, true>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
+      case 16: LaunchAcLanesT<16, true>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
+      case 4: LaunchAcLanesT<4, true>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
+      default: LaunchAcLanesT<8, true>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
+    }
   }
-  AcLaneKernel<<<njobs, kAcCtaThreads, smem, stream>>>(frames, jobs, nat, smem_code_bytes);
   ++g_launches_ac;
 }
 

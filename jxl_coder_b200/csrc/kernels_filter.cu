@@ -159,6 +159,9 @@ void LaunchFilterColorPack(const FrameDev& f, const ColorParams& cp, const Numer
   static size_t configured = 0;
   if (smem > configured) {
     cudaFuncSetAttribute(FilterColorKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    // same (maximal) shared-memory carve-out for every long-running kernel: CTAs of kernels with different carve-outs
+    // cannot share an SM, which would serialise the batches that overlap on different streams
+    cudaFuncSetAttribute(FilterColorKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = smem;
   }
   FilterParams fp;

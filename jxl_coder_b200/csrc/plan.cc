@@ -1,10 +1,18 @@
 #include "plan.h"
 
+#include <cstdlib>
+
 #include <cstring>
 
 #include "vardct_sections.h"
 
 namespace jxlb {
+
+bool UseUnfusedFilters() {
+  static const bool v = getenv("JXLB_SIMPLE_FILTERS") != nullptr;
+  return v;
+}
+
 
 namespace {
 size_t Align(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
@@ -112,7 +120,8 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
     p.off_coef = take(p.coef_bytes);
     p.off_lf = take((size_t) 3 * f.h8 * f.lf_stride * 4);
     p.off_xyb0 = take((size_t) 3 * f.plane_h * f.plane_stride * 4);
-    p.off_xyb1 = take((size_t) 3 * f.plane_h * f.plane_stride * 4);
+    // second XYB buffer: only the unfused per-stage filter kernels (debug aid) ping-pong between two
+    p.off_xyb1 = UseUnfusedFilters() ? take((size_t) 3 * f.plane_h * f.plane_stride * 4) : p.off_xyb0;
   }
   if (f.num_mod_channels) p.off_mod = take((size_t) f.num_mod_channels * f.height * f.mod_stride * 4);
   p.work_bytes = o;

@@ -24,6 +24,9 @@ struct FramePlan {
 };
 
 // Computes the plan.  cs_padded_bytes = size of the padded codestream buffer.
+// True when JXLB_SIMPLE_FILTERS is set: restoration filters run as separate per-stage kernels (debug aid) instead of the
+// fused filter + colour + pack kernel.
+bool UseUnfusedFilters();
 void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGlobals& g, size_t cs_padded_bytes, FramePlan* plan);
 
 // Serialises the const region into `dst` (plan.const_bytes bytes).

@@ -185,7 +185,8 @@ int emu_render(void* h, uint8_t* out, uint32_t stride_bytes, int bits16, float* 
     const size_t plane = (size_t) f.plane_h * f.plane_stride;
     if (xyb_idct) memcpy(xyb_idct, f.xyb0, 3 * plane * sizeof(float));
     float* src = f.xyb0;
-    float* dst = f.xyb1;
+    std::vector<float> second(3 * plane);  // the plan only carries a second XYB buffer for the unfused debug kernels
+    float* dst = second.data();
     auto run = [&](auto fn) {
       for (uint32_t y = 0; y < f.height; ++y)
         for (uint32_t x = 0; x < f.width; ++x) fn((int) x, (int) y);
