@@ -306,13 +306,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contexts", type=int, default=int(os.environ.get("JXLB_BENCH_CONTEXTS", "2")),
+    ap.add_argument("--contexts", type=int, default=int(os.environ.get("JXLB_BENCH_CONTEXTS", "4")),
                     help="prepared batches (decode contexts) alternated by the device-resident measurement")
-    ap.add_argument("--callers", type=int, default=int(os.environ.get("JXLB_BENCH_CALLERS", "2")),
+    ap.add_argument("--callers", type=int, default=int(os.environ.get("JXLB_BENCH_CALLERS", "4")),
                     help="host threads issuing jxlb_decode_batch calls in the e2e measurement")
     args = ap.parse_args()
     if args.impl == "reference":

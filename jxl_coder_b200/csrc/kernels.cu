@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) LfFinalKernel(const FrameDev f) {
 
 constexpr int kReconThreads = 192;  // 3 channels x 64 columns/rows
 
-__global__ void __launch_bounds__(kReconThreads) ReconRegionKernel(const FrameDev f, const NumericTables* nt) {
+__global__ void __launch_bounds__(kReconThreads, 4) ReconRegionKernel(const FrameDev f, const NumericTables* nt) {
   extern __shared__ __align__(16) uint8_t smem[];
   RegionShared& sh = *reinterpret_cast<RegionShared*>(smem);
   ReconRegion(f, *nt, blockIdx.x, blockIdx.y, sh, (int) threadIdx.x, (int) blockDim.x, SyncThreads());

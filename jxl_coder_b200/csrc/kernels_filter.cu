@@ -7,6 +7,8 @@
 // the colour conversion directly, so the 12 B/pixel intermediate planes between the stages never touch HBM.
 // Algorithmic HBM traffic: 12 B/px read (+ halo) + 4 B/px written (RGBA_8888).
 #include <atomic>
+#include <cstdint>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -144,6 +146,235 @@ __global__ void __launch_bounds__(kFilterThreads) FilterColorKernel(const FrameD
   }
 }
 
+
+// ---- fast path: Gaborish + one EPF iteration (stage 1) + colour + pack ------------------------------------------------
+// The configuration libjxl's encoder emits at distance ~1 (gab = 1, epf_iters = 1).  Same arithmetic, operation by
+// operation, as the generic kernel above (GaborishSample / EpfPixelT<1> / XybToEncodedRgb), restructured around
+// 4-pixel horizontal strips held in registers: every thread produces 4 adjacent outputs per stage from 128-bit shared
+// memory loads with compile-time offsets, instead of one output from ~25 scalar loads per channel with run-time strides.
+//   tile: 64 x 16 outputs; Gaborish output 68 x 20; input 70 x 22.  Shared rows are 84 floats: index = column + 8.
+constexpr int kSW = 84, kSH = 22, kSPlane = kSW * kSH;
+constexpr int kFastSmemFloats = 6 * kSPlane + 16;
+
+__device__ __forceinline__ float4 Lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float2 Lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+__global__ void __launch_bounds__(kFilterThreads, 3) FilterColorFastKernel(const FrameDev f, const FilterParams fp, const NumericTables* nt) {
+  extern __shared__ __align__(16) float fsm[];
+  float* in0 = fsm;                  // [3][kSH][kSW] input XYB (rows ty0-3 .., cols tx0-8 ..)
+  float* gb = fsm + 3 * kSPlane;     // Gaborish output, same geometry
+  float* sig = fsm + 6 * kSPlane;    // 1/sigma of the tile's 8 x 2 cells
+  const int tx0 = blockIdx.x * kTW, ty0 = blockIdx.y * kTH;
+  const int W = (int) f.width, H = (int) f.height;
+  const int tid = threadIdx.x;
+  if (tid < 16) {
+    const int cx = (tx0 >> 3) + (tid & 7), cy = (ty0 >> 3) + (tid >> 3);
+    float v = 0.0f;
+    if (cx < (int) f.w8 && cy < (int) f.h8) {
+      const size_t ci = (size_t) cy * f.w8 + cx;
+      v = EpfInvSigma(f, f.cell_hfmul[ci], f.cell_sharp[ci]);
+    }
+    sig[tid] = v;
+  }
+  // ---- load input: rows ty0-3 .. ty0+18, columns tx0-4 .. tx0+67 (needed: -3 .. 66)
+  const size_t pplane = (size_t) f.plane_h * f.plane_stride;
+  const bool interior = tx0 >= 4 && tx0 + 68 <= W && ty0 >= 3 && ty0 + 19 <= H;
+  if (interior) {
+    for (int i = tid; i < 3 * kSH * 18; i += kFilterThreads) {
+      const int q = i % 18, rc = i / 18, r = rc % kSH, c = rc / kSH;
+      const float4 v = *reinterpret_cast<const float4*>(f.xyb0 + c * pplane + (size_t) (ty0 - 3 + r) * f.plane_stride + tx0 - 4 + 4 * q);
+      *reinterpret_cast<float4*>(in0 + c * kSPlane + r * kSW + 4 + 4 * q) = v;
+    }
+  } else {
+    for (int i = tid; i < kSH * 72; i += kFilterThreads) {
+      const int lx = i % 72, r = i / 72;
+      const int gx = Mirror(tx0 - 4 + lx, W), gy = Mirror(ty0 - 3 + r, H);
+      const size_t go = (size_t) gy * f.plane_stride + gx;
+      in0[r * kSW + 4 + lx] = f.xyb0[go];
+      in0[kSPlane + r * kSW + 4 + lx] = f.xyb0[pplane + go];
+      in0[2 * kSPlane + r * kSW + 4 + lx] = f.xyb0[2 * pplane + go];
+    }
+  }
+  __syncthreads();
+  // ---- Gaborish: 18 strips (columns -4 .. 67) x 20 rows (-2 .. 17); shared row index = row + 3
+  for (int i = tid; i < 18 * 20; i += kFilterThreads) {
+    const int strip = i % 18, r = 1 + i / 18;  // r: shared row of the output
+    const int sx = 4 + 4 * strip;              // shared column of the strip's first output
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float w1 = f.rf.gab_w1[c], w2 = f.rf.gab_w2[c];
+      const float norm = 1.0f / (1.0f + 4.0f * (w1 + w2));
+      const float* p = in0 + c * kSPlane + r * kSW + sx;
+      float up[6], mid[6], dn[6];
+      {
+        const float4 a = Lds4(p - kSW), b = Lds4(p), d = Lds4(p + kSW);
+        up[0] = p[-kSW - 1]; up[1] = a.x; up[2] = a.y; up[3] = a.z; up[4] = a.w; up[5] = p[-kSW + 4];
+        mid[0] = p[-1]; mid[1] = b.x; mid[2] = b.y; mid[3] = b.z; mid[4] = b.w; mid[5] = p[4];
+        dn[0] = p[kSW - 1]; dn[1] = d.x; dn[2] = d.y; dn[3] = d.z; dn[4] = d.w; dn[5] = p[kSW + 4];
+      }
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float centre = mid[1 + j];
+        const float cross = up[1 + j] + dn[1 + j] + mid[j] + mid[2 + j];
+        const float diag = up[j] + up[2 + j] + dn[j] + dn[2 + j];
+        o[j] = (centre + w1 * cross + w2 * diag) * norm;
+      }
+      *reinterpret_cast<float4*>(gb + c * kSPlane + r * kSW + sx) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  __syncthreads();
+  // ---- EPF stage 1 on a 4-pixel strip per thread
+  const int strip = tid & 15, ry = tid >> 4;      // output row ry (0 .. 15), columns 4 * strip .. + 3
+  const int sx = 8 + 4 * strip, sr = ry + 3;      // shared column / row of the strip
+  const int x0 = tx0 + 4 * strip, y = ty0 + ry;
+  const float inv_sigma = sig[(ry >> 3) * 8 + (strip >> 1)];
+  float outv[3][4];
+  if (inv_sigma < kEpfSkipThreshold) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 v = Lds4(gb + c * kSPlane + sr * kSW + sx);
+      outv[c][0] = v.x; outv[c][1] = v.y; outv[c][2] = v.z; outv[c][3] = v.w;
+    }
+  } else {
+    float sad[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sad[j][i] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float sc = f.rf.epf_channel_scale[c];
+      const float* p = gb + c * kSPlane + sr * kSW + sx;
+      float r0[8], rm1[6], rp1[6], rm2[4], rp2[4];
+      {
+        const float2 a = Lds2(p - 2), e = Lds2(p + 4);
+        const float4 b = Lds4(p);
+        r0[0] = a.x; r0[1] = a.y; r0[2] = b.x; r0[3] = b.y; r0[4] = b.z; r0[5] = b.w; r0[6] = e.x; r0[7] = e.y;
+        const float4 m = Lds4(p - kSW), q = Lds4(p + kSW);
+        rm1[0] = p[-kSW - 1]; rm1[1] = m.x; rm1[2] = m.y; rm1[3] = m.z; rm1[4] = m.w; rm1[5] = p[-kSW + 4];
+        rp1[0] = p[kSW - 1]; rp1[1] = q.x; rp1[2] = q.y; rp1[3] = q.z; rp1[4] = q.w; rp1[5] = p[kSW + 4];
+        const float4 m2 = Lds4(p - 2 * kSW), q2 = Lds4(p + 2 * kSW);
+        rm2[0] = m2.x; rm2[1] = m2.y; rm2[2] = m2.z; rm2[3] = m2.w;
+        rp2[0] = q2.x; rp2[1] = q2.y; rp2[2] = q2.z; rp2[3] = q2.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // centre plus-shape: cc0 = r0[2+j], up = rm1[1+j], down = rp1[1+j], left = r0[1+j], right = r0[3+j]
+        const float cc0 = r0[2 + j], ccu = rm1[1 + j], ccd = rp1[1 + j], ccl = r0[1 + j], ccr = r0[3 + j];
+        float s;
+        // neighbour (0, -1)
+        s = fabsf(rm1[1 + j] - cc0);
+        s += fabsf(rm2[j] - ccu);
+        s += fabsf(r0[2 + j] - ccd);
+        s += fabsf(rm1[j] - ccl);
+        s += fabsf(rm1[2 + j] - ccr);
+        sad[j][0] += s * sc;
+        // neighbour (0, 1)
+        s = fabsf(rp1[1 + j] - cc0);
+        s += fabsf(r0[2 + j] - ccu);
+        s += fabsf(rp2[j] - ccd);
+        s += fabsf(rp1[j] - ccl);
+        s += fabsf(rp1[2 + j] - ccr);
+        sad[j][1] += s * sc;
+        // neighbour (-1, 0)
+        s = fabsf(r0[1 + j] - cc0);
+        s += fabsf(rm1[j] - ccu);
+        s += fabsf(rp1[j] - ccd);
+        s += fabsf(r0[j] - ccl);
+        s += fabsf(r0[2 + j] - ccr);
+        sad[j][2] += s * sc;
+        // neighbour (1, 0)
+        s = fabsf(r0[3 + j] - cc0);
+        s += fabsf(rm1[2 + j] - ccu);
+        s += fabsf(rp1[2 + j] - ccd);
+        s += fabsf(r0[2 + j] - ccl);
+        s += fabsf(r0[4 + j] - ccr);
+        sad[j][3] += s * sc;
+      }
+    }
+    float wgt[4][4], inv[4];
+    const bool yborder = (y & 7) == 0 || (y & 7) == 7;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float sm = 1.65f;
+      const int xm = (x0 + j) & 7;
+      if (xm == 0 || xm == 7 || yborder) sm *= f.rf.epf_border_sad_mul;
+      const float isg = inv_sigma * sm;
+      float wsum = 1.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float w = 1.0f + sad[j][i] * isg;
+        if (w < 0.0f) w = 0.0f;
+        wsum += w;
+        wgt[j][i] = w;
+      }
+      inv[j] = 1.0f / wsum;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* p = gb + c * kSPlane + sr * kSW + sx;
+      const float4 m = Lds4(p - kSW), b = Lds4(p), q = Lds4(p + kSW);
+      const float up[4] = {m.x, m.y, m.z, m.w}, dn[4] = {q.x, q.y, q.z, q.w};
+      const float mid[6] = {p[-1], b.x, b.y, b.z, b.w, p[4]};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = mid[1 + j];
+        a += wgt[j][0] * up[j];
+        a += wgt[j][1] * dn[j];
+        a += wgt[j][2] * mid[j];
+        a += wgt[j][3] * mid[2 + j];
+        outv[c][j] = a * inv[j];
+      }
+    }
+  }
+  // ---- colour + pack
+  if (y >= H || x0 >= W) return;
+  uint32_t px[4][4];
+  float dith[4] = {0.f, 0.f, 0.f, 0.f};
+  if (!fp.out16) {
+    const float4 d = *reinterpret_cast<const float4*>(nt->dither + (y & 31) * 32 + (x0 & 31));
+    dith[0] = d.x; dith[1] = d.y; dith[2] = d.z; dith[3] = d.w;
+  }
+  const uint32_t maxout = fp.out16 ? 65535u : 255u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float rgb[3];
+    XybToEncodedRgb(outv[0][j], outv[1][j], outv[2][j], fp.cp, rgb);
+    if (fp.out16) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float sv = rgb[c] * 65535.0f;
+        sv = sv < 0.0f ? 0.0f : sv > 65535.0f ? 65535.0f : sv;
+        px[j][c] = (uint32_t) rintf(sv);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) px[j][c] = ToU8Dithered(rgb[c], dith[j]);
+    }
+    if (fp.cp.grey) px[j][0] = px[j][2] = px[j][1];
+    px[j][3] = maxout;
+  }
+  if (fp.alpha_channel >= 0) {
+    const int32_t* arow = f.mod + (size_t) fp.alpha_channel * f.height * f.mod_stride + (size_t) y * f.mod_stride;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (x0 + j < W) px[j][3] = ScaleSample(arow[x0 + j], fp.alpha_bits, maxout);
+  }
+  if (!fp.out16 && fp.pack.format == 0 && !fp.pack.associate && x0 + 3 < W) {
+    uint4 o;
+    o.x = px[0][0] | (px[0][1] << 8) | (px[0][2] << 16) | (px[0][3] << 24);
+    o.y = px[1][0] | (px[1][1] << 8) | (px[1][2] << 16) | (px[1][3] << 24);
+    o.z = px[2][0] | (px[2][1] << 8) | (px[2][2] << 16) | (px[2][3] << 24);
+    o.w = px[3][0] | (px[3][1] << 8) | (px[3][2] << 16) | (px[3][3] << 24);
+    *reinterpret_cast<uint4*>(fp.pack.dst + (size_t) y * fp.pack.dst_stride + 4 * (size_t) x0) = o;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (x0 + j < W) PackRgba(fp.pack, (uint32_t) (x0 + j), (uint32_t) y, px[j][0], px[j][1], px[j][2], px[j][3]);
+  }
+}
+
 }  // namespace
 
 void LaunchFilterColorPack(const FrameDev& f, const ColorParams& cp, const NumericTables* nt_dev, const OutputDesc& od,
@@ -171,6 +402,20 @@ void LaunchFilterColorPack(const FrameDev& f, const ColorParams& cp, const Numer
   fp.alpha_bits = od.alpha_bits;
   fp.out16 = od.bits16;
   dim3 grid((f.width + kTW - 1) / kTW, (f.height + kTH - 1) / kTH, 1);
+  static const bool no_fast = getenv("JXLB_NO_FAST_FILTER") != nullptr;
+  // the uint4 store of the fast path needs 16-byte aligned output rows
+  const bool aligned = (reinterpret_cast<uintptr_t>(pack.dst) & 15) == 0 && (pack.dst_stride & 15) == 0;
+  if (f.rf.gab && f.rf.epf_iters == 1 && aligned && !no_fast) {
+    static bool fast_configured = false;
+    if (!fast_configured) {
+      cudaFuncSetAttribute(FilterColorFastKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kFastSmemFloats * sizeof(float)));
+      cudaFuncSetAttribute(FilterColorFastKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      fast_configured = true;
+    }
+    FilterColorFastKernel<<<grid, kFilterThreads, kFastSmemFloats * sizeof(float), stream>>>(f, fp, nt_dev);
+    ++g_launches_ac;
+    return;
+  }
   FilterColorKernel<<<grid, kFilterThreads, smem, stream>>>(f, fp, nt_dev, halo);
   ++g_launches_ac;
 }

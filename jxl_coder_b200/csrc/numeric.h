@@ -280,9 +280,11 @@ JXLB_HD bool IsSpecial8x8(uint32_t s) { return s == 1 || s == 2 || s == 3 || (s 
 struct NumericTables {
   const float* dequant;                              // pool of 1/weight matrices
   uint32_t dequant_off[kNumQuantTables][3];          // per quant table and channel (X, Y, B)
+  uint8_t dequant_symmetric[kNumQuantTables];        // square table with w[a][b] == w[b][a] in all three channels
+  uint8_t pad_[3];
   // LLF synthesis: A_N[k][n] = r(N, k) * (c_k / N) * cos((2n+1) k pi / 2N), N = 1, 2, 4, 8, 16, 32 at llf[log2 N]
   const float* llf[6];
-  float dither[1024];                                // 32 x 32 (App. B.7)
+  alignas(16) float dither[1024];                                // 32 x 32 (App. B.7)
   float afv_basis[256];
 };
 

@@ -197,14 +197,24 @@ const HostNumericTables& GetHostNumericTables() {
   static HostNumericTables t;
   static std::once_flag once;
   std::call_once(once, [] {
-    for (int q = 0; q < kNumQuantTables; ++q)
+    for (int q = 0; q < kNumQuantTables; ++q) {
+      bool symmetric = true;
       for (int c = 0; c < 3; ++c) {
         std::vector<double> w;
         int rows, cols;
         TableWeights(q, c, &w, &rows, &cols);
         t.tables.dequant_off[q][c] = (uint32_t) t.dequant_pool.size();
         for (double v : w) t.dequant_pool.push_back((float) (1.0 / v));
+        if (rows != cols) symmetric = false;
+        for (int a = 0; a < rows && symmetric; ++a)
+          for (int b = 0; b < a; ++b)
+            if ((float) (1.0 / w[(size_t) a * cols + b]) != (float) (1.0 / w[(size_t) b * cols + a])) {
+              symmetric = false;
+              break;
+            }
       }
+      t.tables.dequant_symmetric[q] = symmetric ? 1 : 0;
+    }
     for (int l = 0; l < 6; ++l) {
       const int N = 1 << l;
       t.llf_off[l] = (uint32_t) t.llf_pool.size();

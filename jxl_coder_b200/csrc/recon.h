@@ -78,6 +78,26 @@ static constexpr int kRegionDim = 64;
 static constexpr int kTileStride = 65;                       // padded row stride (floats): conflict-free rows and columns
 static constexpr int kTileFloats = kRegionDim * kTileStride;  // one channel
 
+// Eight consecutive int16 coefficients (16-byte aligned in the plane), fetched with one 128-bit load on the device.
+struct Coef8 {
+  uint32_t w[4];
+  JXLB_HD int Get(int j) const { return (int) (int16_t) (w[j >> 1] >> ((j & 1) * 16)); }
+  JXLB_HD bool AllZero() const { return (w[0] | w[1] | w[2] | w[3]) == 0; }
+};
+JXLB_HD Coef8 LoadCoef8(const int16_t* p) {
+  Coef8 c;
+#ifdef __CUDA_ARCH__
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  c.w[0] = v.x;
+  c.w[1] = v.y;
+  c.w[2] = v.z;
+  c.w[3] = v.w;
+#else
+  for (int i = 0; i < 4; ++i) c.w[i] = (uint32_t) (uint16_t) p[2 * i] | ((uint32_t) (uint16_t) p[2 * i + 1] << 16);
+#endif
+  return c;
+}
+
 struct RegionCell {
   uint8_t strategy;   // 0..26, 0xFF = outside the frame
   uint8_t flags;      // bit 0: this block is fully inside the region, bit 1: special 8x8 transform, bit 2: transposed layout
@@ -144,9 +164,10 @@ JXLB_HD void ReconRegion(const FrameDev& f, const NumericTables& nt, uint32_t rx
       rc.oy = (int8_t) ((int) iy - dy);
       const int bx = (int) StrategyCellsX(t), by = (int) StrategyCellsY(t);
       const bool contained = rc.ox >= 0 && rc.oy >= 0 && rc.ox + bx <= kRegionCells && rc.oy + by <= kRegionCells;
-      rc.flags = (uint8_t) ((contained ? 1 : 0) | (IsSpecial8x8(t) ? 2 : 0) | (by >= bx ? 4 : 0));
-      rc.kcols_log = (uint8_t) (3 + FloorLog2((uint32_t) (bx > by ? bx : by)));
       const uint32_t qt = StrategyQuantTable(t);
+      // bit 2: the dequant matrix must be read transposed (tall / square blocks whose matrix is not symmetric)
+      rc.flags = (uint8_t) ((contained ? 1 : 0) | (IsSpecial8x8(t) ? 2 : 0) | ((by >= bx && !nt.dequant_symmetric[qt]) ? 4 : 0));
+      rc.kcols_log = (uint8_t) (3 + FloorLog2((uint32_t) (bx > by ? bx : by)));
       for (int c = 0; c < 3; ++c) rc.dq_off[c] = nt.dequant_off[qt][c];
       rc.scale = 65536.0f / (float) f.global_scale / (float) rc.hf_mul;
       if (contained) {
@@ -159,27 +180,68 @@ JXLB_HD void ReconRegion(const FrameDev& f, const NumericTables& nt, uint32_t rx
     sh.cell[i] = rc;
   }
   sync();
-  // P1: dequantise + chroma-from-luma into the three tiles (rows are coalesced int16 loads)
+  // P1: dequantise + chroma-from-luma into the three tiles.  Work unit = 8 consecutive pixels of a row (one 8x8 cell, so
+  // one RegionCell): three 128-bit coefficient loads per unit, all units of a thread issued before the first use so
+  // that the DRAM latency is paid once per thread rather than once per pixel.
   const float xqm = QmScale(f.x_qm_scale), bqm = QmScale(f.b_qm_scale);
   const size_t cplane = (size_t) f.coef_h * f.coef_stride;
-  for (int i = tid; i < kRegionDim * kRegionDim; i += nthreads) {
-    const uint32_t col = i % kRegionDim, row = i / kRegionDim;
-    const RegionCell rc = sh.cell[(row / 8) * kRegionCells + col / 8];
-    float vx = 0.0f, vy = 0.0f, vb = 0.0f;
-    if (rc.strategy != 0xFF && (rc.flags & 1)) {
-      const uint32_t pr = row - (uint32_t) rc.oy * 8, pc = col - (uint32_t) rc.ox * 8;
-      const size_t gi = (size_t) (cy0 * 8 + row) * f.coef_stride + cx0 * 8 + col;
-      const int qx = f.coef[gi], qy = f.coef[cplane + gi], qb = f.coef[2 * cplane + gi];
-      // index into the block's dequant matrix (stored like the coefficient array: transposed for square / tall blocks)
-      const uint32_t ki = (rc.flags & 4) ? ((pc << rc.kcols_log) + pr) : ((pr << rc.kcols_log) + pc);
-      vy = qy ? AdjustQuantBias(qy, 1) * rc.scale * nt.dequant[rc.dq_off[1] + ki] : 0.0f;
-      vx = (qx ? AdjustQuantBias(qx, 0) * (rc.scale * xqm) * nt.dequant[rc.dq_off[0] + ki] : 0.0f) + rc.kx * vy;
-      vb = (qb ? AdjustQuantBias(qb, 2) * (rc.scale * bqm) * nt.dequant[rc.dq_off[2] + ki] : 0.0f) + rc.kb * vy;
+  constexpr int kUnits = kRegionDim * kRegionDim / 8, kRounds = 3;
+  for (int base = tid; base < kUnits; base += kRounds * nthreads) {
+    Coef8 raw[kRounds][3];
+    RegionCell rcs[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const int u = base + r * nthreads;
+      if (u >= kUnits) break;
+      const uint32_t row = (uint32_t) u / 8u, cg = (uint32_t) u % 8u;
+      rcs[r] = sh.cell[(row / 8) * kRegionCells + cg];
+      if (rcs[r].strategy != 0xFF && (rcs[r].flags & 1)) {
+        const int16_t* p = f.coef + (size_t) (cy0 * 8 + row) * f.coef_stride + cx0 * 8 + cg * 8;
+        raw[r][0] = LoadCoef8(p);
+        raw[r][1] = LoadCoef8(p + cplane);
+        raw[r][2] = LoadCoef8(p + 2 * cplane);
+      }
     }
-    const int ti = (int) row * kTileStride + (int) col;
-    sh.tile[ti] = vx;
-    sh.tile[kTileFloats + ti] = vy;
-    sh.tile[2 * kTileFloats + ti] = vb;
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const int u = base + r * nthreads;
+      if (u >= kUnits) break;
+      const uint32_t row = (uint32_t) u / 8u, col0 = ((uint32_t) u % 8u) * 8u;
+      const RegionCell& rc = rcs[r];
+      float* tx = sh.tile + (int) row * kTileStride + (int) col0;
+      float* ty = tx + kTileFloats;
+      float* tb = tx + 2 * kTileFloats;
+      if (rc.strategy == 0xFF || !(rc.flags & 1)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tx[j] = ty[j] = tb[j] = 0.0f;
+        continue;
+      }
+      const uint32_t pr = row - (uint32_t) rc.oy * 8, pc0 = col0 - (uint32_t) rc.ox * 8;
+      // index into the block's dequant matrix (stored like the coefficient array: transposed for square / tall blocks;
+      // symmetric square matrices are read row-wise either way)
+      const bool tr = (rc.flags & 4) != 0;
+      const uint32_t k0 = tr ? ((pc0 << rc.kcols_log) + pr) : ((pr << rc.kcols_log) + pc0);
+      const uint32_t kstep = tr ? (1u << rc.kcols_log) : 1u;
+      const float sy = rc.scale, sx = rc.scale * xqm, sb = rc.scale * bqm;
+      const bool zx = raw[r][0].AllZero(), zy = raw[r][1].AllZero(), zb = raw[r][2].AllZero();
+      float vy[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int q = raw[r][1].Get(j);
+        vy[j] = (!zy && q) ? AdjustQuantBias(q, 1) * sy * nt.dequant[rc.dq_off[1] + k0 + j * kstep] : 0.0f;
+        ty[j] = vy[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int q = raw[r][0].Get(j);
+        tx[j] = ((!zx && q) ? AdjustQuantBias(q, 0) * sx * nt.dequant[rc.dq_off[0] + k0 + j * kstep] : 0.0f) + rc.kx * vy[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int q = raw[r][2].Get(j);
+        tb[j] = ((!zb && q) ? AdjustQuantBias(q, 2) * sb * nt.dequant[rc.dq_off[2] + k0 + j * kstep] : 0.0f) + rc.kb * vy[j];
+      }
+    }
   }
   sync();
   // P2: lowest frequencies from the (smoothed) LF image: one work item per (cell, channel)
