@@ -180,10 +180,24 @@ __global__ void __launch_bounds__(kFilterThreads, 3) FilterColorFastKernel(const
   const size_t pplane = (size_t) f.plane_h * f.plane_stride;
   const bool interior = tx0 >= 4 && tx0 + 68 <= W && ty0 >= 3 && ty0 + 19 <= H;
   if (interior) {
-    for (int i = tid; i < 3 * kSH * 18; i += kFilterThreads) {
-      const int q = i % 18, rc = i / 18, r = rc % kSH, c = rc / kSH;
-      const float4 v = *reinterpret_cast<const float4*>(f.xyb0 + c * pplane + (size_t) (ty0 - 3 + r) * f.plane_stride + tx0 - 4 + 4 * q);
-      *reinterpret_cast<float4*>(in0 + c * kSPlane + r * kSW + 4 + 4 * q) = v;
+    // 3 x 22 x 18 float4 = 1188 loads over 256 threads: all five of a thread issued before the first store
+    constexpr int kLoads = 3 * kSH * 18, kPer = (kLoads + kFilterThreads - 1) / kFilterThreads;
+    float4 v[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = tid + k * kFilterThreads;
+      if (i < kLoads) {
+        const int q = i % 18, rc = i / 18, r = rc % kSH, c = rc / kSH;
+        v[k] = __ldg(reinterpret_cast<const float4*>(f.xyb0 + c * pplane + (size_t) (ty0 - 3 + r) * f.plane_stride + tx0 - 4 + 4 * q));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = tid + k * kFilterThreads;
+      if (i < kLoads) {
+        const int q = i % 18, rc = i / 18, r = rc % kSH, c = rc / kSH;
+        *reinterpret_cast<float4*>(in0 + c * kSPlane + r * kSW + 4 + 4 * q) = v[k];
+      }
     }
   } else {
     for (int i = tid; i < kSH * 72; i += kFilterThreads) {

@@ -411,9 +411,18 @@ struct ColorParams {
   uint32_t grey;           // output is a grey image (R = G = B = luma channel)
 };
 
+// v ^ e for v in (0, 1]: on the device through the MUFU log2 / exp2 units (absolute error of lg2.approx is ~2^-22, so
+// the result is within ~3e-7 relative of powf -- 1e-4 of an 8-bit LSB -- at a tenth of the instructions).
+JXLB_HD float PowUnit(float v, float e) {
+#ifdef __CUDA_ARCH__
+  return exp2f(__log2f(v) * e);
+#else
+  return powf(v, e);
+#endif
+}
 JXLB_HD float SrgbOetf(float v) {
   if (v <= 0.0031308f) return 12.92f * v;
-  return 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+  return 1.055f * PowUnit(v, 1.0f / 2.4f) - 0.055f;
 }
 JXLB_HD float Rec709Oetf(float v) {
   if (v < 0.018f) return 4.5f * v;

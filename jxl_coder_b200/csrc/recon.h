@@ -111,8 +111,11 @@ struct RegionCell {
 
 struct RegionShared {
   RegionCell cell[kRegionCells * kRegionCells];
+  float lf[3][kRegionCells * kRegionCells];  // the region's LF samples (X, Y, B)
+  float llf[1 + 4 + 16 + 64];                // LLF synthesis matrices A_1, A_2, A_4, A_8 (blocks inside a region span <= 8 cells)
   float tile[3 * kTileFloats];
 };
+JXLB_HD int LlfSharedOffset(int log2n) { return log2n == 0 ? 0 : log2n == 1 ? 1 : log2n == 2 ? 5 : 21; }
 
 JXLB_HD float QmScale(uint32_t scale) {
   // 0.8 ^ (scale - 2)
@@ -179,6 +182,18 @@ JXLB_HD void ReconRegion(const FrameDev& f, const NumericTables& nt, uint32_t rx
     }
     sh.cell[i] = rc;
   }
+  {
+    const size_t lfplane0 = (size_t) f.h8 * f.lf_stride;
+    for (int i = tid; i < 3 * kRegionCells * kRegionCells; i += nthreads) {
+      const int c = i / (kRegionCells * kRegionCells), ci = i % (kRegionCells * kRegionCells);
+      const uint32_t gx = cx0 + (uint32_t) (ci % kRegionCells), gy = cy0 + (uint32_t) (ci / kRegionCells);
+      sh.lf[c][ci] = (gx < f.w8 && gy < f.h8) ? f.lf[c * lfplane0 + (size_t) gy * f.lf_stride + gx] : 0.0f;
+    }
+    for (int i = tid; i < 85; i += nthreads) {
+      const int l = i < 1 ? 0 : i < 5 ? 1 : i < 21 ? 2 : 3;
+      sh.llf[i] = nt.llf[l][i - LlfSharedOffset(l)];
+    }
+  }
   sync();
   // P1: dequantise + chroma-from-luma into the three tiles.  Work unit = 8 consecutive pixels of a row (one 8x8 cell, so
   // one RegionCell): three 128-bit coefficient loads per unit, all units of a thread issued before the first use so
@@ -244,8 +259,7 @@ JXLB_HD void ReconRegion(const FrameDev& f, const NumericTables& nt, uint32_t rx
     }
   }
   sync();
-  // P2: lowest frequencies from the (smoothed) LF image: one work item per (cell, channel)
-  const size_t lfplane = (size_t) f.h8 * f.lf_stride;
+  // P2: lowest frequencies from the (smoothed) LF image: one work item per (cell, channel); operands in shared memory
   for (int i = tid; i < 3 * kRegionCells * kRegionCells; i += nthreads) {
     const int c = i / (kRegionCells * kRegionCells), ci = i % (kRegionCells * kRegionCells);
     const int ix = ci % kRegionCells, iy = ci / kRegionCells;
@@ -253,17 +267,17 @@ JXLB_HD void ReconRegion(const FrameDev& f, const NumericTables& nt, uint32_t rx
     if (rc.strategy == 0xFF || !(rc.flags & 1)) continue;
     const int bx = (int) StrategyCellsX(rc.strategy), by = (int) StrategyCellsY(rc.strategy);
     const int kx = ix - rc.ox, ky = iy - rc.oy;
-    const float* lf = f.lf + c * lfplane + (size_t) (cy0 + rc.oy) * f.lf_stride + cx0 + rc.ox;
+    const float* lf = sh.lf[c] + rc.oy * kRegionCells + rc.ox;
     float v;
     if (bx == 1 && by == 1) {
       v = lf[0];
     } else {
-      const float* ay = nt.llf[FloorLog2((uint32_t) by)] + ky * by;
-      const float* ax = nt.llf[FloorLog2((uint32_t) bx)] + kx * bx;
+      const float* ay = sh.llf + LlfSharedOffset(FloorLog2((uint32_t) by)) + ky * by;
+      const float* ax = sh.llf + LlfSharedOffset(FloorLog2((uint32_t) bx)) + kx * bx;
       v = 0.0f;
       for (int ny = 0; ny < by; ++ny) {
         float rowacc = 0.0f;
-        for (int nx = 0; nx < bx; ++nx) rowacc += ax[nx] * lf[(size_t) ny * f.lf_stride + nx];
+        for (int nx = 0; nx < bx; ++nx) rowacc += ax[nx] * lf[ny * kRegionCells + nx];
         v += ay[ny] * rowacc;
       }
     }
