@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -929,9 +930,13 @@ void CopyStatuses(const Batch& b, std::vector<DecodedImage>* out, int* overall) 
 
 int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device, std::vector<DecodedImage>* out,
                 BatchTimings* timings) {
+  using Clock = std::chrono::steady_clock;
+  const auto t0 = Clock::now();
+  auto ms_since = [&](Clock::time_point a) { return std::chrono::duration<double, std::milli>(Clock::now() - a).count(); };
   out->assign(n, DecodedImage());
   Batch b;
   b.Parse(reqs, n, api_level);
+  const double parse_ms = ms_since(t0);
   int overall = JXLB_OK;
   if (!b.AnyOk()) {
     CopyStatuses(b, out, &overall);
@@ -945,15 +950,25 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
     CopyStatuses(b, out, &overall);
     return overall;
   }
+  const auto t1 = Clock::now();
   std::unique_lock<std::mutex> lock;
   Slot* slot = AcquireSlot(b.ctx, &lock);
+  const double slot_ms = ms_since(t1);
   b.stream = slot->stream;
   b.copy_stream = slot->copy_stream;
   try {
+    const auto t2 = Clock::now();
     b.Upload(&slot->spare);
     if (output_device < 0) b.PrepareHostOutputs();
+    const double upload_ms = ms_since(t2);
+    const auto t3 = Clock::now();
     b.Run();
+    const double launch_ms = ms_since(t3);
+    const auto t4 = Clock::now();
     b.Finish(output_device < 0, output_device, out);
+    if (b.ctx->timeline)
+      fprintf(stderr, "[host] decode_batch n=%zu: parse %.1f  slot wait %.1f  stage+upload %.1f  launch %.1f  finish(wait) %.1f  total %.1f ms\n", n,
+              parse_ms, slot_ms, upload_ms, launch_ms, ms_since(t4), ms_since(t0));
     if (timings) *timings = b.tm;
   } catch (CudaError& e) {
     for (auto& p : b.ps)

@@ -19,6 +19,19 @@
 #define JXLB_D inline
 #endif
 
+// Address-space hints for pointers whose provenance the compiler cannot see (they travel through structs and
+// non-inlined functions): with them the device code uses LDS / LDG with 32-bit shared addresses instead of generic LD.
+#if defined(__CUDA_ARCH__) && !defined(JXLB_NO_HINTS) && !defined(JXLB_NO_HINT_SHARED)
+#define JXLB_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define JXLB_ASSUME_SHARED(p) ((void) 0)
+#endif
+#if defined(__CUDA_ARCH__) && !defined(JXLB_NO_HINTS) && !defined(JXLB_NO_HINT_GLOBAL)
+#define JXLB_ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
+#else
+#define JXLB_ASSUME_GLOBAL(p) ((void) 0)
+#endif
+
 namespace jxlb {
 
 // Stream-level status codes (device kernels write these per stream; host maps them to the C-ABI error codes).

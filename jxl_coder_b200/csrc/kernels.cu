@@ -9,6 +9,7 @@
 #include "kernels.h"
 
 #include <atomic>
+#include <cstdlib>
 
 #include "recon.h"
 
@@ -60,21 +61,118 @@ __global__ void __launch_bounds__(kStreamBlockThreads) SingleSectionKernel(const
   f.status[job.status_slot] = DecodeSingleSectionFrame(f, nat, sc, hf, perm, scratch.max_local_nodes);
 }
 
+// Block placement of one LF group by a whole warp (the serial loop at the end of DecodeLfGroupSection, same results and
+// the same error conditions).  "The next BlockInfo entry goes to the first uncovered cell in raster order" is a serial
+// rule, but only over the ~4 K blocks, not the 64 K cells: lane 0 walks a coverage bitmap in shared memory (one bit per
+// cell, find-first-set per 32 cells) and records each block's position; the per-cell planes are then filled by all lanes.
+__device__ int PlaceBlocksWarp(const FrameDev& f, uint32_t lfg, uint32_t* bitmap /* 256 rows x 8 words, shared */) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t cx0, cy0, w8, h8, w64, h64;
+  LfGroupRect(f, lfg, &cx0, &cy0, &w8, &h8, &w64, &h64);
+  const uint32_t nb = f.nb_blocks[lfg];
+  int32_t* binfo = f.blockinfo + f.blockinfo_off[lfg];
+  // sharpness plane -> bytes (range-checked); coverage bitmap with the cells right of the group marked as covered
+  bool bad = false;
+  for (uint32_t i = lane; i < w8 * h8; i += 32) {
+    const uint32_t y = i / w8, x = i - y * w8;
+    const int32_t sh = f.sharpness_i32[(size_t) (cy0 + y) * f.lf_stride + cx0 + x];
+    if (sh < 0 || sh > 7) bad = true;
+    f.cell_sharp[(size_t) (cy0 + y) * f.w8 + cx0 + x] = (uint8_t) sh;
+  }
+  for (uint32_t i = lane; i < h8 * 8; i += 32) {
+    const uint32_t base = (i & 7u) * 32u;
+    bitmap[i] = base >= w8 ? 0xFFFFFFFFu : (w8 - base >= 32u ? 0u : (0xFFFFFFFFu << (w8 - base)));
+  }
+  __syncwarp();
+  int st = kOk;
+  if (lane == 0) {
+    const uint32_t nwords = h8 * 8;
+    uint32_t pos = 0;
+    for (uint32_t k = 0; k < nb; ++k) {
+      uint32_t free_bits = 0;
+      while (pos < nwords && (free_bits = ~bitmap[pos]) == 0) ++pos;
+      if (pos >= nwords) {  // blocks left over after every cell is covered
+        st = kErrBadStream;
+        break;
+      }
+      const uint32_t x = (pos & 7u) * 32u + (uint32_t) __ffs((int) free_bits) - 1u, y = pos >> 3;
+      const int32_t t = binfo[k];
+      int32_t q = binfo[nb + k];
+      q = 1 + (q < 0 ? 0 : q > 255 ? 255 : q);  // hf_mul is clamped to [1, 256]
+      if (t < 0 || t >= kNumStrategies) {
+        st = kErrBadStream;
+        break;
+      }
+      const uint32_t bx = StrategyCellsX((uint32_t) t), by = StrategyCellsY((uint32_t) t);
+      // inside the LF group, and not straddling a 256x256 group boundary (so never straddling a bitmap word either)
+      if (x + bx > w8 || y + by > h8 || (x % kGroupCells) + bx > kGroupCells || (y % kGroupCells) + by > kGroupCells) {
+        st = kErrBadStream;
+        break;
+      }
+      const uint32_t mask = (bx >= 32u ? 0xFFFFFFFFu : ((1u << bx) - 1u)) << (x & 31u);
+      bool overlap = false;
+      for (uint32_t yy = 0; yy < by; ++yy) {
+        uint32_t& wd = bitmap[(y + yy) * 8 + (x >> 5)];
+        if (wd & mask) overlap = true;
+        wd |= mask;
+      }
+      if (overlap) {
+        st = kErrBadStream;
+        break;
+      }
+      binfo[k] = t | (int32_t) (x << 8) | (int32_t) (y << 16);
+      binfo[nb + k] = q;
+    }
+    if (st == kOk) {  // a cell left uncovered means BlockInfo ran out of blocks
+      for (; pos < nwords; ++pos)
+        if (~bitmap[pos] != 0) {
+          st = kErrBadStream;
+          break;
+        }
+    }
+  }
+  st = __shfl_sync(0xFFFFFFFFu, st, 0);
+  if (__any_sync(0xFFFFFFFFu, bad)) st = st == kOk ? kErrBadStream : st;
+  if (st != kOk) return st;
+  for (uint32_t k = lane; k < nb; k += 32) {
+    const uint32_t rec = (uint32_t) binfo[k];
+    const uint32_t t = rec & 0xFFu, x = (rec >> 8) & 0xFFu, y = rec >> 16;
+    const uint16_t q = (uint16_t) binfo[nb + k];
+    const uint32_t bx = StrategyCellsX(t), by = StrategyCellsY(t);
+    for (uint32_t yy = 0; yy < by; ++yy) {
+      const size_t o = (size_t) (cy0 + y + yy) * f.w8 + cx0 + x;
+      for (uint32_t xx = 0; xx < bx; ++xx) {
+        f.cell_strategy[o + xx] = (uint8_t) ((yy | xx) == 0 ? (t | 0x80u) : t);
+        f.cell_hfmul[o + xx] = q;
+        f.cell_off[o + xx] = (uint16_t) ((yy << 8) | xx);
+      }
+    }
+  }
+  return kOk;
+}
+
 __global__ void __launch_bounds__(kStreamBlockThreads) LfGroupKernel(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs,
-                                                                     ScratchLayout scratch) {
+                                                                     ScratchLayout scratch, int warp_place) {
   const uint32_t j = blockIdx.x;
-  if (j >= njobs || threadIdx.x != 0) return;
+  if (j >= njobs) return;
   const StreamJob job = jobs[j];
   const FrameDev& f = frames[job.frame];
-  StreamScratch sc = CarveScratch(scratch, j, nullptr, nullptr);
   extern __shared__ __align__(16) uint8_t lf_smem[];
-  sc.fast = lf_smem;
-  sc.fast_code_bytes = kLfFastCodeBytes;
-  sc.fast_ints = kLfFastInts;
-  BitReader br;
-  const uint32_t sec = 1 + job.index;
-  br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);
-  f.status[job.status_slot] = DecodeLfGroupSection(br, f, job.index, sc, scratch.max_local_nodes);
+  int st = kOk;
+  if (threadIdx.x == 0) {
+    StreamScratch sc = CarveScratch(scratch, j, nullptr, nullptr);
+    sc.fast = lf_smem;
+    sc.fast_code_bytes = kLfFastCodeBytes;
+    sc.fast_ints = kLfFastInts;
+    BitReader br;
+    const uint32_t sec = 1 + job.index;
+    br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);
+    st = DecodeLfGroupSection(br, f, job.index, sc, scratch.max_local_nodes, /*place_blocks=*/!warp_place);
+  }
+  __syncwarp();
+  st = __shfl_sync(0xFFFFFFFFu, st, 0);
+  if (st == kOk && warp_place) st = PlaceBlocksWarp(f, job.index, reinterpret_cast<uint32_t*>(lf_smem));
+  if (threadIdx.x == 0) f.status[job.status_slot] = st;
 }
 
 __global__ void __launch_bounds__(kStreamBlockThreads) PassGroupKernel(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs,
@@ -200,7 +298,8 @@ void LaunchLfGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njob
     cudaFuncSetAttribute(LfGroupKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  LfGroupKernel<<<njobs, kStreamBlockThreads, smem, stream>>>(frames, jobs, njobs, scratch);
+  static const int warp_place = getenv("JXLB_SERIAL_PLACEMENT") == nullptr;
+  LfGroupKernel<<<njobs, kStreamBlockThreads, smem, stream>>>(frames, jobs, njobs, scratch, warp_place);
   ++g_launches;
 }
 void LaunchPassGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat, ScratchLayout scratch,

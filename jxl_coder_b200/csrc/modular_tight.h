@@ -61,17 +61,48 @@ struct TightBits {
   }
 };
 
+// The parts of a CodeView the inner loops need, held in registers.
+struct TightCode {
+  const AliasEntry* alias;
+  const HybridCfg* cfg;
+  uint32_t log_alpha, log_entry;
+};
+JXLB_HD TightCode MakeTightCode(const CodeView& code) {
+  TightCode t;
+  t.alias = code.alias;
+  t.cfg = code.cfg;
+  t.log_alpha = code.log_alpha;
+  t.log_entry = code.log_entry;
+  return t;
+}
+// One alias bucket as two 32-bit words: {cutoff | right << 8 | freq0 << 16, offset1 | freq1 << 16} (one 64-bit load).
+struct AliasWords {
+  uint32_t x, y;
+};
+JXLB_HD AliasWords LoadAlias(const AliasEntry* p) {
+  AliasWords w;
+#ifdef __CUDA_ARCH__
+  const uint2 v = *reinterpret_cast<const uint2*>(p);  // tables are 16-byte aligned, entries 8 bytes
+  w.x = v.x;
+  w.y = v.y;
+#else
+  w.x = (uint32_t) p->cutoff | ((uint32_t) p->right << 8) | ((uint32_t) p->freq0 << 16);
+  w.y = (uint32_t) p->offset1 | ((uint32_t) p->freq1 << 16);
+#endif
+  return w;
+}
+
 // One ANS symbol of `cluster` (alias-table codes only) followed by its hybrid-uint extra bits.
-JXLB_HD uint32_t TightReadUint(TightBits& tb, uint32_t& state, const CodeView& code, uint32_t cluster) {
+JXLB_HD uint32_t TightReadUint(TightBits& tb, uint32_t& state, const TightCode& code, uint32_t cluster) {
   const uint32_t res = state & (kAnsTabSize - 1);
   const uint32_t bucket = res >> code.log_entry;
   const uint32_t pos = res & ((1u << code.log_entry) - 1);
-  const AliasEntry e = code.alias[(cluster << code.log_alpha) + bucket];
+  const AliasWords e = LoadAlias(code.alias + (cluster << code.log_alpha) + bucket);
   const HybridCfg cfg = code.cfg[cluster];
-  const bool hi = pos >= e.cutoff;
-  const uint32_t sym = hi ? e.right : bucket;
-  const uint32_t off = hi ? e.offset1 + pos : pos;
-  const uint32_t freq = hi ? e.freq1 : e.freq0;
+  const bool hi = pos >= (e.x & 0xFFu);
+  const uint32_t sym = hi ? ((e.x >> 8) & 0xFFu) : bucket;
+  const uint32_t off = hi ? (e.y & 0xFFFFu) + pos : pos;
+  const uint32_t freq = hi ? (e.y >> 16) : (e.x >> 16);
   uint32_t s = freq * (state >> kAnsTabBits) + off;
   if (s < (1u << 16)) {
     tb.Refill();
@@ -110,9 +141,19 @@ JXLB_HD bool TightWpEligible(const SubtreeInfo& info, const CodeView& code, cons
 }
 
 // Decodes one WP-only channel.  `last_root` caches which subtree the LUT in scratch was built for (0xFFFFFFFF = none).
-JXLB_HD void DecodeWpChannelTight(TightBits& tb, uint32_t& ans_state, const CodeView& code, const TreeNode* tree,
+// kHints: (device) scratch is shared memory, the code tables / output plane / bitstream are global memory.
+template <bool kHints>
+JXLB_HD void DecodeWpChannelTight(TightBits& tb, uint32_t& ans_state, const CodeView& code_view, const TreeNode* tree,
                                   const SubtreeInfo& info, const WPHeader& wph, const ModChannel& c, int32_t* scratch,
                                   uint32_t* last_root) {
+  const TightCode code = MakeTightCode(code_view);
+  if (kHints) {
+    JXLB_ASSUME_SHARED(scratch);
+    JXLB_ASSUME_GLOBAL(code.alias);
+    JXLB_ASSUME_GLOBAL(code.cfg);
+    JXLB_ASSUME_GLOBAL(c.data);
+    JXLB_ASSUME_GLOBAL(tb.words);
+  }
   const uint32_t xs = c.w, P = TightScratch::Pad(xs);
   uint32_t* divtab = reinterpret_cast<uint32_t*>(scratch);
   uint8_t* lut = reinterpret_cast<uint8_t*>(scratch + 64);
@@ -124,7 +165,7 @@ JXLB_HD void DecodeWpChannelTight(TightBits& tb, uint32_t& ans_state, const Code
     for (int v = -512; v < 512; ++v) {
       TreeNode nd = tree[info.root];
       while (nd.property >= 0) nd = tree[v > nd.split_or_offset ? nd.left_or_ctx : nd.right_or_mul];
-      lut[v + 512] = code.ctx_map[nd.left_or_ctx];
+      lut[v + 512] = code_view.ctx_map[nd.left_or_ctx];
     }
     *last_root = info.root;
   }
@@ -292,10 +333,20 @@ JXLB_HD_NOINLINE uint32_t BuildSimpleSubtree(const TreeNode* tree, const Subtree
   return n;
 }
 
-// Decodes one channel with a compact subtree (see BuildSimpleSubtree).  scratch: TightScratch::SimpleInts(c.w) ints;
-// `nodes` should live in low-latency memory.
-JXLB_HD void DecodeSimpleChannelTight(TightBits& tb, uint32_t& ans_state, const CodeView& code, const SimpleNode* nodes,
-                                      const ModChannel& c, int32_t* scratch) {
+// Decodes one channel with a compact subtree (see BuildSimpleSubtree).  scratch: TightScratch::SimpleInts(c.w) ints with
+// the node array at scratch + 64.
+template <bool kHints>
+JXLB_HD void DecodeSimpleChannelTight(TightBits& tb, uint32_t& ans_state, const CodeView& code_view, const ModChannel& c,
+                                      int32_t* scratch) {
+  const TightCode code = MakeTightCode(code_view);
+  const SimpleNode* nodes = reinterpret_cast<const SimpleNode*>(scratch + 64);  // see the note in DecodeNwChannelTight
+  if (kHints) {
+    JXLB_ASSUME_SHARED(scratch);
+    JXLB_ASSUME_GLOBAL(code.alias);
+    JXLB_ASSUME_GLOBAL(code.cfg);
+    JXLB_ASSUME_GLOBAL(c.data);
+    JXLB_ASSUME_GLOBAL(tb.words);
+  }
   const uint32_t xs = c.w, P = TightScratch::Pad(xs);
   int32_t* rows = scratch + TightScratch::kHeadInts;  // [3][P]: rotating current / N / NN rows
   int32_t* rbuf[3] = {rows, rows + P, rows + 2 * P};
@@ -368,23 +419,165 @@ JXLB_HD void DecodeSimpleChannelTight(TightBits& tb, uint32_t& ans_state, const 
   ans_state = state;
 }
 
+// ---- subtrees over {y, N, W} only: context by table lookup ----------------------------------------------------------------
+// The HF-metadata channels of libjxl-encoded frames (BlockInfo, EPF sharpness) use small trees that test only the row
+// (property 2), N (6) and W (7) and predict Zero / W / Gradient.  A decision "v > split" is unchanged when v is clamped
+// to [min split, max split + 1], so the whole walk collapses into one lookup indexed by the clamped (W, N); entries pack
+// cluster | predictor << 8 | leaf << 16.  Rebuilt per row only when the tree tests y.
+struct NwPlan {
+  int32_t lo_w, lo_n;       // clamp ranges: [lo, lo + n - 1]
+  uint32_t n_w, n_n;
+  uint32_t uses_y, plain;   // plain: every leaf has multiplier 1 and offset 0
+};
+static constexpr uint32_t kNwLutEntries = 1024;
+JXLB_HD uint32_t NwInts(uint32_t w) { return TightScratch::kHeadInts + 2u * TightScratch::Pad(w) + kNwLutEntries; }
+
+// Examines a compact subtree (BuildSimpleSubtree output); false when it does not qualify.
+JXLB_HD_NOINLINE bool PlanNwSubtree(const SimpleNode* nodes, uint32_t n, NwPlan* plan) {
+  int32_t lo_w = 0x7FFFFFFF, hi_w = (int32_t) 0x80000000, lo_n = 0x7FFFFFFF, hi_n = (int32_t) 0x80000000;
+  bool any_w = false, any_n = false;
+  plan->uses_y = 0;
+  plan->plain = 1;
+  for (uint32_t i = 0; i < n; ++i) {
+    const SimpleNode nd = nodes[i];
+    if (nd.property < 0) {
+      if (nd.predictor != 0 && nd.predictor != 1 && nd.predictor != 5) return false;
+      if (nd.mul != 1 || nd.split_or_offset != 0) plan->plain = 0;
+    } else if (nd.property == 2) {
+      plan->uses_y = 1;
+    } else if (nd.property == 6) {
+      any_n = true;
+      if (nd.split_or_offset < lo_n) lo_n = nd.split_or_offset;
+      if (nd.split_or_offset > hi_n) hi_n = nd.split_or_offset;
+    } else if (nd.property == 7) {
+      any_w = true;
+      if (nd.split_or_offset < lo_w) lo_w = nd.split_or_offset;
+      if (nd.split_or_offset > hi_w) hi_w = nd.split_or_offset;
+    } else {
+      return false;
+    }
+  }
+  if (!any_w) lo_w = hi_w = 0;
+  if (!any_n) lo_n = hi_n = 0;
+  if (hi_w > 0x3FFFFFFF || hi_n > 0x3FFFFFFF || lo_w < -0x3FFFFFFF || lo_n < -0x3FFFFFFF) return false;
+  const int64_t nw = (int64_t) hi_w - lo_w + 2, nn = (int64_t) hi_n - lo_n + 2;
+  if (nw * nn > (int64_t) kNwLutEntries) return false;
+  plan->lo_w = lo_w;
+  plan->lo_n = lo_n;
+  plan->n_w = (uint32_t) nw;
+  plan->n_n = (uint32_t) nn;
+  return true;
+}
+
+JXLB_HD void BuildNwLut(const SimpleNode* nodes, const NwPlan& plan, uint32_t y, uint32_t* lut) {
+  for (uint32_t iw = 0; iw < plan.n_w; ++iw)
+    for (uint32_t in = 0; in < plan.n_n; ++in) {
+      const int32_t wv = plan.lo_w + (int32_t) iw, nv = plan.lo_n + (int32_t) in;
+      uint32_t k = 0;
+      SimpleNode nd = nodes[0];
+      while (nd.property >= 0) {
+        const int32_t v = nd.property == 2 ? (int32_t) y : nd.property == 6 ? nv : wv;
+        k = v > nd.split_or_offset ? nd.left : nd.right;
+        nd = nodes[k];
+      }
+      lut[iw * plan.n_n + in] = (uint32_t) nd.cluster | ((uint32_t) nd.predictor << 8) | (k << 16);
+    }
+}
+
+// scratch: NwInts(c.w) ints; the node array sits at scratch + 64 (as left by BuildSimpleSubtree).
+template <bool kHints>
+JXLB_HD void DecodeNwChannelTight(TightBits& tb, uint32_t& ans_state, const CodeView& code_view, const NwPlan& plan,
+                                  const ModChannel& c, int32_t* scratch) {
+  const TightCode code = MakeTightCode(code_view);
+  // NOTE: hints are only ever applied to pointers that are shared / global on EVERY path that can produce them: nvcc
+  // infers the address space of the underlying value, not of the program point (a select of a shared and a global
+  // pointer hinted in one branch miscompiles the other).  Hence `nodes` is derived here, not passed in.
+  const SimpleNode* nodes = reinterpret_cast<const SimpleNode*>(scratch + 64);
+  if (kHints) {
+    JXLB_ASSUME_SHARED(scratch);
+    JXLB_ASSUME_GLOBAL(code.alias);
+    JXLB_ASSUME_GLOBAL(code.cfg);
+    JXLB_ASSUME_GLOBAL(c.data);
+    JXLB_ASSUME_GLOBAL(tb.words);
+  }
+  const uint32_t xs = c.w, P = TightScratch::Pad(xs);
+  int32_t* rows = scratch + TightScratch::kHeadInts;  // [2][P]: current / N rows
+  uint32_t* lut = reinterpret_cast<uint32_t*>(rows + 2 * P);
+  uint32_t state = ans_state;
+  const int32_t lo_w = plan.lo_w, hi_w = plan.lo_w + (int32_t) plan.n_w - 1;
+  const int32_t lo_n = plan.lo_n, hi_n = plan.lo_n + (int32_t) plan.n_n - 1;
+  const uint32_t n_n = plan.n_n;
+  if (!plan.uses_y) BuildNwLut(nodes, plan, 0, lut);
+  for (uint32_t y = 0; y < c.h; ++y) {
+    if (plan.uses_y) BuildNwLut(nodes, plan, y, lut);
+    int32_t* out_row = c.data + (size_t) y * c.stride;
+    int32_t* cur = rows + (y & 1) * P;
+    const int32_t* rN = rows + ((y & 1) ^ 1) * P;
+    int32_t W = y > 0 ? rN[0] : 0, N = W, NW = W;
+    for (uint32_t x = 0; x < xs; ++x) {
+      const int32_t n_next = (x + 1 < xs && y > 0) ? rN[x + 1] : N;  // the N of the next column (NE of this one)
+      const int32_t wc = W < lo_w ? lo_w : W > hi_w ? hi_w : W;
+      const int32_t nc = N < lo_n ? lo_n : N > hi_n ? hi_n : N;
+      const uint32_t e = lut[(uint32_t) (wc - lo_w) * n_n + (uint32_t) (nc - lo_n)];
+      const uint32_t predictor = (e >> 8) & 0xFFu;
+      const int32_t pred = predictor == 0 ? 0 : predictor == 1 ? W : (int32_t) ClampedGradient(W, N, NW);
+      const uint32_t u = TightReadUint(tb, state, code, e & 0xFFu);
+      int32_t val;
+      if (plan.plain) {
+        val = UnpackSigned(u) + pred;
+      } else {
+        const SimpleNode lf = nodes[e >> 16];
+        val = (int32_t) ((int64_t) UnpackSigned(u) * (int64_t) lf.mul + lf.split_or_offset + pred);
+      }
+      cur[x] = val;
+      out_row[x] = val;
+      W = val;
+      if (y > 0) {
+        NW = N;
+        N = n_next;
+      } else {
+        NW = val;
+        N = val;
+      }
+    }
+  }
+  ans_state = state;
+}
+
 // Decodes all channels of one modular sub-stream.  Streams whose every channel fits one of the tight loops (alias-table
 // code without LZ77; WP-only or small neighbourhood subtrees) take them; anything else goes through the general decoder
 // DecodeModularChannelsFast with identical results.  scratch: ModFastScratch::Ints(max w) ints (any memory);
 // fast_scratch: optional low-latency memory (shared memory on the device) of fast_ints ints, 16-byte aligned.
+#ifdef __CUDA_ARCH__
+#define JXLB_DEV_HINTS true
+#else
+#define JXLB_DEV_HINTS false
+#endif
+
 JXLB_HD_NOINLINE int DecodeModularChannelsTight(BitReader& br_io, const ModularContext& mc, const WPHeader& wph, const ModChannel* ch,
                                                 uint32_t nch, uint32_t stream_id, int32_t* scratch, uint32_t* lz77_window,
                                                 uint32_t lz77_mask, int32_t* fast_scratch, uint32_t fast_ints) {
   constexpr uint32_t kMaxCh = 8;
   bool tight = TightCodeOk(mc.code) && nch <= kMaxCh;
+#ifdef __CUDA_ARCH__
+  // On the device the tight loops exist only in their hinted form: shared-memory scratch, everything else in HBM.
+  if (!fast_scratch || !__isShared(fast_scratch) || !__isGlobal(mc.code.blob) || !__isGlobal(br_io.words) || !__isGlobal(scratch)) tight = false;
+#endif
   uint8_t kind[kMaxCh];  // 0 = empty, 1 = WP-only, 2 = simple subtree
   SubtreeInfo infos[kMaxCh];
   for (uint32_t ci = 0; ci < nch && tight; ++ci) {
     kind[ci] = 0;
     if (!ch[ci].w || !ch[ci].h) continue;
+#ifdef __CUDA_ARCH__
+    if (!__isGlobal(ch[ci].data)) {
+      tight = false;
+      break;
+    }
+#endif
     infos[ci] = AnalyseSubtree(mc.tree, mc.num_nodes, ci, stream_id);
-    int32_t* base = (fast_scratch && TightScratch::WpInts(ch[ci].w) <= fast_ints) ? fast_scratch : scratch;
-    if (TightWpEligible(infos[ci], mc.code, wph, ch[ci].w, 0xFFFFFFFFu)) {
+    const bool wp_fast = fast_scratch && TightScratch::WpInts(ch[ci].w) <= fast_ints;
+    int32_t* base = wp_fast ? fast_scratch : scratch;
+    if (TightWpEligible(infos[ci], mc.code, wph, ch[ci].w, 0xFFFFFFFFu) && (wp_fast || !JXLB_DEV_HINTS)) {
       kind[ci] = 1;
     } else if (BuildSimpleSubtree(mc.tree, infos[ci], mc.code, reinterpret_cast<SimpleNode*>(base + 64)) != 0) {
       kind[ci] = 2;
@@ -403,15 +596,30 @@ JXLB_HD_NOINLINE int DecodeModularChannelsTight(BitReader& br_io, const ModularC
     const ModChannel c = ch[ci];
     if (kind[ci] == 1) {
       const bool fast = fast_scratch && TightScratch::WpInts(c.w) <= fast_ints;
-      DecodeWpChannelTight(tb, state, mc.code, mc.tree, infos[ci], wph, c, fast ? fast_scratch : scratch,
-                           fast ? &last_root_fast : &last_root_slow);
+      if (fast) DecodeWpChannelTight<JXLB_DEV_HINTS>(tb, state, mc.code, mc.tree, infos[ci], wph, c, fast_scratch, &last_root_fast);
+#ifndef __CUDA_ARCH__
+      else DecodeWpChannelTight<false>(tb, state, mc.code, mc.tree, infos[ci], wph, c, scratch, &last_root_slow);
+#endif
     } else {
-      const bool fast = fast_scratch && TightScratch::SimpleInts(c.w) <= fast_ints;
-      int32_t* base = fast ? fast_scratch : scratch;
-      SimpleNode* nodes = reinterpret_cast<SimpleNode*>(base + 64);
-      BuildSimpleSubtree(mc.tree, infos[ci], mc.code, nodes);
-      (fast ? last_root_fast : last_root_slow) = 0xFFFFFFFFu;  // the node array overwrote the LUT
-      DecodeSimpleChannelTight(tb, state, mc.code, nodes, c, base);
+      // the compact node array goes to the head of whichever scratch the channel will use
+      const bool nw_fast = fast_scratch && NwInts(c.w) <= fast_ints;
+      const bool simple_fast = fast_scratch && TightScratch::SimpleInts(c.w) <= fast_ints;
+      SimpleNode* nodes = reinterpret_cast<SimpleNode*>((nw_fast ? fast_scratch : scratch) + 64);
+      const uint32_t nn = BuildSimpleSubtree(mc.tree, infos[ci], mc.code, nodes);
+      NwPlan plan;
+      if (PlanNwSubtree(nodes, nn, &plan)) {
+        (nw_fast ? last_root_fast : last_root_slow) = 0xFFFFFFFFu;  // the node array overwrote the WP LUT
+        if (nw_fast) DecodeNwChannelTight<JXLB_DEV_HINTS>(tb, state, mc.code, plan, c, fast_scratch);
+        else DecodeNwChannelTight<false>(tb, state, mc.code, plan, c, scratch);
+      } else {
+        if (simple_fast != nw_fast) {
+          nodes = reinterpret_cast<SimpleNode*>((simple_fast ? fast_scratch : scratch) + 64);
+          BuildSimpleSubtree(mc.tree, infos[ci], mc.code, nodes);
+        }
+        (simple_fast ? last_root_fast : last_root_slow) = 0xFFFFFFFFu;
+        if (simple_fast) DecodeSimpleChannelTight<JXLB_DEV_HINTS>(tb, state, mc.code, c, fast_scratch);
+        else DecodeSimpleChannelTight<false>(tb, state, mc.code, c, scratch);
+      }
     }
   }
   tb.To(br);

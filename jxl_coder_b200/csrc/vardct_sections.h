@@ -177,8 +177,10 @@ JXLB_HD void LfGroupRect(const FrameDev& f, uint32_t lfg, uint32_t* cx0, uint32_
 }
 
 // LfGroup section of a VarDCT frame (App. B.7): LF coefficients, HF metadata, block placement.
+// place_blocks = false: stop after the entropy-coded data (the CUDA kernel then places the blocks with the whole warp,
+// PlaceBlocksWarp in kernels.cu, which must produce exactly what the serial loop below produces).
 JXLB_HD_NOINLINE int DecodeLfGroupSection(BitReader& br, const FrameDev& f, uint32_t lfg, StreamScratch& s,
-                                          uint32_t max_local_nodes) {
+                                          uint32_t max_local_nodes, bool place_blocks = true) {
   uint32_t cx0, cy0, w8, h8, w64, h64;
   LfGroupRect(f, lfg, &cx0, &cy0, &w8, &h8, &w64, &h64);
   const uint32_t nlf = f.num_lf_groups;
@@ -229,6 +231,7 @@ JXLB_HD_NOINLINE int DecodeLfGroupSection(BitReader& br, const FrameDev& f, uint
   if (st != kOk) return st;
   if (mh.nb_transforms) return kErrUnsupported;
   s.arena.used = arena_mark;
+  if (!place_blocks) return br.Overrun() ? kErrTruncated : kOk;
   // ---- block placement: next BlockInfo entry goes to the first uncovered cell in raster order
   for (uint32_t y = 0; y < h8; ++y) {
     uint8_t* row = f.cell_strategy + (size_t) (cy0 + y) * f.w8 + cx0;
