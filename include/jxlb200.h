@@ -133,7 +133,9 @@ JXLB_API int jxlb_batch_fetch(jxlb_batch* b, size_t index, jxlb_image* out);
 /* Device pointer + size of result `index` after jxlb_batch_run (valid until the next run / free). */
 JXLB_API const void* jxlb_batch_device_pixels(const jxlb_batch* b, size_t index, size_t* bytes);
 /* Device time (ms, CUDA events on the decode stream) of the last run: [0] upload, [1] LF sections, [2] group sections,
-   [3] LF dequant + smoothing, [4] dequant + inverse transforms, [5] filters + colour + pack, [6] download, [7] all kernels. */
+   [3] reconstruction phase (per image: LF dequant + smoothing, inverse transforms, filters + colour + pack, interleaved),
+   [4] dequant + inverse-transform kernels, [5] filter + colour + pack kernels ([4], [5]: mean of the sampled launches x images),
+   [6] download, [7] all kernels. */
 JXLB_API void jxlb_batch_stage_ms(const jxlb_batch* b, float* ms8);
 /* Same layout, averaged over every run of the batch waited for so far; *runs (may be NULL) = how many. */
 JXLB_API void jxlb_batch_stage_ms_mean(const jxlb_batch* b, float* ms8, int32_t* runs);

@@ -299,7 +299,7 @@ def last_batch_timings():
 class PreparedBatch:
     """Throughput interface: parse + upload once (inputs resident in HBM), run the kernels repeatedly, results stay in HBM."""
 
-    STAGES = ("upload", "lf_sections", "group_sections", "lf_final", "inverse_transforms", "filters_color_pack", "download", "all_kernels")
+    STAGES = ("upload", "lf_sections", "group_sections", "reconstruction_phase", "inverse_transforms", "filters_color_pack", "download", "all_kernels")
 
     def __init__(self, datas, width=-1, height=-1, config=PreferredColorConfig.RGBA_8888, scale_mode=ScaleMode.FIT,
                  filt=JxlResizeFilter.MITCHELL_NETRAVALI, api_level=34, device=-1):

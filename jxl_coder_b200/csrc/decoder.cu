@@ -130,6 +130,7 @@ HostPool& Pool() {
 
 struct BatchBuffers {
   DevBuffer const_buf, work_buf, scratch_buf, meta_buf, stage_out, final_out;
+  DevBuffer xyb_ring;  // kXybRing XYB plane sets shared by the images of a batch (see Batch::Run)
   PinnedBuffer staging, status_host;
 };
 
@@ -418,6 +419,16 @@ struct Batch {
   bool ac_fast = true;        // every lane-decoded image has an alias-table (ANS) AC code
   ScratchLayout sl_single{}, sl_lf{}, sl_grp{};
   size_t const_total = 0, work_total = 0, stage_total = 0, final_total = 0, meta_total = 0;
+  // Reconstruction runs image by image (LF final -> inverse transforms -> filters + colour + pack -> download), so the
+  // 12 B/pixel XYB planes between the two kernels only ever exist for a few images at a time: a ring of kXybRing plane
+  // sets replaces one set per image (12 GB for a 64 x 4096^2 batch), and a finished image starts its download while the
+  // next ones are still being reconstructed.
+  static constexpr size_t kXybRing = 4;
+  size_t xyb_slot_bytes = 0;
+  // per-kernel timing: every kTimeEvery-th VarDCT image of a run brackets its inverse-transform and filter kernels with
+  // events (stage times = mean over the sampled launches x number of images)
+  static constexpr size_t kTimeEvery = 4;
+  size_t n_vardct = 0;
   uint32_t nframes = 0, status_total = 0;
   std::vector<size_t> final_off, final_bytes;
   const FrameDev* frames_d = nullptr;
@@ -441,6 +452,17 @@ struct Batch {
   int pending_runs = 0, run_index = 0;
   double stage_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int stage_runs = 0;
+  std::vector<cudaEvent_t> sample_ev[kEventSets];  // 3 events per sampled image: before IDCT, after IDCT, after filters
+  size_t sampled_in_run[kEventSets] = {};
+  void EnsureSampleEvents() {
+    const size_t want = 3 * ((n_vardct + kTimeEvery - 1) / kTimeEvery + 1);
+    std::vector<cudaEvent_t>& v = sample_ev[run_index];
+    while (v.size() < want) {
+      cudaEvent_t e = nullptr;
+      CUDA_OK(cudaEventCreate(&e));
+      v.push_back(e);
+    }
+  }
   cudaEvent_t span_start = nullptr, span_end = nullptr;  // first run start / last run end since ResetStats
   bool span_armed = true;
   bool events = false, upload_timed = false;
@@ -456,6 +478,8 @@ struct Batch {
     if (events)
       for (auto& set : ev_ring)
         for (auto& e : set) cudaEventDestroy(e);
+    for (auto& v : sample_ev)
+      for (auto& e : v) cudaEventDestroy(e);
     if (span_start) cudaEventDestroy(span_start);
     if (span_end) cudaEventDestroy(span_end);
     if (own_streams) {
@@ -480,6 +504,7 @@ struct Batch {
     freed(own.meta_buf);
     freed(own.stage_out);
     freed(own.final_out);
+    freed(own.xyb_ring);
     freeh(own.staging);
     freeh(own.status_host);
   }
@@ -504,6 +529,8 @@ struct Batch {
       p.stage_off = stage_total;
       // the fused VarDCT kernel packs straight into final_out; only modular frames (and the unfused debug path) stage RGBA
       if (p.plan.proto.encoding != 0 || UseUnfusedFilters()) stage_total += Align256(p.stage_stride * p.md.ysize);
+      xyb_slot_bytes = std::max(xyb_slot_bytes, Align256(p.plan.xyb_bytes * (UseUnfusedFilters() ? 2 : 1)));
+      if (p.plan.proto.encoding == 0) ++n_vardct;
       final_bytes[i] = (size_t) p.md.xsize * FormatBytesPerPixel((uint32_t) p.format) * p.md.ysize;
       final_off[i] = final_total;
       final_total += Align256(final_bytes[i]);
@@ -602,6 +629,7 @@ struct Batch {
     buf->meta_buf.Ensure(meta_total);
     buf->stage_out.Ensure(stage_total);
     buf->final_out.Ensure(final_total);
+    buf->xyb_ring.Ensure(xyb_slot_bytes * std::min(kXybRing, std::max<size_t>(n, 1)));
     buf->staging.Ensure(const_total + meta_total);
     buf->status_host.Ensure((size_t) status_total * 4 + 256);
     sl_lf.base = buf->scratch_buf.p;
@@ -614,7 +642,13 @@ struct Batch {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) return;
       FillConstRegion(p.plan, p.cs.data(), p.fh, p.g, stg + p.const_off);
-      frames[frame_of[i]] = BindFrameDev(p.plan, buf->const_buf.p + p.const_off, buf->work_buf.p + p.work_off);
+      FrameDev fd = BindFrameDev(p.plan, buf->const_buf.p + p.const_off, buf->work_buf.p + p.work_off);
+      if (p.plan.xyb_bytes) {
+        uint8_t* slot = buf->xyb_ring.p + (i % kXybRing) * xyb_slot_bytes;
+        fd.xyb0 = reinterpret_cast<float*>(slot);
+        fd.xyb1 = UseUnfusedFilters() ? reinterpret_cast<float*>(slot + p.plan.xyb_bytes) : fd.xyb0;
+      }
+      frames[frame_of[i]] = fd;
     });
     uint8_t* meta_h = stg + const_total;
     memcpy(meta_h, frames.data(), nframes * sizeof(FrameDev));
@@ -695,18 +729,9 @@ struct Batch {
     LaunchAcLanes(frames_d, jobs_ac_cta_d, (uint32_t) jobs_ac_cta.size(), ctx->nat_dev, ac_smem_code_bytes, ac_fast, s);
     LaunchGroupModular(frames_d, jobs_lane_mod_d, (uint32_t) jobs_lane_mod.size(), sl_grp, s);
     CUDA_OK(cudaEventRecord(ev[4], s));
-    for (size_t i = 0; i < n; ++i) {
-      if (ps[i].status != JXLB_OK) continue;
-      const FrameDev& f = frames[frame_of[i]];
-      if (f.encoding == 0) LaunchLfFinal(f, s);
-    }
-    CUDA_OK(cudaEventRecord(ev[5], s));
-    for (size_t i = 0; i < n; ++i) {
-      if (ps[i].status != JXLB_OK) continue;
-      const FrameDev& f = frames[frame_of[i]];
-      if (f.encoding == 0) LaunchRecon(f, ctx->nt_dev, s);
-    }
-    CUDA_OK(cudaEventRecord(ev[6], s));
+    EnsureSampleEvents();
+    cudaEvent_t* sev = sample_ev[run_index].data();
+    size_t sampled = 0, vd = 0;
     for (size_t i = 0; i < n; ++i) {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
@@ -723,13 +748,6 @@ struct Batch {
         od.alpha_channel = (int32_t) (f.num_color_mod_channels + (uint32_t) ai);
         od.alpha_bits = p.md.extra[ai].bits;
       }
-      const bool fused = f.encoding == 0 && !UseUnfusedFilters();
-      if (f.encoding == 0 && !fused) {
-        int cur = LaunchFilters(f, s);
-        LaunchColor(f, p.cp, ctx->nt_dev, cur ? f.xyb1 : f.xyb0, od, s);
-      } else if (f.encoding != 0) {
-        LaunchModularToRgba(f, od, s);
-      }
       PackParams pk;  // ReformatColorConfig
       pk.src = od.data;
       pk.src_stride = od.stride_bytes;
@@ -742,14 +760,34 @@ struct Batch {
       pk.attenuate = !p.alpha_premultiplied ? 1 : 0;
       pk.dst_stride = pk.width * FormatBytesPerPixel(pk.format);
       pk.dst = buf->final_out.p + final_off[i];
-      if (fused) LaunchFilterColorPack(f, p.cp, ctx->nt_dev, od, pk, s);
-      else LaunchPack(pk, s);
+      if (f.encoding == 0) {
+        const bool timed = (vd++ % kTimeEvery) == 0;
+        LaunchLfFinal(f, s);
+        if (timed) CUDA_OK(cudaEventRecord(sev[3 * sampled], s));
+        LaunchRecon(f, ctx->nt_dev, s);
+        if (timed) CUDA_OK(cudaEventRecord(sev[3 * sampled + 1], s));
+        if (!UseUnfusedFilters()) {
+          LaunchFilterColorPack(f, p.cp, ctx->nt_dev, od, pk, s);
+        } else {
+          int cur = LaunchFilters(f, s);
+          LaunchColor(f, p.cp, ctx->nt_dev, cur ? f.xyb1 : f.xyb0, od, s);
+          LaunchPack(pk, s);
+        }
+        if (timed) {
+          CUDA_OK(cudaEventRecord(sev[3 * sampled + 2], s));
+          ++sampled;
+        }
+      } else {
+        LaunchModularToRgba(f, od, s);
+        LaunchPack(pk, s);
+      }
       if (i < host_dst.size() && host_dst[i]) {
         CUDA_OK(cudaEventRecord(img_ev[i], s));
         CUDA_OK(cudaStreamWaitEvent(copy_stream, img_ev[i], 0));
         CUDA_OK(cudaMemcpyAsync(host_dst[i], buf->final_out.p + final_off[i], final_bytes[i], cudaMemcpyDeviceToHost, copy_stream));
       }
     }
+    sampled_in_run[run_index] = sampled;
     CUDA_OK(cudaEventRecord(ev[7], s));
     CUDA_OK(cudaEventRecord(span_end, s));
     ran = true;
@@ -775,16 +813,24 @@ struct Batch {
       upload_timed = true;
       stage_ms[1] = el(e[2], e[3]);
       stage_ms[2] = el(e[3], e[4]);
-      stage_ms[3] = el(e[4], e[5]);
-      stage_ms[4] = el(e[5], e[6]);
-      stage_ms[5] = el(e[6], e[7]);
+      // reconstruction runs image by image: [3] = the whole phase, [4] / [5] = mean sampled kernel time x images
+      stage_ms[3] = el(e[4], e[7]);
+      {
+        double idct = 0, filt = 0;
+        const size_t ns = sampled_in_run[set];
+        for (size_t k = 0; k < ns; ++k) {
+          idct += el(sample_ev[set][3 * k], sample_ev[set][3 * k + 1]);
+          filt += el(sample_ev[set][3 * k + 1], sample_ev[set][3 * k + 2]);
+        }
+        stage_ms[4] = ns ? (float) (idct / ns * n_vardct) : 0.f;
+        stage_ms[5] = ns ? (float) (filt / ns * n_vardct) : 0.f;
+      }
       stage_ms[6] = finished[set] ? el(e[7], e[8]) : 0.f;
       stage_ms[7] = el(e[2], e[7]);
       finished[set] = false;
       if (ctx->timeline)
-        fprintf(stderr, "[timeline] batch %p run: start %.2f lf_done %.2f groups_done %.2f lf_final_done %.2f recon_done %.2f filter_done %.2f ms\n",
-                (void*) this, el(ctx->origin, e[2]), el(ctx->origin, e[3]), el(ctx->origin, e[4]), el(ctx->origin, e[5]),
-                el(ctx->origin, e[6]), el(ctx->origin, e[7]));
+        fprintf(stderr, "[timeline] batch %p run: start %.2f lf_done %.2f groups_done %.2f recon+filter_done %.2f ms\n", (void*) this,
+                el(ctx->origin, e[2]), el(ctx->origin, e[3]), el(ctx->origin, e[4]), el(ctx->origin, e[7]));
       for (int i = 0; i < 8; ++i) stage_sum[i] += stage_ms[i];
       ++stage_runs;
     }
@@ -834,7 +880,7 @@ struct Batch {
     CollectRuns();
     tm.ms[0] = stage_ms[0];
     tm.ms[1] = stage_ms[1] + stage_ms[2];
-    tm.ms[2] = stage_ms[3] + stage_ms[4];
+    tm.ms[2] = stage_ms[4];
     tm.ms[3] = stage_ms[5];
     tm.ms[4] = stage_ms[6];
     tm.ms[5] = stage_ms[7] + stage_ms[6];

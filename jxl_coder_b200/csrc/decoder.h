@@ -46,7 +46,7 @@ void BatchStageMsMean(const Batch* b, float* ms8, int* runs);
 void ResetBatchStats(Batch* b);
 float BatchSpanMs(const Batch* first, const Batch* last);
 int FetchBatchImage(Batch* b, size_t i, DecodedImage* out);
-// ms8: [0] upload, [1] LF sections, [2] group sections, [3] LF dequant+smoothing, [4] dequant+inverse transforms,
+// ms8: [0] upload, [1] LF sections, [2] group sections, [3] reconstruction phase, [4] dequant+inverse transform kernels (sampled),
 //      [5] filters+colour+pack, [6] download, [7] all kernels
 void BatchStageMs(const Batch* b, float* ms8);
 const void* BatchDevicePixels(const Batch* b, size_t i, size_t* bytes);

@@ -119,9 +119,7 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
     p.coef_bytes = (size_t) 3 * f.coef_h * f.coef_stride * 2;
     p.off_coef = take(p.coef_bytes);
     p.off_lf = take((size_t) 3 * f.h8 * f.lf_stride * 4);
-    p.off_xyb0 = take((size_t) 3 * f.plane_h * f.plane_stride * 4);
-    // second XYB buffer: only the unfused per-stage filter kernels (debug aid) ping-pong between two
-    p.off_xyb1 = UseUnfusedFilters() ? take((size_t) 3 * f.plane_h * f.plane_stride * 4) : p.off_xyb0;
+    p.xyb_bytes = (size_t) 3 * f.plane_h * f.plane_stride * 4;
   }
   if (f.num_mod_channels) p.off_mod = take((size_t) f.num_mod_channels * f.height * f.mod_stride * 4);
   p.work_bytes = o;
@@ -176,8 +174,8 @@ FrameDev BindFrameDev(const FramePlan& p, const uint8_t* cb, uint8_t* wb) {
     f.group_ac_end_bit = reinterpret_cast<uint64_t*>(wb + p.off_group_ac_end);
     f.coef = reinterpret_cast<int16_t*>(wb + p.off_coef);
     f.lf = reinterpret_cast<float*>(wb + p.off_lf);
-    f.xyb0 = reinterpret_cast<float*>(wb + p.off_xyb0);
-    f.xyb1 = reinterpret_cast<float*>(wb + p.off_xyb1);
+    f.xyb0 = nullptr;  // bound by the caller (plan.xyb_bytes each)
+    f.xyb1 = nullptr;
   }
   if (f.num_mod_channels) f.mod = reinterpret_cast<int32_t*>(wb + p.off_mod);
   return f;

@@ -24,6 +24,7 @@ struct Emu {
   FrameGlobals g;
   FramePlan plan;
   std::vector<uint8_t> cs, cregion, wregion;
+  std::vector<float> xyb;
   FrameDev f;
   int status = 0;
   int failed_stream = -1;
@@ -80,6 +81,8 @@ void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, si
   e->wregion.assign(e->plan.work_bytes, 0);
   FillConstRegion(e->plan, e->cs.data(), e->fh, e->g, e->cregion.data());
   e->f = BindFrameDev(e->plan, e->cregion.data(), e->wregion.data());
+  e->xyb.assign(e->plan.xyb_bytes / sizeof(float), 0.0f);
+  e->f.xyb0 = e->xyb.data();
   const FrameDev& f = e->f;
   // scratch
   std::vector<uint8_t> arena_mem(8u << 20), hf_mem(8u << 20);
