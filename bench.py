@@ -28,6 +28,9 @@ MPIX_PER_IMAGE = SIZE * SIZE / 1e6
 # algorithmic bytes per pixel of the inverse-transform kernel (SURVEY.md §8d "if split: K_idct"):
 # 3 x int16 coefficients read (6 B) + per-cell metadata and LF (0.25 B) + 3 x f32 XYB samples written (12 B)
 IDCT_BYTES_PER_PIXEL = 18.25
+# dram__bytes_read.sum + dram__bytes_write.sum of one ReconRegionKernel launch (one 4096x4096 image), ncu --set full,
+# profiles/r1d_ncu_recon_filter.txt
+TRAFFIC_BYTES_PER_IMAGE = 269_600_000
 
 
 def load_inputs(batch=BATCH, distinct=DISTINCT, size=SIZE):
@@ -106,7 +109,7 @@ def run_reference(args):
     datas = load_inputs()
     cores = os.cpu_count() or 1
     # one step = a bounded sample of the 64-image workload: `cores` concurrent decodes x 1 image each
-    sample_images = max(cores, 8)
+    sample_images = 2 * max(cores, 8)
     vals = []
     for i in range(args.warmup):
         cpu_reference(datas, cores, 0, 1)
@@ -185,6 +188,14 @@ def run_ours(args):
         stage_n += nruns
     assert stage_n == args.steps, (stage_n, args.steps)
     batch = batches[(args.steps - 1) % contexts]
+    # roofline pass: the same step run ALONE (one context, nothing overlapping), so that the CUDA-event time of the
+    # dominant kernel is its own duration rather than its share of a GPU it splits with three other batches
+    alone_ms = {}
+    if args.steps > 0:
+        batch.reset_stats()
+        for _ in range(2):
+            assert batch.run() == 0
+        alone_ms, _ = batch.stage_ms_mean()
     # correctness spot check of what was just timed (against the reference when it is present on this box)
     parity = None
     try:
@@ -255,7 +266,7 @@ def run_ours(args):
         return
     steps = args.steps
     stages = {k: round(v / max(1, stage_n), 3) for k, v in stage_acc.items()}
-    idct_ms = stages["inverse_transforms"]
+    idct_ms = alone_ms.get("inverse_transforms", 0.0) or stages["inverse_transforms"]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -279,8 +290,12 @@ def run_ours(args):
                 "api": "jxlb_decode_batch (synchronous, host buffers -> pinned host RGBA), %d concurrent caller threads" % callers},
         "gpu_launches": int(launches_per_step * steps),
         "stages_ms_per_step": stages,
+        "stages_ms_alone": {k: round(v, 3) for k, v in alone_ms.items()},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                     "traffic": TRAFFIC_BYTES_PER_IMAGE * BATCH if TRAFFIC_BYTES_PER_IMAGE else None,
+                     "kernel_ms": round(idct_ms, 3), "launches": 2 * BATCH,
+                     "how": "64 ReconRegionKernel + 64 ReconLargeKernel launches of one 64-image batch run alone (no other context in flight) after the timed region; every 4th image's launch pair is bracketed by CUDA events on its stream, mean x 64; peak = burst HBM copy bandwidth",
+                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "algorithmic_bytes_per_pixel": IDCT_BYTES_PER_PIXEL},
         "clocks": sampler.summary(),
         "parity_spot_check": parity,
@@ -291,7 +306,7 @@ def run_ours(args):
             from oracle import refjxl
             if refjxl.available():
                 cores = os.cpu_count() or 1
-                v, dt, nimg = cpu_reference(datas, cores, 0, 1)
+                v, dt, nimg = cpu_reference(datas, cores, 0, 2)
                 out["cpu_baseline"] = {"value": round(v, 2), "unit": "MP/s", "cores": cores, "kind": "reference",
                                        "sample": "%d concurrent DecodeJpegXlOneShot calls (reference's prebuilt libjxl 0.12.0, SSE2) on %d of the 4096x4096 images, %.1f s" % (cores, nimg, dt)}
             else:
@@ -310,7 +325,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contexts", type=int, default=int(os.environ.get("JXLB_BENCH_CONTEXTS", "4")),
+    ap.add_argument("--contexts", type=int, default=int(os.environ.get("JXLB_BENCH_CONTEXTS", "6")),
                     help="prepared batches (decode contexts) alternated by the device-resident measurement")
     ap.add_argument("--callers", type=int, default=int(os.environ.get("JXLB_BENCH_CALLERS", "4")),
                     help="host threads issuing jxlb_decode_batch calls in the e2e measurement")
