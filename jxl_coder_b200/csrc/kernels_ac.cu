@@ -53,6 +53,12 @@ struct AcTables {
   uint8_t freq[64];
 };
 
+// ZeroDensityFreqCtx (frame.h) in closed form for k < 64: 0, 0, 1 .. 14, then pairs 15 .. 22, then quads 23 .. 30.
+// Saves a dependent shared-memory load on every coefficient.
+__device__ __forceinline__ uint32_t FreqCtxArith(uint32_t k) {
+  return k < 2 ? 0u : k < 16 ? k - 1u : k < 32 ? (k >> 1) + 7u : (k >> 2) + 15u;
+}
+
 // Bit reader of one lane: like BitReader, plus a one-word lookahead so that a refill never waits for memory (the load
 // issued by refill n is consumed by refill n + 1).  Lanes refill at different iterations; keeping the load off the
 // critical path is what stops one lane's L2 miss from stalling the other lanes of its warp.
@@ -183,6 +189,7 @@ __global__ void __launch_bounds__(kAcCtaGroups * 32 / kLanes) AcLaneKernel(const
   // per-(block, channel) state
   bool in_coeffs = false;
   uint32_t nz = 0, k = 0, prev = 0, h0 = 0, c = 1;
+  uint32_t nnz_ctx = 0;  // tabs->nnz[(nz + covered - 1) >> l2], refreshed only when nz changes
   const uint16_t* order = nat.pool;
   int16_t* plane = f.coef;
   while (bi < nblocks) {
@@ -229,8 +236,7 @@ __global__ void __launch_bounds__(kAcCtaGroups * 32 / kLanes) AcLaneKernel(const
       h0 = ctx_off + nbc * kNonZeroBuckets + kZeroDensityContexts * bc;
     } else {
       pos_pref = __ldg(order + k);  // used only if this coefficient is non-zero; issued early to hide its latency
-      const uint32_t nl = (nz + covered - 1) >> l2;
-      ctx = h0 + ((uint32_t) tabs->nnz[nl] + tabs->freq[k >> l2]) * 2 + prev;
+      ctx = h0 + (nnz_ctx + FreqCtxArith(k >> l2)) * 2 + prev;
     }
     uint32_t u;
     if (kFast) {
@@ -253,6 +259,7 @@ __global__ void __launch_bounds__(kAcCtaGroups * 32 / kLanes) AcLaneKernel(const
         in_coeffs = true;
         k = covered;
         prev = nz > size / 16 ? 0 : 1;
+        nnz_ctx = tabs->nnz[(nz + covered - 1) >> l2];
         const uint32_t ooff = f.orders.offset[ord][c];
         order = (ooff & kOrderInFramePool) ? f.order_pool + (ooff & ~kOrderInFramePool) : nat.pool + ooff;
         plane = f.coef + c * cplane + (size_t) (gby0 + by) * 8 * coef_stride + (gbx0 + bx) * 8;
@@ -275,6 +282,7 @@ __global__ void __launch_bounds__(kAcCtaGroups * 32 / kLanes) AcLaneKernel(const
       }
       prev = u != 0 ? 1 : 0;
       nz -= prev;
+      if (prev) nnz_ctx = tabs->nnz[(nz + covered - 1) >> l2];
       ++k;
       if (nz == 0) {
         in_coeffs = false;
