@@ -220,7 +220,9 @@ def run_ours(args):
     # ---- end to end through the public batch call: host buffers in, pinned host pixels out.  The reference's entry
     # points are re-entrant and are called from several app threads at once, so the e2e arm issues its
     # steps from `callers` host threads, each step one synchronous jxlb_decode_batch call on the whole 64-image batch.
-    callers = max(1, args.callers)
+    # default: 6 caller threads on 1-2 GPUs; fewer per rank on 4 / 8 GPUs, where the ranks share the host's cores and RAM
+    # (every caller keeps 4 GiB of pinned result buffers in the pool)
+    callers = args.callers if args.callers > 0 else (6 if world <= 2 else 4 if world <= 4 else 2)
 
     def e2e_steps_run(nsteps):
         nxt = [0]
@@ -251,7 +253,7 @@ def run_ours(args):
     e2e_steps_run(2 * callers if args.warmup else 0)  # every decode slot allocates its buffers + pinned pool once
     barrier()
     t1 = time.perf_counter()
-    e2e_steps = max(1, args.steps)
+    e2e_steps = max(1, args.steps, 3 * callers)
     e2e_steps_run(e2e_steps)
     barrier()
     e2e_wall = time.perf_counter() - t1
@@ -281,12 +283,13 @@ def run_ours(args):
         "config": {"workload": "batch of 64 synthetic 4096x4096 lossy VarDCT (q=90, effort 7) JXL -> RGBA_8888 per GPU (configs[1]); %d distinct images cycled" % DISTINCT,
                    "images_per_gpu": BATCH, "l2": "inputs_larger_than_L2 (each step touches > 30 GB of planes)",
                    "value_is": "kernels only, codestreams + host-parsed tables resident in HBM; %d prepared batches (decode contexts) run alternately with jxlb_batch_run_async, one batch run per step; device time = CUDA events first-run start -> last-run end" % contexts,
-                   "contexts": contexts, "e2e_callers": callers,
+                   "contexts": contexts,
                    "stages_note": "stages_ms_per_step are per-run CUDA-event intervals on the run's own stream; with 2 contexts they include time shared with the other context's kernels",
                    "roofline_kernel": "ReconRegionKernel + ReconLargeKernel (dequant + CfL + LLF + inverse VarDCT -> XYB f32 planes)",
                    "wall_ms_per_step": round(1e3 * wall / steps, 2)},
         "e2e": {"value": round(e2e_value, 1), "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": round(1e3 * float(t_e2e.item()) / e2e_steps, 2),
+                "callers": callers,
                 "api": "jxlb_decode_batch (synchronous, host buffers -> pinned host RGBA), %d concurrent caller threads" % callers},
         "gpu_launches": int(launches_per_step * steps),
         "stages_ms_per_step": stages,
@@ -327,7 +330,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--contexts", type=int, default=int(os.environ.get("JXLB_BENCH_CONTEXTS", "6")),
                     help="prepared batches (decode contexts) alternated by the device-resident measurement")
-    ap.add_argument("--callers", type=int, default=int(os.environ.get("JXLB_BENCH_CALLERS", "4")),
+    ap.add_argument("--callers", type=int, default=int(os.environ.get("JXLB_BENCH_CALLERS", "0")),
                     help="host threads issuing jxlb_decode_batch calls in the e2e measurement")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -142,23 +142,28 @@ struct Slot {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   BatchBuffers spare;
 };
-constexpr int kSlots = 4;
+constexpr int kSlots = 8;
 
 struct DeviceContext {
   int device = 0;
   std::mutex mu;  // guards lazily created state below
   Slot slots[kSlots];
   std::atomic<uint32_t> next_slot{0};
-  // LF-stage tokens (JXLB_LF_TOKENS=n, default 0 = off).  The LF-group kernel is latency-bound (one lane per 2048x2048
+  // LF-stage tokens (JXLB_LF_TOKENS=n for prepared batches, default 0 = off; JXLB_LF_TOKENS_E2E=n for jxlb_decode_batch,
+  // default 2).  The LF-group kernel is latency-bound (one lane per 2048x2048
   // LF group) and leaves the GPU almost idle.  With n > 0 each Run() waits for the LF stage issued n launches earlier
   // before starting its own, which STAGGERS the batches in flight on different streams (one runs its LF stage while the
   // others run their throughput kernels).  Measured on B200 (profiles/r1c_overlap_notes.txt): the LF warps then lose
   // ~45 % of their speed to issue-slot contention with the dense kernels sharing their SM sub-partitions, and the
-  // default -- several batches entering their LF stage together, then sharing the GPU for the dense stages -- wins.
+  // default -- several batches entering their LF stage together, then sharing the GPU for the dense stages -- wins when
+  // the results stay in HBM.  With host outputs the picture flips: batches in lockstep also finish together and their
+  // 4 GiB downloads pile up on the PCIe link after the kernels, while two tokens keep the link busy throughout
+  // (e2e 143 -> 117 ms per 64-image step with 6 callers).
   static constexpr int kLfEvents = 32;
   cudaEvent_t lf_ev[kLfEvents]{};
   uint64_t lf_count = 0;
-  int lf_tokens = 0;
+  int lf_tokens = 0;      // prepared batches (results stay in HBM)
+  int lf_tokens_e2e = 2;  // jxlb_decode_batch: staggering also spreads the result downloads over the PCIe link
   cudaEvent_t origin = nullptr;  // JXLB_TIMELINE=1: stage boundaries of every run are printed relative to this event
   bool timeline = false;
   NumericTables* nt_dev = nullptr;
@@ -174,6 +179,7 @@ struct DeviceContext {
     }
     for (auto& e : lf_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (const char* e = getenv("JXLB_LF_TOKENS")) lf_tokens = std::max(0, atoi(e));  // 0 = no staggering
+    if (const char* e = getenv("JXLB_LF_TOKENS_E2E")) lf_tokens_e2e = std::max(0, atoi(e));
     timeline = getenv("JXLB_TIMELINE") != nullptr;
     CUDA_OK(cudaEventCreate(&origin));
     CUDA_OK(cudaEventRecord(origin, slots[0].stream));
@@ -710,14 +716,18 @@ struct Batch {
       if (p.status != JXLB_OK) continue;
       uint8_t* wb = buf->work_buf.p + p.work_off;
       CUDA_OK(cudaMemsetAsync(wb + p.plan.off_status, 0xFF, (size_t) p.plan.num_streams * 4, s));
-      if (p.plan.coef_bytes) CUDA_OK(cudaMemsetAsync(wb + p.plan.off_coef, 0, p.plan.coef_bytes, s));
+      if (p.plan.coef_bytes) {
+        if (p.plan.coef_bytes % 16 == 0) LaunchFill(wb + p.plan.off_coef, p.plan.coef_bytes, 0u, s);
+        else CUDA_OK(cudaMemsetAsync(wb + p.plan.off_coef, 0, p.plan.coef_bytes, s));
+      }
     }
     LaunchSingleSectionFrames(frames_d, jobs_single_d, (uint32_t) jobs_single.size(), ctx->nat_dev, sl_single, s);
-    if (!jobs_lf.empty() && ctx->lf_tokens > 0) {
+    const int tokens = host_dst.empty() ? ctx->lf_tokens : ctx->lf_tokens_e2e;
+    if (!jobs_lf.empty() && tokens > 0) {
       std::lock_guard<std::mutex> l(ctx->mu);
       const uint64_t k = ctx->lf_count++;
-      if (k >= (uint64_t) ctx->lf_tokens)
-        CUDA_OK(cudaStreamWaitEvent(s, ctx->lf_ev[(k - ctx->lf_tokens) % DeviceContext::kLfEvents], 0));
+      if (k >= (uint64_t) tokens)
+        CUDA_OK(cudaStreamWaitEvent(s, ctx->lf_ev[(k - tokens) % DeviceContext::kLfEvents], 0));
       LaunchLfGroups(frames_d, jobs_lf_d, (uint32_t) jobs_lf.size(), sl_lf, s);
       CUDA_OK(cudaEventRecord(ctx->lf_ev[k % DeviceContext::kLfEvents], s));
     } else {
@@ -781,11 +791,8 @@ struct Batch {
         LaunchModularToRgba(f, od, s);
         LaunchPack(pk, s);
       }
-      if (i < host_dst.size() && host_dst[i]) {
-        CUDA_OK(cudaEventRecord(img_ev[i], s));
-        CUDA_OK(cudaStreamWaitEvent(copy_stream, img_ev[i], 0));
-        CUDA_OK(cudaMemcpyAsync(host_dst[i], buf->final_out.p + final_off[i], final_bytes[i], cudaMemcpyDeviceToHost, copy_stream));
-      }
+      // download: only the "image done" event is recorded here; Finish() enqueues each copy once its image is complete
+      if (i < host_dst.size() && host_dst[i]) CUDA_OK(cudaEventRecord(img_ev[i], s));
     }
     sampled_in_run[run_index] = sampled;
     CUDA_OK(cudaEventRecord(ev[7], s));
@@ -840,6 +847,18 @@ struct Batch {
   // Downloads the per-stream statuses (and, if host_out, the pixels), synchronises and resolves per-image status.
   void Finish(bool to_host, int output_device, std::vector<DecodedImage>* out) {
     cudaStream_t s = stream;
+    // Overlapped download (e2e path).  The calling thread would only block in a synchronize anyway, so it waits for each
+    // image's "done" event and enqueues that image's copy THEN.  Copies queued ahead of time with cudaStreamWaitEvent
+    // sit at the head of the copy engine's queue until their kernels finish and block every copy behind them --
+    // including the codestream uploads of the other batches in flight, whose kernels then start ~200 ms late
+    // (profiles/r1c_overlap_notes.txt).
+    if (to_host)
+      for (size_t i = 0; i < n && i < host_dst.size(); ++i) {
+        if (!host_dst[i] || ps[i].status != JXLB_OK) continue;
+        CUDA_OK(cudaEventSynchronize(img_ev[i]));
+        CUDA_OK(cudaMemcpyAsync(host_dst[i], buf->final_out.p + final_off[i], final_bytes[i], cudaMemcpyDeviceToHost, copy_stream));
+      }
+    if (ran) CUDA_OK(cudaEventSynchronize(ev[7]));  // every kernel of the run is done: the status words are final
     uint32_t* sh = reinterpret_cast<uint32_t*>(buf->status_host.p);
     for (size_t i = 0; i < n; ++i) {
       Parsed& p = ps[i];
@@ -851,7 +870,7 @@ struct Batch {
     for (size_t i = 0; i < n && out; ++i) {
       if (ps[i].status != JXLB_OK) continue;
       if (to_host && i < host_dst.size() && host_dst[i]) {
-        result[i] = host_dst[i];  // already in flight on the copy stream (see Run)
+        result[i] = host_dst[i];  // in flight on the copy stream (above)
         host_dst[i] = nullptr;
       } else if (to_host) {
         result[i] = Pool().Get(final_bytes[i]);
@@ -1013,8 +1032,10 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
     const auto t4 = Clock::now();
     b.Finish(output_device < 0, output_device, out);
     if (b.ctx->timeline)
-      fprintf(stderr, "[host] decode_batch n=%zu: parse %.1f  slot wait %.1f  stage+upload %.1f  launch %.1f  finish(wait) %.1f  total %.1f ms\n", n,
-              parse_ms, slot_ms, upload_ms, launch_ms, ms_since(t4), ms_since(t0));
+      fprintf(stderr, "[host] decode_batch n=%zu: parse %.1f  slot wait %.1f  stage+upload %.1f  launch %.1f  finish(wait) %.1f  total %.1f ms | device: "
+              "upload %.1f lf %.1f groups %.1f recon-phase %.1f download-tail %.1f kernels %.1f\n", n,
+              parse_ms, slot_ms, upload_ms, launch_ms, ms_since(t4), ms_since(t0), b.stage_ms[0], b.stage_ms[1], b.stage_ms[2], b.stage_ms[3],
+              b.stage_ms[6], b.stage_ms[7]);
     if (timings) *timings = b.tm;
   } catch (CudaError& e) {
     for (auto& p : b.ps)

@@ -8,6 +8,7 @@
 // shared memory (recon.h), per-pixel filters and colour conversion (pixel_stages.h).
 #include "kernels.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 
@@ -271,7 +272,22 @@ __global__ void __launch_bounds__(256) PackKernel(const PackParams p) {
 
 dim3 PixelGrid(uint32_t w, uint32_t h, uint32_t bx) { return dim3((w + bx - 1) / bx, h, 1); }
 
+// Fills n16 16-byte words.  Used instead of cudaMemsetAsync for the coefficient planes: large memsets are executed by a
+// copy engine, where they queue behind the 64 MiB result downloads of the other batches in flight.
+__global__ void __launch_bounds__(256) FillKernel(uint4* p, size_t n16, uint32_t v) {
+  const uint4 w = make_uint4(v, v, v, v);
+  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t) gridDim.x * blockDim.x) p[i] = w;
+}
+
 }  // namespace
+
+void LaunchFill(void* p, size_t bytes, uint32_t value32, cudaStream_t stream) {
+  if (!bytes) return;
+  const size_t n16 = bytes / 16;  // callers pass 16-byte multiples (regions are 256-byte aligned)
+  const unsigned blocks = (unsigned) std::min<size_t>((n16 + 255) / 256, 148 * 16);
+  FillKernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<uint4*>(p), n16, value32);
+  ++g_launches;
+}
 
 void LaunchPack(const PackParams& p, cudaStream_t stream) {
   PackKernel<<<PixelGrid(p.width, p.height, 256), 256, 0, stream>>>(p);

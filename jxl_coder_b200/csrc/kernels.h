@@ -41,6 +41,8 @@ struct AcCtaJob {
   uint32_t ngroups;
   uint32_t pad;
 };
+// Sets `bytes` (a multiple of 16, 16-byte aligned) to the repeated 32-bit value with a kernel.
+void LaunchFill(void* p, size_t bytes, uint32_t value32, cudaStream_t stream);
 void LaunchBuildGroupBlocks(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, cudaStream_t stream);
 uint32_t AcLaneSmemBytes(uint32_t code_bytes);
 void LaunchAcLanes(const FrameDev* frames, const AcCtaJob* jobs, uint32_t njobs, NaturalOrders nat, uint32_t smem_code_bytes,
