@@ -96,3 +96,94 @@ def test_larger_multi_group_image(J, ref):
     want = ref.decode_sampled(data, cfg=2)["pixels"].reshape(768, 1024, 4)
     out = J.JxlCoder.decode(data, 2).as_array()
     golden_lib.lossy_close(out, want, "1024x768")
+
+
+def _multi_group_inputs(ref, n=6):
+    """n different multi-group lossy images (LF-group kernel, lane-parallel AC, region IDCT, fast filter path)."""
+    from oracle import synth
+    out = []
+    for i in range(n):
+        w, h = 512 + 64 * (i % 3), 384 + 40 * (i % 2)
+        img = synth.synth_image(w, h, 20 + i)
+        out.append(cases._cached("rgb_lossy_%dx%d_s%d" % (w, h, 20 + i), lambda: ref.encode(img, w, h)))
+    return out
+
+
+def test_prepared_batches_overlap_and_match(J, ref):
+    """Two prepared batches run asynchronously on their own streams (the benchmark's device-resident mode): every run
+    of every batch must reproduce the synchronous result bit for bit, and the span timer must cover the runs."""
+    datas = _multi_group_inputs(ref)
+    want = [b.as_array().copy() for b in J.decode_batch(datas, config=2)]
+    for w, d in zip(want, datas):
+        r = ref.decode_sampled(d, cfg=2)
+        golden_lib.lossy_close(w, r["pixels"].reshape(w.shape), "multi-group")
+    a = J.PreparedBatch(datas, config=2)
+    b = J.PreparedBatch(list(reversed(datas)), config=2)
+    assert set(a.status) == {0} and set(b.status) == {0}
+    a.reset_stats()
+    b.reset_stats()
+    for _ in range(3):
+        assert a.run_async() == 0
+        assert b.run_async() == 0
+    assert a.wait() == 0 and b.wait() == 0
+    for i in range(len(datas)):
+        assert (a.fetch(i).as_array() == want[i]).all()
+        assert (b.fetch(i).as_array() == want[len(datas) - 1 - i]).all()
+    ms, runs = a.stage_ms_mean()
+    assert runs == 3 and ms["all_kernels"] > 0 and ms["inverse_transforms"] > 0
+    assert a.span_ms(b) > 0 and a.span_ms() > 0
+    a.free()
+    b.free()
+
+
+def test_concurrent_callers_match(J, ref):
+    """jxlb_decode_batch is re-entrant: four threads decoding at once (separate decode slots on one GPU) return the
+    same pixels as a single caller."""
+    import threading
+    datas = _multi_group_inputs(ref)
+    want = [b.as_array().copy() for b in J.decode_batch(datas, config=2)]
+    errs = []
+
+    def work(k):
+        try:
+            for _ in range(2):
+                order = list(range(len(datas)))
+                order = order[k:] + order[:k]
+                res = J.decode_batch([datas[i] for i in order], config=2)
+                for i, r in zip(order, res):
+                    if not (r.as_array() == want[i]).all():
+                        errs.append((k, i))
+        except Exception as e:  # noqa
+            errs.append(repr(e))
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+
+
+@pytest.mark.parametrize("cfg", [3, 5])
+def test_f16_and_1010102_on_lossy(J, ref, cfg):
+    """configs[2] / configs[3] output formats on a lossy multi-group image: RGBA_F16 and RGBA_1010102 are integer
+    re-packings of the 8-bit decode (Rgba8ToF16 / Rgba8ToRGBA1010102), so they must equal the reference's packing of
+    OUR 8-bit pixels exactly, and the reference's own output within the lossy tolerance."""
+    data = _multi_group_inputs(ref, 1)[0]
+    got = J.JxlCoder.decode(data, cfg)
+    r = ref.decode_sampled(data, cfg=cfg)
+    assert got.width == r["width"] and got.height == r["height"]
+    bpp = 8 if cfg == 3 else 4
+    mine = np.ascontiguousarray(got.pixels[:, : got.width * bpp])
+    theirs = np.ascontiguousarray(r["pixels"][:, : got.width * bpp])
+    if cfg == 3:
+        a = mine.view(np.float16).astype(np.float32)
+        b = theirs.view(np.float16).astype(np.float32)
+        assert np.abs(a - b).max() <= 1.0 / 255 + 1e-3
+        assert (a == b).mean() > 0.95
+    else:
+        a = mine.view(np.uint32)
+        b = theirs.view(np.uint32)
+        for sh in (0, 10, 20):
+            d = np.abs(((a >> sh) & 0x3FF).astype(int) - ((b >> sh) & 0x3FF).astype(int))
+            assert d.max() <= 4 and (d == 0).mean() > 0.95  # 1 LSB of 8 bits = 4 of 10
+        assert ((a >> 30) == (b >> 30)).all()
