@@ -1,13 +1,17 @@
-// JxlAnimatedImage entry points (include/jxlb200.h).  Round-1 state: the frame table (count, durations, loops, size)
-// is parsed on the CPU exactly as the reference's JxlAnimatedDecoder constructor does
-// (/root/reference/jxlcoder/src/main/cpp/interop/JxlAnimatedDecoder.hpp:68-185); per-frame pixel decode with
-// blending / reference slots is not implemented yet and reports JXLB_UNSUPPORTED.
+// JxlAnimatedImage entry points (include/jxlb200.h).  The frame table (count, durations, loops, size) is parsed on the
+// CPU exactly as the reference's JxlAnimatedDecoder constructor does
+// (/root/reference/jxlcoder/src/main/cpp/interop/JxlAnimatedDecoder.hpp:68-185).  getFrame(i) decodes displayed frame i
+// on the GPU through the still-image pipeline: the frames the reference's own JxlAnimatedEncoder writes are full-canvas
+// kReplace frames (interop/JxlAnimatedEncoder.hpp:111-118), i.e. independent pictures, so frame i needs no earlier
+// frame (which is also what lets a 120-frame animation spread over several GPUs).  Frames that need composition
+// (crops, blending, reference slots) report JXLB_UNSUPPORTED; so does a rescaling request.
 #include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/jxlb200.h"
+#include "decoder.h"
 #include "frame_parser.h"
 
 using namespace jxlb;
@@ -76,14 +80,35 @@ int32_t jxlb_anim_loops(const jxlb_anim* a) { return a ? (int32_t) a->md.num_loo
 int32_t jxlb_anim_width(const jxlb_anim* a) { return a ? (int32_t) a->md.xsize : 0; }
 int32_t jxlb_anim_height(const jxlb_anim* a) { return a ? (int32_t) a->md.ysize : 0; }
 int jxlb_anim_get_frame(jxlb_anim* a, int32_t frame, int32_t width, int32_t height, jxlb_image* out) {
-  (void) width;
-  (void) height;
-  if (out) {
-    memset(out, 0, sizeof *out);
-    snprintf(out->message, sizeof out->message, "animated frame decode is not implemented yet");
+  if (!out) return JXLB_BAD_ARG;
+  memset(out, 0, sizeof *out);
+  out->device = -1;
+  if (!a || frame < 0 || frame >= (int32_t) a->frames.size()) {
+    snprintf(out->message, sizeof out->message, "frame index out of range");
+    return JXLB_BAD_ARG;
   }
-  if (!a || frame < 0 || frame >= (int32_t) a->frames.size()) return JXLB_BAD_ARG;
-  return JXLB_UNSUPPORTED;
+  // JxlAnimatedDecoderCoordinator.cpp:162-: rescale only when both target dimensions are positive
+  const bool rescale = width > 0 && height > 0 && ((uint32_t) width != a->md.xsize || (uint32_t) height != a->md.ysize);
+  if (rescale) {
+    snprintf(out->message, sizeof out->message, "rescale (getFrame with a target size)");
+    return JXLB_UNSUPPORTED;
+  }
+  jxlb_request r{a->cs.data(), a->cs_len, -1, -1, a->cfg, a->scale_mode, a->filter};
+  std::vector<DecodedImage> res;
+  BatchTimings tm;
+  const int32_t fi = frame;
+  DecodeBatch(&r, 1, a->api_level, -1, -1, &res, &tm, &fi);
+  const DecodedImage& d = res[0];
+  out->data = d.data;
+  out->width = d.width;
+  out->height = d.height;
+  out->stride_bytes = d.stride_bytes;
+  out->format = d.format;
+  out->color_space = d.color_space;
+  out->premultiplied = d.premultiplied;
+  out->device = d.device;
+  snprintf(out->message, sizeof out->message, "%s", d.message.c_str());
+  return d.status;
 }
 void jxlb_anim_close(jxlb_anim* a) { delete a; }
 

@@ -286,7 +286,7 @@ int ColorSpaceTag(const ImageMetadata& md, int api) {
   return JXLB_CS_SRGB;
 }
 
-void ParseRequest(const jxlb_request& r, int api, Parsed* p) {
+void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = -1) {
   if (CheckPreconditions(r, api, p)) return;
   if (!r.data || r.len == 0) {
     Fail(p, JXLB_INVALID_JXL, "empty input");
@@ -332,8 +332,8 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p) {
     Fail(p, JXLB_UNSUPPORTED, "float samples");
     return;
   }
-  // frames: decode the last one; earlier frames must not be needed
-  int nframes = 0;
+  // frames: decode the last one (or displayed frame `target_frame`); earlier frames must not be needed
+  int nframes = 0, displayed = 0;
   for (;;) {
     p->fh = FrameHeader();
     st = ParseFrameHeader(p->cs.data(), p->cs.size(), p->cs_len, md, frame_bit, &p->fh, &err);
@@ -342,7 +342,13 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p) {
       return;
     }
     ++nframes;
-    if (p->fh.is_last) break;
+    const bool shown = p->fh.frame_type == 0 || p->fh.frame_type == 3;
+    if (shown) ++displayed;
+    if (target_frame >= 0 ? (shown && displayed - 1 == target_frame) : p->fh.is_last) break;
+    if (p->fh.is_last) {
+      Fail(p, JXLB_BAD_ARG, "frame index out of range");
+      return;
+    }
     frame_bit = p->fh.end_byte * 8;
   }
   const FrameHeader& fh = p->fh;
@@ -516,11 +522,11 @@ struct Batch {
   }
 
   // Host side: parse every request, lay out the batch.  No CUDA calls.
-  void Parse(const jxlb_request* reqs, size_t count, int api) {
+  void Parse(const jxlb_request* reqs, size_t count, int api, const int32_t* frame_index = nullptr) {
     n = count;
     api_level = api <= 0 ? 34 : api;
     ps.assign(n, Parsed());
-    ParallelFor(n, [&](size_t i) { ParseRequest(reqs[i], api_level, &ps[i]); });
+    ParallelFor(n, [&](size_t i) { ParseRequest(reqs[i], api_level, &ps[i], frame_index ? frame_index[i] : -1); });
     frame_of.assign(n, 0);
     final_off.assign(n, 0);
     final_bytes.assign(n, 0);
@@ -994,13 +1000,13 @@ void CopyStatuses(const Batch& b, std::vector<DecodedImage>* out, int* overall) 
 }  // namespace
 
 int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device, std::vector<DecodedImage>* out,
-                BatchTimings* timings) {
+                BatchTimings* timings, const int32_t* frame_index) {
   using Clock = std::chrono::steady_clock;
   const auto t0 = Clock::now();
   auto ms_since = [&](Clock::time_point a) { return std::chrono::duration<double, std::milli>(Clock::now() - a).count(); };
   out->assign(n, DecodedImage());
   Batch b;
-  b.Parse(reqs, n, api_level);
+  b.Parse(reqs, n, api_level, frame_index);
   const double parse_ms = ms_since(t0);
   int overall = JXLB_OK;
   if (!b.AnyOk()) {

@@ -62,3 +62,18 @@ SMALL = [k for k in CASES]
 
 def get(name):
     return _cached(name, CASES[name])
+
+
+# ---- animations (the reference's JxlAnimatedEncoder: full-canvas kReplace frames, 40 ms each) ----
+ANIM_W, ANIM_H, ANIM_N = 320, 264, 4
+
+
+def anim_case(kind):
+    """kind: "rgb_lossy" | "rgba_lossless"."""
+    alpha = kind == "rgba_lossless"
+
+    def make():
+        ch = 4 if alpha else 3
+        frames = np.stack([synth.synth_image(ANIM_W, ANIM_H, 40 + i, alpha=alpha).reshape(ANIM_H, ANIM_W, ch) for i in range(ANIM_N)])
+        return refjxl.anim_encode(frames, ANIM_W, ANIM_H, colorspace=2 if alpha else 1, compression=1 if alpha else 2, duration=40)
+    return _cached("anim_%s_%dx%dx%d" % (kind, ANIM_W, ANIM_H, ANIM_N), make)

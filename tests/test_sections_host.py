@@ -51,3 +51,25 @@ def test_sections_bit_exact(name, ref):
         want = np.stack(st["modular_image"])
         assert (m == want).all()
     e.close()
+
+
+@pytest.mark.parametrize("kind", ["rgb_lossy", "rgba_lossless"])
+def test_animation_frames_host(kind, ref):
+    """Displayed frame i of an animation decodes as an independent picture (same host/device code as the kernels, run on
+    the CPU) and matches the reference's coalesced frame i."""
+    import golden_lib
+    data = cases.anim_case(kind)
+    ra = ref.Anim(data, cfg=2)
+    for i in range(cases.ANIM_N):
+        e = H.Decoded(data, frame=i)
+        assert e.status == 0
+        out = e.render()
+        e.close()
+        want = ra.frame(i)["pixels"][:, : cases.ANIM_W * 4].reshape(cases.ANIM_H, cases.ANIM_W, 4)
+        if kind == "rgba_lossless":
+            a = out[..., 3:4].astype(np.uint16)
+            out[..., :3] = (out[..., :3].astype(np.uint16) * a // 255).astype(np.uint8)
+            assert (out == want).all()
+        else:
+            golden_lib.lossy_close(out, want, "anim %d" % i)
+    ra.close()
