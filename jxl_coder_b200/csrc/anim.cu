@@ -4,7 +4,7 @@
 // on the GPU through the still-image pipeline: the frames the reference's own JxlAnimatedEncoder writes are full-canvas
 // kReplace frames (interop/JxlAnimatedEncoder.hpp:111-118), i.e. independent pictures, so frame i needs no earlier
 // frame (which is also what lets a 120-frame animation spread over several GPUs).  Frames that need composition
-// (crops, blending, reference slots) report JXLB_UNSUPPORTED; so does a rescaling request.
+// (crops, blending, reference slots) report JXLB_UNSUPPORTED.
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -89,11 +89,8 @@ int jxlb_anim_get_frame(jxlb_anim* a, int32_t frame, int32_t width, int32_t heig
   }
   // JxlAnimatedDecoderCoordinator.cpp:162-: rescale only when both target dimensions are positive
   const bool rescale = width > 0 && height > 0 && ((uint32_t) width != a->md.xsize || (uint32_t) height != a->md.ysize);
-  if (rescale) {
-    snprintf(out->message, sizeof out->message, "rescale (getFrame with a target size)");
-    return JXLB_UNSUPPORTED;
-  }
-  jxlb_request r{a->cs.data(), a->cs_len, -1, -1, a->cfg, a->scale_mode, a->filter};
+  // RescaleImage with the coordinator's scale mode and sampler (same refusals as decodeSampled: resize.h)
+  jxlb_request r{a->cs.data(), a->cs_len, rescale ? width : -1, rescale ? height : -1, a->cfg, a->scale_mode, a->filter};
   std::vector<DecodedImage> res;
   BatchTimings tm;
   const int32_t fi = frame;

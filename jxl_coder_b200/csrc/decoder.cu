@@ -25,6 +25,7 @@
 #include "kernels.h"
 #include "numeric_tables.h"
 #include "plan.h"
+#include "resize.h"
 
 namespace jxlb {
 
@@ -248,6 +249,11 @@ struct Parsed {
   // offsets into the batch buffers
   size_t const_off = 0, work_off = 0, stage_off = 0, stage_stride = 0;
   uint32_t status_base = 0;
+  // rescale (decodeSampled with a target size): plan + offsets of its tables (const region) and images (work region)
+  bool resize = false;
+  ResizePlan rp;
+  size_t rs_table_off = 0, rs_table_bytes = 0, rs_work_off = 0, rs_mid_bytes = 0, rs_scaled_bytes = 0;
+  uint32_t out_w = 0, out_h = 0;   // size of the picture handed back
 };
 
 int Fail(Parsed* p, int status, const std::string& msg) {
@@ -390,9 +396,27 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
   }
   // rescale (JniDecoding.cpp:116-136)
   const bool use_sampler = (r.width > 0 || r.height > 0) && (r.width != 0 && r.height != 0);
+  p->out_w = md.xsize;
+  p->out_h = md.ysize;
   if (use_sampler) {
-    Fail(p, JXLB_UNSUPPORTED, "rescale (decodeSampled with a target size)");
-    return;
+    // RescaleImage (SizeScaler.cpp:38-144) -> weave_scale_u8; the u16 path and the premultiply-around-the-convolution
+    // of sources with alpha are not pinned yet and are refused (resize.h)
+    if (p->out16 || p->has_alpha) {
+      Fail(p, JXLB_UNSUPPORTED, "rescale of 16-bit or alpha sources");
+      return;
+    }
+    const int rs = MakeResizePlan(md.xsize, md.ysize, r.width, r.height, r.scale_mode, r.filter, &p->rp);
+    if (rs == kResizeUnsupported) {
+      Fail(p, JXLB_UNSUPPORTED, "rescale configuration (upscaling, ScaleToFill crop or a filter that is not pinned)");
+      return;
+    }
+    if (rs != kResizeOk) {
+      Fail(p, JXLB_BAD_ARG, "invalid target size");
+      return;
+    }
+    p->resize = true;
+    p->out_w = p->rp.out_w;
+    p->out_h = p->rp.out_h;
   }
   if (api < 34) {
     Fail(p, JXLB_UNSUPPORTED, "api_level < 34 colour-matrix pass");
@@ -540,10 +564,20 @@ struct Batch {
       p.stage_stride = Align256((size_t) p.md.xsize * 4 * (p.out16 ? 2 : 1));
       p.stage_off = stage_total;
       // the fused VarDCT kernel packs straight into final_out; only modular frames (and the unfused debug path) stage RGBA
-      if (p.plan.proto.encoding != 0 || UseUnfusedFilters()) stage_total += Align256(p.stage_stride * p.md.ysize);
+      if (p.plan.proto.encoding != 0 || UseUnfusedFilters() || p.resize) stage_total += Align256(p.stage_stride * p.md.ysize);
+      if (p.resize) {
+        auto axis_bytes = [](const ResizeAxis& a) { return Align256(a.start.size() * 4) + Align256(a.count.size() * 4) + Align256(a.weights.size() * 2); };
+        p.rs_table_off = const_total;
+        p.rs_table_bytes = axis_bytes(p.rp.v) + axis_bytes(p.rp.h);
+        const_total += p.rs_table_bytes;
+        p.rs_mid_bytes = p.rp.identity_v ? 0 : Align256((size_t) p.rp.scaled_h * p.rp.src_w * 4);
+        p.rs_scaled_bytes = p.rp.identity_h ? 0 : Align256((size_t) p.rp.scaled_h * p.rp.scaled_w * 4);
+        p.rs_work_off = work_total;
+        work_total += p.rs_mid_bytes + p.rs_scaled_bytes;
+      }
       xyb_slot_bytes = std::max(xyb_slot_bytes, Align256(p.plan.xyb_bytes * (UseUnfusedFilters() ? 2 : 1)));
       if (p.plan.proto.encoding == 0) ++n_vardct;
-      final_bytes[i] = (size_t) p.md.xsize * FormatBytesPerPixel((uint32_t) p.format) * p.md.ysize;
+      final_bytes[i] = (size_t) p.out_w * FormatBytesPerPixel((uint32_t) p.format) * p.out_h;
       final_off[i] = final_total;
       final_total += Align256(final_bytes[i]);
       frame_of[i] = nframes++;
@@ -654,6 +688,17 @@ struct Batch {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) return;
       FillConstRegion(p.plan, p.cs.data(), p.fh, p.g, stg + p.const_off);
+      if (p.resize) {
+        uint8_t* t = stg + p.rs_table_off;
+        for (const ResizeAxis* a : {&p.rp.v, &p.rp.h}) {
+          memcpy(t, a->start.data(), a->start.size() * 4);
+          t += Align256(a->start.size() * 4);
+          memcpy(t, a->count.data(), a->count.size() * 4);
+          t += Align256(a->count.size() * 4);
+          memcpy(t, a->weights.data(), a->weights.size() * 2);
+          t += Align256(a->weights.size() * 2);
+        }
+      }
       FrameDev fd = BindFrameDev(p.plan, buf->const_buf.p + p.const_off, buf->work_buf.p + p.work_off);
       if (p.plan.xyb_bytes) {
         uint8_t* slot = buf->xyb_ring.p + (i % kXybRing) * xyb_slot_bytes;
@@ -776,6 +821,13 @@ struct Batch {
       pk.attenuate = !p.alpha_premultiplied ? 1 : 0;
       pk.dst_stride = pk.width * FormatBytesPerPixel(pk.format);
       pk.dst = buf->final_out.p + final_off[i];
+      const PackParams pk_final = pk;
+      if (p.resize) {  // the decode stage hands straight RGBA8 to the rescaler; ReformatColorConfig runs on its result
+        pk.format = JXLB_FORMAT_RGBA_8888;
+        pk.associate = 0;
+        pk.dst = od.data;
+        pk.dst_stride = od.stride_bytes;
+      }
       if (f.encoding == 0) {
         const bool timed = (vd++ % kTimeEvery) == 0;
         LaunchLfFinal(f, s);
@@ -795,7 +847,40 @@ struct Batch {
         }
       } else {
         LaunchModularToRgba(f, od, s);
-        LaunchPack(pk, s);
+        if (!p.resize) LaunchPack(pk, s);
+      }
+      if (p.resize) {
+        ResizeDev rd{};
+        rd.src = od.data;
+        rd.src_stride = od.stride_bytes;
+        rd.src_w = p.rp.src_w;
+        rd.src_h = p.rp.src_h;
+        rd.scaled_w = p.rp.scaled_w;
+        rd.scaled_h = p.rp.scaled_h;
+        rd.has_v = !p.rp.identity_v;
+        rd.has_h = !p.rp.identity_h;
+        const uint8_t* t = buf->const_buf.p + p.rs_table_off;
+        for (int ax = 0; ax < 2; ++ax) {
+          const ResizeAxis& a = ax ? p.rp.h : p.rp.v;
+          ResizeAxisDev& d = ax ? rd.h : rd.v;
+          d.start = reinterpret_cast<const uint32_t*>(t);
+          t += Align256(a.start.size() * 4);
+          d.count = reinterpret_cast<const uint32_t*>(t);
+          t += Align256(a.count.size() * 4);
+          d.weights = reinterpret_cast<const int16_t*>(t);
+          t += Align256(a.weights.size() * 2);
+          d.taps = a.taps;
+        }
+        rd.mid = buf->work_buf.p + p.rs_work_off;
+        rd.scaled = rd.mid + p.rs_mid_bytes;
+        const uint8_t* res = LaunchResize(rd, s);
+        PackParams pr = pk_final;
+        pr.src = res + (size_t) p.rp.crop_y * (res == rd.scaled ? rd.scaled_w * 4 : res == rd.mid ? rd.src_w * 4 : rd.src_stride) + (size_t) p.rp.crop_x * 4;
+        pr.src_stride = res == rd.scaled ? rd.scaled_w * 4 : res == rd.mid ? rd.src_w * 4 : rd.src_stride;
+        pr.width = p.out_w;
+        pr.height = p.out_h;
+        pr.dst_stride = pr.width * FormatBytesPerPixel(pr.format);
+        LaunchPack(pr, s);
       }
       // download: only the "image done" event is recorded here; Finish() enqueues each copy once its image is complete
       if (i < host_dst.size() && host_dst[i]) CUDA_OK(cudaEventRecord(img_ev[i], s));
@@ -946,9 +1031,9 @@ struct Batch {
       }
       if (!out) continue;
       DecodedImage& d = (*out)[i];
-      d.width = p.md.xsize;
-      d.height = p.md.ysize;
-      d.stride_bytes = p.md.xsize * FormatBytesPerPixel((uint32_t) p.format);
+      d.width = p.out_w;
+      d.height = p.out_h;
+      d.stride_bytes = p.out_w * FormatBytesPerPixel((uint32_t) p.format);
       d.format = p.format;
       d.color_space = p.color_space;
       d.premultiplied = p.has_alpha ? 1 : 0;
@@ -1104,9 +1189,9 @@ int FetchBatchImage(Batch* b, size_t i, DecodedImage* out) {
   }
   out->data = h;
   out->device = -1;
-  out->width = p.md.xsize;
-  out->height = p.md.ysize;
-  out->stride_bytes = p.md.xsize * FormatBytesPerPixel((uint32_t) p.format);
+  out->width = p.out_w;
+  out->height = p.out_h;
+  out->stride_bytes = p.out_w * FormatBytesPerPixel((uint32_t) p.format);
   out->format = p.format;
   out->color_space = p.color_space;
   out->premultiplied = p.has_alpha ? 1 : 0;

@@ -41,6 +41,24 @@ struct AcCtaJob {
   uint32_t ngroups;
   uint32_t pad;
 };
+// Rescale (kernels_resize.cu): device views of a ResizePlan's axis tables and of the three images involved.
+struct ResizeAxisDev {
+  const uint32_t* start;
+  const uint32_t* count;
+  const int16_t* weights;
+  uint32_t taps;
+};
+struct ResizeDev {
+  const uint8_t* src;      // RGBA8, src_stride bytes per row
+  uint32_t src_stride, src_w, src_h, scaled_w, scaled_h;
+  bool has_v, has_h;       // a pass whose size does not change is skipped
+  ResizeAxisDev v, h;
+  uint8_t* mid;            // [scaled_h][src_w] RGBA8
+  uint8_t* scaled;         // [scaled_h][scaled_w] RGBA8
+};
+// Returns the pointer holding the result: r.scaled, r.mid (horizontal pass skipped; row stride src_w * 4) or r.src.
+const uint8_t* LaunchResize(const ResizeDev& r, cudaStream_t stream);
+
 // Sets `bytes` (a multiple of 16, 16-byte aligned) to the repeated 32-bit value with a kernel.
 void LaunchFill(void* p, size_t bytes, uint32_t value32, cudaStream_t stream);
 void LaunchBuildGroupBlocks(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, cudaStream_t stream);

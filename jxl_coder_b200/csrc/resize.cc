@@ -1,0 +1,189 @@
+#include "resize.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace jxlb {
+
+namespace {
+
+// pic-scale's bc_spline in f32, operation by operation (the quantised weights depend on the rounding of each step).
+float BcSpline(float d, float b, float c) {
+  const float x = std::fabs(d);
+  const float dp = x * x;
+  const float tp = dp * x;
+  const float sixth = 1.0f / 6.0f;
+  if (x < 1.0f) {
+    const float c1 = (12.0f - 9.0f * b) - 6.0f * c;
+    const float c2 = (-18.0f + 12.0f * b) + 6.0f * c;
+    const float c3 = 6.0f - 2.0f * b;
+    return ((c1 * tp + c2 * dp) + c3) * sixth;
+  }
+  if (x < 2.0f) {
+    const float c1 = -b - 6.0f * c;
+    const float c2 = 6.0f * b + 30.0f * c;
+    const float c3 = -12.0f * b - 48.0f * c;
+    const float c4 = 8.0f * b + 24.0f * c;
+    return (((c1 * tp + c2 * dp) + c3 * x) + c4) * sixth;
+  }
+  return 0.0f;
+}
+
+struct Kernel {
+  int kind;              // 0 bilinear, 1 bc-spline
+  float b, c;
+  float min_kernel_size;
+  float operator()(float x) const {
+    if (kind == 0) {
+      const float a = std::fabs(x);
+      return a < 1.0f ? 1.0f - a : 0.0f;
+    }
+    return BcSpline(x, b, c);
+  }
+};
+
+bool KernelFor(int32_t filter, Kernel* k) {
+  const float third = 1.0f / 3.0f;
+  switch (filter) {
+    case 1: *k = Kernel{0, 0.f, 0.f, 2.0f}; return true;        // Bilinear
+    case 4: *k = Kernel{1, third, third, 4.0f}; return true;    // MitchellNetravalli
+    case 6: *k = Kernel{1, 0.0f, 0.5f, 4.0f}; return true;      // CatmullRom
+    case 7: *k = Kernel{1, 0.0f, 0.0f, 4.0f}; return true;      // Hermite
+    default: return false;                                      // Nearest, Cubic, Lanczos, BSpline, Hann, Bicubic: not pinned yet
+  }
+}
+
+void MakeAxis(uint32_t in_size, uint32_t out_size, const Kernel& k, ResizeAxis* a) {
+  a->in_size = in_size;
+  a->out_size = out_size;
+  const float scale = (float) in_size / (float) out_size;
+  const float cutoff = std::max(scale, 1.0f);
+  const uint32_t base_size = (uint32_t) std::floor(k.min_kernel_size * cutoff + 0.5f);
+  const float radius = (float) base_size / 2.0f;
+  const float fscale = 1.0f / cutoff;
+  a->taps = base_size;
+  a->start.assign(out_size, 0);
+  a->count.assign(out_size, 0);
+  a->weights.assign((size_t) out_size * base_size, 0);
+  std::vector<float> w(base_size);
+  for (uint32_t i = 0; i < out_size; ++i) {
+    const float center_x = std::min(((float) i + 0.5f) * scale, (float) in_size);
+    const float fs = std::max(std::floor(center_x - radius), 0.0f);
+    const uint32_t start = (uint32_t) fs;
+    const float fe = std::min(std::min(std::ceil(center_x + radius), (float) (start + base_size)), (float) in_size);
+    const uint32_t end = (uint32_t) fe;
+    const float center = center_x - 0.5f;
+    float sum = 0.0f;
+    const uint32_t n = end > start ? end - start : 0;
+    for (uint32_t t = 0; t < n; ++t) {
+      const float dx = std::fabs((float) (start + t) - center);
+      w[t] = k(dx * fscale);
+      sum += w[t];
+    }
+    a->start[i] = start;
+    a->count[i] = n;
+    if (sum != 0.0f) {
+      const float rec = 1.0f / sum;
+      for (uint32_t t = 0; t < n; ++t) a->weights[(size_t) i * base_size + t] = (int16_t) std::trunc((w[t] * rec) * 32768.0f);
+    }
+  }
+}
+
+}  // namespace
+
+int MakeResizePlan(uint32_t src_w, uint32_t src_h, int32_t req_w, int32_t req_h, int32_t scale_mode, int32_t filter, ResizePlan* p) {
+  if (!src_w || !src_h || req_w == 0 || req_h == 0) return kResizeBadArg;
+  // resolve_dimensions (weaver/src/scale.rs:100-135)
+  size_t nw, nh;
+  if (req_w > 0 && req_h == -1) {
+    const double s = (double) req_w / (double) src_w;
+    nw = (size_t) req_w;
+    nh = std::max<size_t>((size_t) std::round((double) src_h * s), 1);
+  } else if (req_w > 0 && req_h == -2) {
+    const double s = (double) req_w / (double) src_w;
+    nw = (size_t) req_w;
+    nh = (std::max<size_t>((size_t) std::round((double) src_h * s), 1) + 1) & ~(size_t) 1;
+  } else if (req_w == -1 && req_h > 0) {
+    const double s = (double) req_h / (double) src_h;
+    nw = std::max<size_t>((size_t) std::round((double) src_w * s), 1);
+    nh = (size_t) req_h;
+  } else if (req_w == -2 && req_h > 0) {
+    const double s = (double) req_h / (double) src_h;
+    nw = (std::max<size_t>((size_t) std::round((double) src_w * s), 1) + 1) & ~(size_t) 1;
+    nh = (size_t) req_h;
+  } else {
+    nw = (size_t) std::max(req_w, 1);
+    nh = (size_t) std::max(req_h, 1);
+  }
+  // scale mode (weaver/src/scale.rs:199-236)
+  size_t sw, sh, cx = 0, cy = 0, cw, ch;
+  if (scale_mode == 2 || scale_mode == 1) {
+    const double xf = (double) nw / (double) src_w, yf = (double) nh / (double) src_h;
+    const double s = scale_mode == 2 ? std::max(xf, yf) : std::min(xf, yf);
+    sw = std::max<size_t>((size_t) std::round((double) src_w * s), 1);
+    sh = std::max<size_t>((size_t) std::round((double) src_h * s), 1);
+    cx = (size_t) std::max<int64_t>(((int64_t) sw - (int64_t) nw) / 2, 0);
+    cy = (size_t) std::max<int64_t>(((int64_t) sh - (int64_t) nh) / 2, 0);
+    cw = std::min(nw, sw);
+    ch = std::min(nh, sh);
+  } else {
+    sw = nw;
+    sh = nh;
+    cw = nw;
+    ch = nh;
+  }
+  if (sw > src_w || sh > src_h) return kResizeUnsupported;  // upscaling: border rule of pic-scale not pinned
+  // ScaleToFill with an actual crop: pic-scale 0.7.6's crop_with_copy leaves the last row zero for a horizontal crop and
+  // shifts rows for a vertical one (observed through the oracle); not restated yet, so refused rather than guessed.
+  if (cx > 0 || cy > 0 || cw != sw || ch != sh) return kResizeUnsupported;
+  Kernel k;
+  if (!KernelFor(filter, &k)) return kResizeUnsupported;
+  p->src_w = src_w;
+  p->src_h = src_h;
+  p->scaled_w = (uint32_t) sw;
+  p->scaled_h = (uint32_t) sh;
+  p->crop_x = (uint32_t) cx;
+  p->crop_y = (uint32_t) cy;
+  p->out_w = (uint32_t) cw;
+  p->out_h = (uint32_t) ch;
+  p->identity_v = sh == src_h;
+  p->identity_h = sw == src_w;
+  if (!p->identity_v) MakeAxis(src_h, (uint32_t) sh, k, &p->v);
+  if (!p->identity_h) MakeAxis(src_w, (uint32_t) sw, k, &p->h);
+  return kResizeOk;
+}
+
+void ResizeRgba8Host(const ResizePlan& p, const uint8_t* src, uint32_t src_stride, std::vector<uint8_t>* out) {
+  std::vector<uint8_t> mid((size_t) p.scaled_h * p.src_w * 4);
+  for (uint32_t y = 0; y < p.scaled_h; ++y)
+    for (uint32_t x = 0; x < p.src_w * 4; ++x) {
+      if (p.identity_v) {
+        mid[(size_t) y * p.src_w * 4 + x] = src[(size_t) y * src_stride + x];
+        continue;
+      }
+      int32_t acc = 1 << 14;
+      const int16_t* w = &p.v.weights[(size_t) y * p.v.taps];
+      for (uint32_t t = 0; t < p.v.count[y]; ++t) acc += (int32_t) w[t] * src[(size_t) (p.v.start[y] + t) * src_stride + x];
+      acc >>= 15;
+      mid[(size_t) y * p.src_w * 4 + x] = (uint8_t) std::min(std::max(acc, 0), 255);
+    }
+  std::vector<uint8_t> scaled((size_t) p.scaled_h * p.scaled_w * 4);
+  for (uint32_t y = 0; y < p.scaled_h; ++y)
+    for (uint32_t x = 0; x < p.scaled_w; ++x)
+      for (uint32_t c = 0; c < 4; ++c) {
+        if (p.identity_h) {
+          scaled[((size_t) y * p.scaled_w + x) * 4 + c] = mid[((size_t) y * p.src_w + x) * 4 + c];
+          continue;
+        }
+        int32_t acc = 1 << 14;
+        const int16_t* w = &p.h.weights[(size_t) x * p.h.taps];
+        for (uint32_t t = 0; t < p.h.count[x]; ++t) acc += (int32_t) w[t] * mid[((size_t) y * p.src_w + p.h.start[x] + t) * 4 + c];
+        acc >>= 15;
+        scaled[((size_t) y * p.scaled_w + x) * 4 + c] = (uint8_t) std::min(std::max(acc, 0), 255);
+      }
+  out->assign((size_t) p.out_w * p.out_h * 4, 0);
+  for (uint32_t y = 0; y < p.out_h; ++y)
+    std::copy_n(&scaled[((size_t) (y + p.crop_y) * p.scaled_w + p.crop_x) * 4], (size_t) p.out_w * 4, &(*out)[(size_t) y * p.out_w * 4]);
+}
+
+}  // namespace jxlb

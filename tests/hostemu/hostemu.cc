@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include "../../jxl_coder_b200/csrc/resize.h"
 
 #include "../../jxl_coder_b200/csrc/frame_parser.h"
 #include "../../jxl_coder_b200/csrc/plan.h"
@@ -225,6 +226,23 @@ uint32_t emu_natural_order(uint32_t order_id, uint16_t* out) {
   const NaturalOrders& nat = NaturalOrderPoolHost();
   memcpy(out, nat.pool + nat.offset[order_id], nat.size[order_id] * 2);
   return nat.size[order_id];
+}
+
+
+// Rescale (resize.h) of an RGBA8 image on the CPU: returns 0 and fills out (caller provides >= req capacity) or a
+// kResize* status.  dims[0..1] = output width / height.
+int emu_resize(const uint8_t* src, uint32_t w, uint32_t h, int32_t req_w, int32_t req_h, int32_t scale_mode, int32_t filter,
+               uint8_t* out, size_t out_capacity, uint32_t* dims) {
+  ResizePlan plan;
+  int st = MakeResizePlan(w, h, req_w, req_h, scale_mode, filter, &plan);
+  if (st) return st;
+  std::vector<uint8_t> res;
+  ResizeRgba8Host(plan, src, w * 4, &res);
+  dims[0] = plan.out_w;
+  dims[1] = plan.out_h;
+  if (res.size() > out_capacity) return -1;
+  memcpy(out, res.data(), res.size());
+  return 0;
 }
 
 }  // extern "C"

@@ -7,7 +7,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = ["tests/hostemu/hostemu.cc", "jxl_coder_b200/csrc/frame_parser.cc", "jxl_coder_b200/csrc/plan.cc",
-       "jxl_coder_b200/csrc/natural_orders.cc", "jxl_coder_b200/csrc/numeric_tables.cc", "jxl_coder_b200/csrc/color_params.cc"]
+       "jxl_coder_b200/csrc/natural_orders.cc", "jxl_coder_b200/csrc/numeric_tables.cc", "jxl_coder_b200/csrc/color_params.cc",
+       "jxl_coder_b200/csrc/resize.cc"]
 OUT = os.path.join(HERE, "hostemu", "_build", "libhostemu.so")
 _lib = None
 
@@ -40,6 +41,8 @@ def lib():
         L.emu_plane_h.argtypes = [C.c_void_p]
         L.emu_logcount.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.emu_natural_order.argtypes = [C.c_uint32, C.c_void_p]
+        L.emu_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
+                                 C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
 
@@ -111,3 +114,16 @@ class Decoded:
         if self.h:
             lib().emu_free(self.h)
             self.h = None
+
+
+def resize_rgba8(img, req_w, req_h, scale_mode, filt):
+    """CPU restatement of the rescale plan + passes (csrc/resize.cc).  Returns the output array or the kResize* status."""
+    h, w, _ = img.shape
+    src = np.ascontiguousarray(img, dtype=np.uint8)
+    cap = max(w * h * 4, 16)
+    out = np.zeros(cap, np.uint8)
+    dims = (C.c_uint32 * 2)()
+    st = lib().emu_resize(src.ctypes.data, w, h, req_w, req_h, scale_mode, filt, out.ctypes.data, cap, dims)
+    if st:
+        return st
+    return out[: dims[0] * dims[1] * 4].reshape(dims[1], dims[0], 4).copy()

@@ -213,3 +213,124 @@ def test_animated_frames_match_reference(J, ref, kind):
         a.get_frame(n)
     a.close()
     ra.close()
+
+
+# ---- decodeSampled with a target size (RescaleImage -> weave_scale_u8) ----
+def _resize_src(ref, w, h):
+    import test_resize_host as T
+    img = T._image(w, h, w * 1000 + h)
+    data = cases._cached("resize_src_%dx%d" % (w, h), lambda: ref.encode(img[..., :3].reshape(-1), w, h, colorspace=1, compression=1))
+    return img, data
+
+
+@pytest.mark.parametrize("case", __import__("test_resize_host").CASES)
+def test_decode_sampled_rescale_bit_exact_on_lossless(J, ref, case):
+    """Lossless sources decode exactly, so the rescaled picture must equal the reference's bit for bit."""
+    w, h, rw, rh, mode, filt = case
+    _, data = _resize_src(ref, w, h)
+    r = ref.decode_sampled(data, w=rw, h=rh, cfg=2, scale_mode=mode, filt=filt)
+    want = r["pixels"][:, : r["width"] * 4].reshape(r["height"], r["width"], 4)
+    before = J.kernel_launches()
+    got = J.JxlCoder.decode_sampled(data, rw, rh, 2, mode, filt)
+    assert J.kernel_launches() > before
+    assert (got.width, got.height) == (r["width"], r["height"])
+    assert (got.as_array() == want).all()
+
+
+@pytest.mark.parametrize("cfg", [3, 4, 5])
+def test_decode_sampled_rescale_then_reformat(J, ref, cfg):
+    """ReformatColorConfig runs on the rescaled picture (RGBA_F16, RGB_565, RGBA_1010102 -- configs[3]'s output format)."""
+    _, data = _resize_src(ref, 200, 120)
+    r = ref.decode_sampled(data, w=50, h=30, cfg=cfg, scale_mode=1, filt=4)
+    got = J.JxlCoder.decode_sampled(data, 50, 30, cfg, 1, 4)
+    assert (got.width, got.height) == (r["width"], r["height"])
+    bpp = {3: 8, 4: 2, 5: 4}[cfg]
+    assert (got.pixels[:, : got.width * bpp] == r["pixels"][:, : got.width * bpp]).all()
+
+
+def test_decode_sampled_rescale_on_lossy_multi_group(J, ref):
+    """configs[3] in small: lossy VarDCT multi-group image -> FIT + Mitchell -> RGBA_1010102.  The rescaler must be
+    bit-exact on OUR decoded pixels (CPU restatement pinned against the reference in test_resize_host.py), and the
+    whole call within the lossy tolerance of the reference."""
+    import hostemu_lib as H
+    from oracle import synth
+    w, h = 1024, 768
+    img = synth.synth_image(w, h, 11)
+    data = cases._cached("rgb_lossy_1024x768", lambda: ref.encode(img, w, h))
+    full = J.JxlCoder.decode(data, 2).as_array()
+    for (rw, rh, mode, filt) in [(256, 192, 1, 4), (300, 300, 1, 6), (333, 77, 3, 1), (512, -1, 1, 7)]:
+        got = J.JxlCoder.decode_sampled(data, rw, rh, 2, mode, filt).as_array()
+        mine = H.resize_rgba8(full, rw, rh, mode, filt)
+        assert got.shape == mine.shape and (got == mine).all(), (rw, rh, mode, filt)
+        r = ref.decode_sampled(data, w=rw, h=rh, cfg=2, scale_mode=mode, filt=filt)
+        want = r["pixels"][:, : r["width"] * 4].reshape(r["height"], r["width"], 4)
+        d = np.abs(got.astype(int) - want.astype(int))
+        assert d.max() <= 1 and (d == 0).mean() > 0.97, (d.max(), (d == 0).mean())
+    got = J.JxlCoder.decode_sampled(data, 256, 192, 5, 1, 4)
+    r = ref.decode_sampled(data, w=256, h=192, cfg=5, scale_mode=1, filt=4)
+    a = np.ascontiguousarray(got.pixels[:, : 256 * 4]).view(np.uint32)
+    b = np.ascontiguousarray(r["pixels"][:, : 256 * 4]).view(np.uint32)
+    for sh in (0, 10, 20):
+        d = np.abs(((a >> sh) & 0x3FF).astype(int) - ((b >> sh) & 0x3FF).astype(int))
+        assert d.max() <= 4 and (d == 0).mean() > 0.97
+    assert ((a >> 30) == (b >> 30)).all()
+
+
+def test_decode_sampled_unpinned_rescales_are_refused(J, ref):
+    _, data = _resize_src(ref, 96, 64)
+    for (rw, rh, mode, filt) in [(200, 64, 3, 4), (24, 16, 3, 5), (40, 40, 2, 4)]:
+        with pytest.raises(J.UnsupportedJXLException):
+            J.JxlCoder.decode_sampled(data, rw, rh, 2, mode, filt)
+    alpha = cases.get("rgba_lossless_128")
+    with pytest.raises(J.UnsupportedJXLException):
+        J.JxlCoder.decode_sampled(alpha, 32, 32, 2, 1, 4)
+    # w = h = -1: no rescale (JxlCoder.kt:55-62); 0 on an axis: no rescale either (JniDecoding.cpp:116-117)
+    assert J.JxlCoder.decode_sampled(data, -1, -1, 2, 1, 4).width == 96
+    assert J.JxlCoder.decode_sampled(data, 0, 10, 2, 1, 4).width == 96
+
+
+def test_animated_frame_rescale(J, ref):
+    data = cases.anim_case("rgb_lossy")
+    ra = ref.Anim(data, cfg=2, scale_mode=1, filt=4)
+    a = J.JxlAnimatedImage(data, J.PreferredColorConfig.RGBA_8888, J.ScaleMode.FIT, J.JxlResizeFilter.MITCHELL_NETRAVALI)
+    r = ra.frame(2, 80, 66)
+    want = r["pixels"][:, : r["width"] * 4].reshape(r["height"], r["width"], 4)
+    got = a.get_frame(2, 80, 66).as_array()
+    assert got.shape == want.shape
+    d = np.abs(got.astype(int) - want.astype(int))
+    assert d.max() <= 1 and (d == 0).mean() > 0.97
+    a.close()
+    ra.close()
+
+
+def test_config3_full_size_8k_to_1080p_1010102(J, ref):
+    """BASELINE configs[3] at full size: 7680x4320 lossy -> decodeSampled(1920, 1080, RGBA_1010102, FIT, Mitchell).
+    Against the reference within the lossy tolerance (1 LSB of 8 bits = 4 of 10), and the rescale bit-exact on our own
+    decoded pixels (CPU restatement of the rescaler)."""
+    import hostemu_lib as H
+    from oracle import gen_inputs
+    data = gen_inputs.c4_image()
+    got = J.JxlCoder.decode_sampled(data, 1920, 1080, 5, 1, 4)
+    assert (got.width, got.height) == (1920, 1080)
+    a = np.ascontiguousarray(got.pixels[:, : 1920 * 4]).view(np.uint32)
+    full = J.JxlCoder.decode(data, 2).as_array()
+    mine = H.resize_rgba8(full, 1920, 1080, 1, 4).astype(np.uint32)
+    packed = (mine[..., 0] << 2) | (mine[..., 1] << 12) | (mine[..., 2] << 22) | ((mine[..., 3] >> 6) << 30)
+    assert (a == packed).all()
+    r = ref.decode_sampled(data, w=1920, h=1080, cfg=5, scale_mode=1, filt=4)
+    b = np.ascontiguousarray(r["pixels"][:, : 1920 * 4]).view(np.uint32)
+    for sh in (0, 10, 20):
+        d = np.abs(((a >> sh) & 0x3FF).astype(int) - ((b >> sh) & 0x3FF).astype(int))
+        assert d.max() <= 4 and (d == 0).mean() > 0.97, (sh, d.max(), (d == 0).mean())
+    assert ((a >> 30) == (b >> 30)).all()
+
+
+def test_config2_full_size_1080p_f16(J, ref):
+    """BASELINE configs[2] at full size (one image of the batch): 1920x1080 lossy -> RGBA_F16."""
+    from oracle import gen_inputs
+    data = gen_inputs.c3_image(0)
+    got = J.JxlCoder.decode(data, 3)
+    r = ref.decode_sampled(data, cfg=3)
+    a = np.ascontiguousarray(got.pixels[:, : 1920 * 8]).view(np.float16).astype(np.float32)
+    b = np.ascontiguousarray(r["pixels"][:, : 1920 * 8]).view(np.float16).astype(np.float32)
+    assert np.abs(a - b).max() <= 1.0 / 255 + 1e-3 and (a == b).mean() > 0.97
