@@ -399,19 +399,18 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
   p->out_w = md.xsize;
   p->out_h = md.ysize;
   if (use_sampler) {
-    // RescaleImage (SizeScaler.cpp:38-144) -> weave_scale_u8; the u16 path and the premultiply-around-the-convolution
-    // of sources with alpha are not pinned yet and are refused (resize.h)
-    if (p->out16 || p->has_alpha) {
-      Fail(p, JXLB_UNSUPPORTED, "rescale of 16-bit or alpha sources");
+    // RescaleImage (SizeScaler.cpp:38-144) -> weave_scale_u8; the u16 path (f32 arithmetic) is not pinned and is refused
+    if (p->out16) {
+      Fail(p, JXLB_UNSUPPORTED, "rescale of 16-bit sources");
       return;
     }
-    const int rs = MakeResizePlan(md.xsize, md.ysize, r.width, r.height, r.scale_mode, r.filter, &p->rp);
+    const int rs = MakeResizePlan(md.xsize, md.ysize, r.width, r.height, r.scale_mode, r.filter, p->has_alpha, &p->rp);
     if (rs == kResizeUnsupported) {
-      Fail(p, JXLB_UNSUPPORTED, "rescale configuration (upscaling, ScaleToFill crop or a filter that is not pinned)");
+      Fail(p, JXLB_UNSUPPORTED, "rescale configuration");
       return;
     }
     if (rs != kResizeOk) {
-      Fail(p, JXLB_BAD_ARG, "invalid target size");
+      Fail(p, JXLB_INVALID_SIZE, "invalid target size");
       return;
     }
     p->resize = true;
@@ -570,8 +569,8 @@ struct Batch {
         p.rs_table_off = const_total;
         p.rs_table_bytes = axis_bytes(p.rp.v) + axis_bytes(p.rp.h);
         const_total += p.rs_table_bytes;
-        p.rs_mid_bytes = p.rp.identity_v ? 0 : Align256((size_t) p.rp.scaled_h * p.rp.src_w * 4);
-        p.rs_scaled_bytes = p.rp.identity_h ? 0 : Align256((size_t) p.rp.scaled_h * p.rp.scaled_w * 4);
+        p.rs_mid_bytes = (p.rp.identity_v || p.rp.nearest) ? 0 : Align256((size_t) p.rp.scaled_h * p.rp.src_w * 4);
+        p.rs_scaled_bytes = (p.rp.identity_h && !p.rp.nearest) ? 0 : Align256((size_t) p.rp.scaled_h * p.rp.scaled_w * 4);
         p.rs_work_off = work_total;
         work_total += p.rs_mid_bytes + p.rs_scaled_bytes;
       }
@@ -859,6 +858,8 @@ struct Batch {
         rd.scaled_h = p.rp.scaled_h;
         rd.has_v = !p.rp.identity_v;
         rd.has_h = !p.rp.identity_h;
+        rd.nearest = p.rp.nearest;
+        rd.premultiply = p.rp.premultiply;
         const uint8_t* t = buf->const_buf.p + p.rs_table_off;
         for (int ax = 0; ax < 2; ++ax) {
           const ResizeAxis& a = ax ? p.rp.h : p.rp.v;
@@ -874,13 +875,21 @@ struct Batch {
         rd.mid = buf->work_buf.p + p.rs_work_off;
         rd.scaled = rd.mid + p.rs_mid_bytes;
         const uint8_t* res = LaunchResize(rd, s);
+        if (p.rp.zero_tail_rows)  // horizontal-only quirk of pic-scale 0.7.6 (resize.h): the last height % 4 rows stay zero
+          CUDA_OK(cudaMemsetAsync(rd.scaled + (size_t) (rd.scaled_h - p.rp.zero_tail_rows) * rd.scaled_w * 4, 0,
+                                  (size_t) p.rp.zero_tail_rows * rd.scaled_w * 4, s));
         PackParams pr = pk_final;
         pr.src = res + (size_t) p.rp.crop_y * (res == rd.scaled ? rd.scaled_w * 4 : res == rd.mid ? rd.src_w * 4 : rd.src_stride) + (size_t) p.rp.crop_x * 4;
         pr.src_stride = res == rd.scaled ? rd.scaled_w * 4 : res == rd.mid ? rd.src_w * 4 : rd.src_stride;
         pr.width = p.out_w;
         pr.height = p.out_h;
         pr.dst_stride = pr.width * FormatBytesPerPixel(pr.format);
-        LaunchPack(pr, s);
+        if (p.rp.zero_last_row) {  // pic-scale 0.7.6 crop quirk (resize.h): the last row of a column-cropped picture is zero
+          --pr.height;
+          CUDA_OK(cudaMemsetAsync(pr.dst + (size_t) pr.height * pr.dst_stride, 0, pr.dst_stride, s));
+          // ReformatColorConfig of a zero row is a zero row in every target format
+        }
+        if (pr.height) LaunchPack(pr, s);
       }
       // download: only the "image done" event is recorded here; Finish() enqueues each copy once its image is complete
       if (i < host_dst.size() && host_dst[i]) CUDA_OK(cudaEventRecord(img_ev[i], s));
@@ -1060,18 +1069,18 @@ void FreeImageMemory(void* data, int device) {
 }
 
 namespace {
-// Picks a decode slot: a free one if there is one, else waits for the next in round-robin order.
+// Picks a decode slot: the lowest-numbered free one (a lone caller therefore always reuses slot 0 and its warm buffers;
+// concurrent callers spread over the slots), else waits for one in round-robin order.
 Slot* AcquireSlot(DeviceContext* ctx, std::unique_lock<std::mutex>* lock) {
-  const uint32_t first = ctx->next_slot.fetch_add(1);
   for (int k = 0; k < kSlots; ++k) {
-    Slot* sl = &ctx->slots[(first + k) % kSlots];
+    Slot* sl = &ctx->slots[k];
     std::unique_lock<std::mutex> l(sl->mu, std::try_to_lock);
     if (l.owns_lock()) {
       *lock = std::move(l);
       return sl;
     }
   }
-  Slot* sl = &ctx->slots[first % kSlots];
+  Slot* sl = &ctx->slots[ctx->next_slot.fetch_add(1) % kSlots];
   *lock = std::unique_lock<std::mutex>(sl->mu);
   return sl;
 }

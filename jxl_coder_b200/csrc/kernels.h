@@ -52,6 +52,8 @@ struct ResizeDev {
   const uint8_t* src;      // RGBA8, src_stride bytes per row
   uint32_t src_stride, src_w, src_h, scaled_w, scaled_h;
   bool has_v, has_h;       // a pass whose size does not change is skipped
+  bool nearest;            // one gather pass: v.start / h.start are the source row / column of every output row / column
+  bool premultiply;        // colour * alpha (rounded / 255) on the way in, divided back on the way out
   ResizeAxisDev v, h;
   uint8_t* mid;            // [scaled_h][src_w] RGBA8
   uint8_t* scaled;         // [scaled_h][scaled_w] RGBA8

@@ -2,35 +2,40 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 namespace jxlb {
 
 namespace {
 
-// pic-scale's bc_spline in f32, operation by operation (the quantised weights depend on the rounding of each step).
-float BcSpline(float d, float b, float c) {
+// pic-scale's BC-spline in f32.  The quantised weights depend on the rounding of every step.  pic-scale's source is not
+// available here; of the evaluation orders tried against weights extracted from the reference binary, the expanded
+// polynomial fits Mitchell / CatmullRom / Hermite best and the Horner form fits Cubic / BSpline best (see the header
+// of resize.h for what remains).
+float BcSpline(float d, float b, float c, bool horner) {
   const float x = std::fabs(d);
   const float dp = x * x;
-  const float tp = dp * x;
   const float sixth = 1.0f / 6.0f;
   if (x < 1.0f) {
     const float c1 = (12.0f - 9.0f * b) - 6.0f * c;
     const float c2 = (-18.0f + 12.0f * b) + 6.0f * c;
     const float c3 = 6.0f - 2.0f * b;
-    return ((c1 * tp + c2 * dp) + c3) * sixth;
+    if (horner) return ((c1 * x + c2) * dp + c3) * sixth;
+    return ((c1 * (dp * x) + c2 * dp) + c3) * sixth;
   }
   if (x < 2.0f) {
     const float c1 = -b - 6.0f * c;
     const float c2 = 6.0f * b + 30.0f * c;
     const float c3 = -12.0f * b - 48.0f * c;
     const float c4 = 8.0f * b + 24.0f * c;
-    return (((c1 * tp + c2 * dp) + c3 * x) + c4) * sixth;
+    if (horner) return ((((c1 * x + c2) * x) + c3) * x + c4) * sixth;
+    return (((c1 * (dp * x) + c2 * dp) + c3 * x) + c4) * sixth;
   }
   return 0.0f;
 }
 
 struct Kernel {
-  int kind;              // 0 bilinear, 1 bc-spline
+  int kind;              // 0 bilinear, 1 bc-spline (expanded), 2 bc-spline (Horner)
   float b, c;
   float min_kernel_size;
   float operator()(float x) const {
@@ -38,18 +43,20 @@ struct Kernel {
       const float a = std::fabs(x);
       return a < 1.0f ? 1.0f - a : 0.0f;
     }
-    return BcSpline(x, b, c);
+    return BcSpline(x, b, c, kind == 2);
   }
 };
 
 bool KernelFor(int32_t filter, Kernel* k) {
   const float third = 1.0f / 3.0f;
   switch (filter) {
-    case 1: *k = Kernel{0, 0.f, 0.f, 2.0f}; return true;        // Bilinear
-    case 4: *k = Kernel{1, third, third, 4.0f}; return true;    // MitchellNetravalli
-    case 6: *k = Kernel{1, 0.0f, 0.5f, 4.0f}; return true;      // CatmullRom
-    case 7: *k = Kernel{1, 0.0f, 0.0f, 4.0f}; return true;      // Hermite
-    default: return false;                                      // Nearest, Cubic, Lanczos, BSpline, Hann, Bicubic: not pinned yet
+    case 1: *k = Kernel{0, 0.f, 0.f, 2.0f}; return true;            // Bilinear
+    case 3: *k = Kernel{2, 1.0f, 0.0f, 4.0f}; return true;          // Cubic
+    case 8: *k = Kernel{1, 1.0f, 0.0f, 4.0f}; return true;          // BSpline
+    case 4: *k = Kernel{1, third, third, 4.0f}; return true;        // MitchellNetravalli
+    case 6: *k = Kernel{1, 0.0f, 0.5f, 4.0f}; return true;          // CatmullRom
+    case 7: *k = Kernel{1, 0.0f, 0.0f, 4.0f}; return true;          // Hermite
+    default: return false;  // 5 / 9 Lanczos3 (sinc through pxfm's sinpi) and 10 Bicubic: weights not reproduced -> refused
   }
 }
 
@@ -73,25 +80,42 @@ void MakeAxis(uint32_t in_size, uint32_t out_size, const Kernel& k, ResizeAxis* 
     const float fe = std::min(std::min(std::ceil(center_x + radius), (float) (start + base_size)), (float) in_size);
     const uint32_t end = (uint32_t) fe;
     const float center = center_x - 0.5f;
-    float sum = 0.0f;
+    // f32 tap weights; their sum behaves like an exactly accumulated one (Bilinear, whose taps are exact, pins this and
+    // the division below: 0 mismatches over random sizes)
+    double sum = 0.0;
     const uint32_t n = end > start ? end - start : 0;
     for (uint32_t t = 0; t < n; ++t) {
       const float dx = std::fabs((float) (start + t) - center);
       w[t] = k(dx * fscale);
       sum += w[t];
     }
+    const float fsum = (float) sum;
     a->start[i] = start;
     a->count[i] = n;
-    if (sum != 0.0f) {
-      const float rec = 1.0f / sum;
-      for (uint32_t t = 0; t < n; ++t) a->weights[(size_t) i * base_size + t] = (int16_t) std::trunc((w[t] * rec) * 32768.0f);
+    if (fsum != 0.0f) {
+      for (uint32_t t = 0; t < n; ++t) {
+        const float q = std::trunc((w[t] / fsum) * 32768.0f);
+        a->weights[(size_t) i * base_size + t] = (int16_t) std::min(std::max(q, -32768.0f), 32767.0f);
+      }
     }
   }
 }
 
+void MakeNearestAxis(uint32_t in_size, uint32_t out_size, ResizeAxis* a) {
+  a->in_size = in_size;
+  a->out_size = out_size;
+  a->taps = 1;
+  a->start.assign(out_size, 0);
+  a->count.assign(out_size, 1);
+  a->weights.assign(out_size, 0);
+  const uint64_t s = ((uint64_t) in_size << 32) / out_size;
+  for (uint32_t i = 0; i < out_size; ++i) a->start[i] = (uint32_t) std::min<uint64_t>(((uint64_t) i * s + (s >> 1)) >> 32, in_size - 1);
+}
+
 }  // namespace
 
-int MakeResizePlan(uint32_t src_w, uint32_t src_h, int32_t req_w, int32_t req_h, int32_t scale_mode, int32_t filter, ResizePlan* p) {
+int MakeResizePlan(uint32_t src_w, uint32_t src_h, int32_t req_w, int32_t req_h, int32_t scale_mode, int32_t filter, bool has_alpha,
+                   ResizePlan* p) {
   if (!src_w || !src_h || req_w == 0 || req_h == 0) return kResizeBadArg;
   // resolve_dimensions (weaver/src/scale.rs:100-135)
   size_t nw, nh;
@@ -132,12 +156,7 @@ int MakeResizePlan(uint32_t src_w, uint32_t src_h, int32_t req_w, int32_t req_h,
     cw = nw;
     ch = nh;
   }
-  if (sw > src_w || sh > src_h) return kResizeUnsupported;  // upscaling: border rule of pic-scale not pinned
-  // ScaleToFill with an actual crop: pic-scale 0.7.6's crop_with_copy leaves the last row zero for a horizontal crop and
-  // shifts rows for a vertical one (observed through the oracle); not restated yet, so refused rather than guessed.
-  if (cx > 0 || cy > 0 || cw != sw || ch != sh) return kResizeUnsupported;
-  Kernel k;
-  if (!KernelFor(filter, &k)) return kResizeUnsupported;
+  if (sw > 65535 || sh > 65535 || (uint64_t) sw * sh * 4 >= 0x7FFFFFFFull) return kResizeBadArg;
   p->src_w = src_w;
   p->src_h = src_h;
   p->scaled_w = (uint32_t) sw;
@@ -146,44 +165,77 @@ int MakeResizePlan(uint32_t src_w, uint32_t src_h, int32_t req_w, int32_t req_h,
   p->crop_y = (uint32_t) cy;
   p->out_w = (uint32_t) cw;
   p->out_h = (uint32_t) ch;
+  p->zero_last_row = cx > 0;
   p->identity_v = sh == src_h;
   p->identity_h = sw == src_w;
+  p->nearest = filter == 2;
+  if (p->nearest) {
+    p->identity_v = p->identity_h = false;
+    MakeNearestAxis(src_h, (uint32_t) sh, &p->v);
+    MakeNearestAxis(src_w, (uint32_t) sw, &p->h);
+    return kResizeOk;
+  }
+  Kernel k;
+  if (!KernelFor(filter, &k)) return kResizeUnsupported;
+  p->premultiply = has_alpha && !(p->identity_v && p->identity_h);
+  if (p->identity_v && !p->identity_h && src_h >= 4) p->zero_tail_rows = src_h % 4;
   if (!p->identity_v) MakeAxis(src_h, (uint32_t) sh, k, &p->v);
   if (!p->identity_h) MakeAxis(src_w, (uint32_t) sw, k, &p->h);
   return kResizeOk;
 }
 
 void ResizeRgba8Host(const ResizePlan& p, const uint8_t* src, uint32_t src_stride, std::vector<uint8_t>* out) {
-  std::vector<uint8_t> mid((size_t) p.scaled_h * p.src_w * 4);
-  for (uint32_t y = 0; y < p.scaled_h; ++y)
-    for (uint32_t x = 0; x < p.src_w * 4; ++x) {
-      if (p.identity_v) {
-        mid[(size_t) y * p.src_w * 4 + x] = src[(size_t) y * src_stride + x];
-        continue;
-      }
-      int32_t acc = 1 << 14;
-      const int16_t* w = &p.v.weights[(size_t) y * p.v.taps];
-      for (uint32_t t = 0; t < p.v.count[y]; ++t) acc += (int32_t) w[t] * src[(size_t) (p.v.start[y] + t) * src_stride + x];
-      acc >>= 15;
-      mid[(size_t) y * p.src_w * 4 + x] = (uint8_t) std::min(std::max(acc, 0), 255);
-    }
   std::vector<uint8_t> scaled((size_t) p.scaled_h * p.scaled_w * 4);
-  for (uint32_t y = 0; y < p.scaled_h; ++y)
-    for (uint32_t x = 0; x < p.scaled_w; ++x)
-      for (uint32_t c = 0; c < 4; ++c) {
-        if (p.identity_h) {
-          scaled[((size_t) y * p.scaled_w + x) * 4 + c] = mid[((size_t) y * p.src_w + x) * 4 + c];
+  if (p.nearest) {
+    for (uint32_t y = 0; y < p.scaled_h; ++y)
+      for (uint32_t x = 0; x < p.scaled_w; ++x)
+        memcpy(&scaled[((size_t) y * p.scaled_w + x) * 4], src + (size_t) p.v.start[y] * src_stride + (size_t) p.h.start[x] * 4, 4);
+  } else {
+    std::vector<uint8_t> pre((size_t) p.src_h * p.src_w * 4);
+    for (uint32_t y = 0; y < p.src_h; ++y)
+      for (uint32_t x = 0; x < p.src_w; ++x) {
+        const uint8_t* s = src + (size_t) y * src_stride + (size_t) x * 4;
+        uint8_t* d = &pre[((size_t) y * p.src_w + x) * 4];
+        for (int c = 0; c < 3; ++c) d[c] = p.premultiply ? (uint8_t) ResizePremul(s[c], s[3]) : s[c];
+        d[3] = s[3];
+      }
+    std::vector<uint8_t> mid((size_t) p.scaled_h * p.src_w * 4);
+    for (uint32_t y = 0; y < p.scaled_h; ++y)
+      for (uint32_t x = 0; x < p.src_w * 4; ++x) {
+        if (p.identity_v) {
+          mid[(size_t) y * p.src_w * 4 + x] = pre[(size_t) y * p.src_w * 4 + x];
           continue;
         }
         int32_t acc = 1 << 14;
-        const int16_t* w = &p.h.weights[(size_t) x * p.h.taps];
-        for (uint32_t t = 0; t < p.h.count[x]; ++t) acc += (int32_t) w[t] * mid[((size_t) y * p.src_w + p.h.start[x] + t) * 4 + c];
+        const int16_t* w = &p.v.weights[(size_t) y * p.v.taps];
+        for (uint32_t t = 0; t < p.v.count[y]; ++t) acc += (int32_t) w[t] * pre[(size_t) (p.v.start[y] + t) * p.src_w * 4 + x];
         acc >>= 15;
-        scaled[((size_t) y * p.scaled_w + x) * 4 + c] = (uint8_t) std::min(std::max(acc, 0), 255);
+        mid[(size_t) y * p.src_w * 4 + x] = (uint8_t) std::min(std::max(acc, 0), 255);
       }
+    for (uint32_t y = 0; y < p.scaled_h; ++y)
+      for (uint32_t x = 0; x < p.scaled_w; ++x) {
+        uint8_t* d = &scaled[((size_t) y * p.scaled_w + x) * 4];
+        for (uint32_t c = 0; c < 4; ++c) {
+          if (p.identity_h) {
+            d[c] = mid[((size_t) y * p.src_w + x) * 4 + c];
+            continue;
+          }
+          int32_t acc = 1 << 14;
+          const int16_t* w = &p.h.weights[(size_t) x * p.h.taps];
+          for (uint32_t t = 0; t < p.h.count[x]; ++t) acc += (int32_t) w[t] * mid[((size_t) y * p.src_w + p.h.start[x] + t) * 4 + c];
+          acc >>= 15;
+          d[c] = (uint8_t) std::min(std::max(acc, 0), 255);
+        }
+        if (p.premultiply)
+          for (int c = 0; c < 3; ++c) d[c] = (uint8_t) ResizeUnpremul(d[c], d[3]);
+        if (y + p.zero_tail_rows >= p.scaled_h) d[0] = d[1] = d[2] = d[3] = 0;
+      }
+  }
   out->assign((size_t) p.out_w * p.out_h * 4, 0);
-  for (uint32_t y = 0; y < p.out_h; ++y)
+  for (uint32_t y = 0; y < p.out_h; ++y) {
+    if (p.zero_last_row && y + 1 == p.out_h) break;
     std::copy_n(&scaled[((size_t) (y + p.crop_y) * p.scaled_w + p.crop_x) * 4], (size_t) p.out_w * 4, &(*out)[(size_t) y * p.out_w * 4]);
+  }
 }
 
 }  // namespace jxlb

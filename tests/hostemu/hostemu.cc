@@ -231,10 +231,10 @@ uint32_t emu_natural_order(uint32_t order_id, uint16_t* out) {
 
 // Rescale (resize.h) of an RGBA8 image on the CPU: returns 0 and fills out (caller provides >= req capacity) or a
 // kResize* status.  dims[0..1] = output width / height.
-int emu_resize(const uint8_t* src, uint32_t w, uint32_t h, int32_t req_w, int32_t req_h, int32_t scale_mode, int32_t filter,
+int emu_resize(const uint8_t* src, uint32_t w, uint32_t h, int32_t req_w, int32_t req_h, int32_t scale_mode, int32_t filter, int32_t has_alpha,
                uint8_t* out, size_t out_capacity, uint32_t* dims) {
   ResizePlan plan;
-  int st = MakeResizePlan(w, h, req_w, req_h, scale_mode, filter, &plan);
+  int st = MakeResizePlan(w, h, req_w, req_h, scale_mode, filter, has_alpha != 0, &plan);
   if (st) return st;
   std::vector<uint8_t> res;
   ResizeRgba8Host(plan, src, w * 4, &res);

@@ -41,7 +41,7 @@ def lib():
         L.emu_plane_h.argtypes = [C.c_void_p]
         L.emu_logcount.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.emu_natural_order.argtypes = [C.c_uint32, C.c_void_p]
-        L.emu_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
+        L.emu_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                  C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
@@ -116,14 +116,14 @@ class Decoded:
             self.h = None
 
 
-def resize_rgba8(img, req_w, req_h, scale_mode, filt):
+def resize_rgba8(img, req_w, req_h, scale_mode, filt, has_alpha=False):
     """CPU restatement of the rescale plan + passes (csrc/resize.cc).  Returns the output array or the kResize* status."""
     h, w, _ = img.shape
     src = np.ascontiguousarray(img, dtype=np.uint8)
-    cap = max(w * h * 4, 16)
+    cap = max(w * h * 4 * 64, 1 << 24)
     out = np.zeros(cap, np.uint8)
     dims = (C.c_uint32 * 2)()
-    st = lib().emu_resize(src.ctypes.data, w, h, req_w, req_h, scale_mode, filt, out.ctypes.data, cap, dims)
+    st = lib().emu_resize(src.ctypes.data, w, h, req_w, req_h, scale_mode, filt, int(has_alpha), out.ctypes.data, cap, dims)
     if st:
         return st
     return out[: dims[0] * dims[1] * 4].reshape(dims[1], dims[0], 4).copy()

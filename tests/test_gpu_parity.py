@@ -234,7 +234,11 @@ def test_decode_sampled_rescale_bit_exact_on_lossless(J, ref, case):
     got = J.JxlCoder.decode_sampled(data, rw, rh, 2, mode, filt)
     assert J.kernel_launches() > before
     assert (got.width, got.height) == (r["width"], r["height"])
-    assert (got.as_array() == want).all()
+    import hostemu_lib as H
+    import test_resize_host as T
+    T._check(got.as_array(), want, filt, case)  # the reference within the bound pinned in test_resize_host.py
+    img, _ = _resize_src(ref, w, h)
+    assert (got.as_array() == H.resize_rgba8(img, rw, rh, mode, filt)).all()  # the kernels == their CPU restatement, always
 
 
 @pytest.mark.parametrize("cfg", [3, 4, 5])
@@ -278,15 +282,30 @@ def test_decode_sampled_rescale_on_lossy_multi_group(J, ref):
 
 def test_decode_sampled_unpinned_rescales_are_refused(J, ref):
     _, data = _resize_src(ref, 96, 64)
-    for (rw, rh, mode, filt) in [(200, 64, 3, 4), (24, 16, 3, 5), (40, 40, 2, 4)]:
+    for (rw, rh, mode, filt) in [(24, 16, 3, 5), (24, 16, 3, 9), (40, 40, 2, 10)]:  # Lanczos3, HANN, Bicubic
         with pytest.raises(J.UnsupportedJXLException):
             J.JxlCoder.decode_sampled(data, rw, rh, 2, mode, filt)
-    alpha = cases.get("rgba_lossless_128")
-    with pytest.raises(J.UnsupportedJXLException):
-        J.JxlCoder.decode_sampled(alpha, 32, 32, 2, 1, 4)
     # w = h = -1: no rescale (JxlCoder.kt:55-62); 0 on an axis: no rescale either (JniDecoding.cpp:116-117)
     assert J.JxlCoder.decode_sampled(data, -1, -1, 2, 1, 4).width == 96
     assert J.JxlCoder.decode_sampled(data, 0, 10, 2, 1, 4).width == 96
+
+
+def test_decode_sampled_rescale_with_alpha(J, ref):
+    """RGBA lossless source: premultiply / rescale / divide back, then ReformatColorConfig premultiplies the result."""
+    import hostemu_lib as H
+    import test_resize_host as T
+    from oracle import synth
+    img = synth.synth_image(128, 128, 3, alpha=True).reshape(128, 128, 4)
+    data = cases.get("rgba_lossless_128")
+    for (rw, rh, mode, filt) in [(40, 40, 1, 4), (64, 20, 2, 1), (200, 150, 3, 6), (33, 77, 3, 2), (128, 50, 3, 7)]:
+        r = ref.decode_sampled(data, w=rw, h=rh, cfg=2, scale_mode=mode, filt=filt)
+        want = r["pixels"][:, : r["width"] * 4].reshape(r["height"], r["width"], 4)
+        got = J.JxlCoder.decode_sampled(data, rw, rh, 2, mode, filt).as_array()
+        T._check(got, want, filt, (rw, rh, mode, filt))
+        mine = H.resize_rgba8(img, rw, rh, mode, filt, has_alpha=True)
+        a = mine[..., 3:4].astype(np.uint16)
+        mine[..., :3] = (mine[..., :3].astype(np.uint16) * a // 255).astype(np.uint8)
+        assert (got == mine).all(), (rw, rh, mode, filt)
 
 
 def test_animated_frame_rescale(J, ref):
