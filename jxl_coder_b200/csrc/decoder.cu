@@ -20,6 +20,7 @@
 #include <mutex>
 #include <thread>
 
+#include "color_matrix.h"
 #include "color_params.h"
 #include "frame_parser.h"
 #include "kernels.h"
@@ -254,6 +255,11 @@ struct Parsed {
   ResizePlan rp;
   size_t rs_table_off = 0, rs_table_bytes = 0, rs_work_off = 0, rs_mid_bytes = 0, rs_scaled_bytes = 0;
   uint32_t out_w = 0, out_h = 0;   // size of the picture handed back
+  // api_level < 34 colour pass (color_matrix.h): tables live in the const region
+  bool color_matrix = false;
+  ColorMatrixPlan cmp;
+  size_t cm_off = 0;
+  bool matrix_before_resize = false;  // getFrameImpl applies it before RescaleImage, decodeSampledImageImpl after
 };
 
 int Fail(Parsed* p, int status, const std::string& msg) {
@@ -417,9 +423,18 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
     p->out_w = p->rp.out_w;
     p->out_h = p->rp.out_h;
   }
-  if (api < 34) {
-    Fail(p, JXLB_UNSUPPORTED, "api_level < 34 colour-matrix pass");
-    return;
+  if (api < 34) {  // JniDecoding.cpp:138-228
+    bool needed = false;
+    if (!MakeColorMatrixPlan(md, &needed, &p->cmp)) {
+      Fail(p, JXLB_UNSUPPORTED, "api_level < 34 colour pass with PQ / HLG tone mapping");
+      return;
+    }
+    if (needed && p->out16) {
+      Fail(p, JXLB_UNSUPPORTED, "api_level < 34 colour pass on 16-bit samples");
+      return;
+    }
+    p->color_matrix = needed;
+    p->matrix_before_resize = target_frame >= 0;
   }
   // ReformatColorConfig: resolve Default (ReformatBitmap.cpp:52-63)
   int cfg = r.color_config;
@@ -563,7 +578,11 @@ struct Batch {
       p.stage_stride = Align256((size_t) p.md.xsize * 4 * (p.out16 ? 2 : 1));
       p.stage_off = stage_total;
       // the fused VarDCT kernel packs straight into final_out; only modular frames (and the unfused debug path) stage RGBA
-      if (p.plan.proto.encoding != 0 || UseUnfusedFilters() || p.resize) stage_total += Align256(p.stage_stride * p.md.ysize);
+      if (p.plan.proto.encoding != 0 || UseUnfusedFilters() || p.resize || p.color_matrix) stage_total += Align256(p.stage_stride * p.md.ysize);
+      if (p.color_matrix) {
+        p.cm_off = const_total;
+        const_total += Align256(sizeof(ColorMatrixPlan));
+      }
       if (p.resize) {
         auto axis_bytes = [](const ResizeAxis& a) { return Align256(a.start.size() * 4) + Align256(a.count.size() * 4) + Align256(a.weights.size() * 2); };
         p.rs_table_off = const_total;
@@ -687,6 +706,7 @@ struct Batch {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) return;
       FillConstRegion(p.plan, p.cs.data(), p.fh, p.g, stg + p.const_off);
+      if (p.color_matrix) memcpy(stg + p.cm_off, &p.cmp, sizeof(ColorMatrixPlan));
       if (p.resize) {
         uint8_t* t = stg + p.rs_table_off;
         for (const ResizeAxis* a : {&p.rp.v, &p.rp.h}) {
@@ -821,7 +841,8 @@ struct Batch {
       pk.dst_stride = pk.width * FormatBytesPerPixel(pk.format);
       pk.dst = buf->final_out.p + final_off[i];
       const PackParams pk_final = pk;
-      if (p.resize) {  // the decode stage hands straight RGBA8 to the rescaler; ReformatColorConfig runs on its result
+      const bool post = p.resize || p.color_matrix;
+      if (post) {  // the decode stage hands straight RGBA8 to the rescaler / colour pass; ReformatColorConfig runs on their result
         pk.format = JXLB_FORMAT_RGBA_8888;
         pk.associate = 0;
         pk.dst = od.data;
@@ -846,8 +867,12 @@ struct Batch {
         }
       } else {
         LaunchModularToRgba(f, od, s);
-        if (!p.resize) LaunchPack(pk, s);
+        if (!post) LaunchPack(pk, s);
       }
+      const uint8_t* res = od.data;
+      uint32_t res_stride = od.stride_bytes;
+      const ColorMatrixPlan* cm_dev = reinterpret_cast<const ColorMatrixPlan*>(buf->const_buf.p + p.cm_off);
+      if (p.color_matrix && p.matrix_before_resize) LaunchColorMatrix(od.data, od.stride_bytes, p.md.xsize, p.md.ysize, cm_dev, s);
       if (p.resize) {
         ResizeDev rd{};
         rd.src = od.data;
@@ -874,21 +899,29 @@ struct Batch {
         }
         rd.mid = buf->work_buf.p + p.rs_work_off;
         rd.scaled = rd.mid + p.rs_mid_bytes;
-        const uint8_t* res = LaunchResize(rd, s);
+        res = LaunchResize(rd, s);
+        res_stride = res == rd.scaled ? rd.scaled_w * 4 : res == rd.mid ? rd.src_w * 4 : rd.src_stride;
         if (p.rp.zero_tail_rows)  // horizontal-only quirk of pic-scale 0.7.6 (resize.h): the last height % 4 rows stay zero
           CUDA_OK(cudaMemsetAsync(rd.scaled + (size_t) (rd.scaled_h - p.rp.zero_tail_rows) * rd.scaled_w * 4, 0,
                                   (size_t) p.rp.zero_tail_rows * rd.scaled_w * 4, s));
+        res += (size_t) p.rp.crop_y * res_stride + (size_t) p.rp.crop_x * 4;
+      }
+      if (post) {
         PackParams pr = pk_final;
-        pr.src = res + (size_t) p.rp.crop_y * (res == rd.scaled ? rd.scaled_w * 4 : res == rd.mid ? rd.src_w * 4 : rd.src_stride) + (size_t) p.rp.crop_x * 4;
-        pr.src_stride = res == rd.scaled ? rd.scaled_w * 4 : res == rd.mid ? rd.src_w * 4 : rd.src_stride;
+        pr.src = res;
+        pr.src_stride = res_stride;
         pr.width = p.out_w;
         pr.height = p.out_h;
         pr.dst_stride = pr.width * FormatBytesPerPixel(pr.format);
-        if (p.rp.zero_last_row) {  // pic-scale 0.7.6 crop quirk (resize.h): the last row of a column-cropped picture is zero
+        if (p.resize && p.rp.zero_last_row) {  // pic-scale 0.7.6 crop quirk (resize.h): the last row of a column-cropped picture is zero
           --pr.height;
           CUDA_OK(cudaMemsetAsync(pr.dst + (size_t) pr.height * pr.dst_stride, 0, pr.dst_stride, s));
           // ReformatColorConfig of a zero row is a zero row in every target format
         }
+        // colour pass after the rescale, before the reformat (JniDecoding.cpp:120-228); the zero rows of the quirks above
+        // pass through it unchanged only when the tables map 0 to 0, which they do (toLinear(0) = 0, gamma[0] = 0)
+        if (p.color_matrix && !p.matrix_before_resize && pr.height)
+          LaunchColorMatrix(const_cast<uint8_t*>(res), res_stride, pr.width, pr.height, cm_dev, s);
         if (pr.height) LaunchPack(pr, s);
       }
       // download: only the "image done" event is recorded here; Finish() enqueues each copy once its image is complete

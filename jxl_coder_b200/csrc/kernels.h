@@ -61,6 +61,10 @@ struct ResizeDev {
 // Returns the pointer holding the result: r.scaled, r.mid (horizontal pass skipped; row stride src_w * 4) or r.src.
 const uint8_t* LaunchResize(const ResizeDev& r, cudaStream_t stream);
 
+// api_level < 34 colour pass (kernels_colormatrix.cu), in place on straight RGBA8; plan_dev: a ColorMatrixPlan in device memory.
+struct ColorMatrixPlan;
+void LaunchColorMatrix(uint8_t* img, uint32_t stride, uint32_t width, uint32_t height, const ColorMatrixPlan* plan_dev, cudaStream_t stream);
+
 // Sets `bytes` (a multiple of 16, 16-byte aligned) to the repeated 32-bit value with a kernel.
 void LaunchFill(void* p, size_t bytes, uint32_t value32, cudaStream_t stream);
 void LaunchBuildGroupBlocks(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, cudaStream_t stream);

@@ -38,7 +38,10 @@ def main():
     print("C4 8K decode only -> RGBA8: gpu best %.1f ms (%.0f MP/s)" % (b * 1e3, mp / b), flush=True)
     # configs[2]: 256 x 1080p -> F16
     ds = [gen_inputs.c3_image(i % 4) for i in range(256)]
-    b, m = best(lambda: J.decode_batch(ds, config=3), 3)
+    def c3():
+        for bmp in J.decode_batch(ds, config=3, keep_native=True):
+            bmp.free()
+    b, m = best(c3, 3)
     mp = 256 * 1920 * 1080 / 1e6
     print("C3 timings", J.last_batch_timings())
     t = time.time()

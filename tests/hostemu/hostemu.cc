@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include "../../jxl_coder_b200/csrc/resize.h"
+#include "../../jxl_coder_b200/csrc/color_matrix.h"
 
 #include "../../jxl_coder_b200/csrc/frame_parser.h"
 #include "../../jxl_coder_b200/csrc/plan.h"
@@ -242,6 +243,25 @@ int emu_resize(const uint8_t* src, uint32_t w, uint32_t h, int32_t req_w, int32_
   dims[1] = plan.out_h;
   if (res.size() > out_capacity) return -1;
   memcpy(out, res.data(), res.size());
+  return 0;
+}
+
+
+// api_level < 34 colour pass (color_matrix.h) of the image whose file is `jxl`, in place on an RGBA8 array.
+// 0 applied, 1 not needed for this colour encoding, 2 needed but not covered, -1 parse error.
+int emu_color_matrix(const uint8_t* jxl, size_t len, uint8_t* rgba, uint32_t w, uint32_t h) {
+  std::vector<uint8_t> cs;
+  size_t cs_len = 0;
+  if (ExtractCodestream(jxl, len, &cs, &cs_len)) return -1;
+  ImageMetadata md;
+  uint64_t fb = 0;
+  std::string err;
+  if (ParseImageHeader(cs.data(), cs.size(), cs_len, &md, &fb, &err)) return -1;
+  bool needed = false;
+  static ColorMatrixPlan plan;
+  if (!MakeColorMatrixPlan(md, &needed, &plan)) return 2;
+  if (!needed) return 1;
+  ApplyColorMatrixHost(plan, rgba, w * 4, w, h);
   return 0;
 }
 

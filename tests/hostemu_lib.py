@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = ["tests/hostemu/hostemu.cc", "jxl_coder_b200/csrc/frame_parser.cc", "jxl_coder_b200/csrc/plan.cc",
        "jxl_coder_b200/csrc/natural_orders.cc", "jxl_coder_b200/csrc/numeric_tables.cc", "jxl_coder_b200/csrc/color_params.cc",
-       "jxl_coder_b200/csrc/resize.cc"]
+       "jxl_coder_b200/csrc/resize.cc", "jxl_coder_b200/csrc/color_matrix.cc"]
 OUT = os.path.join(HERE, "hostemu", "_build", "libhostemu.so")
 _lib = None
 
@@ -43,6 +43,7 @@ def lib():
         L.emu_natural_order.argtypes = [C.c_uint32, C.c_void_p]
         L.emu_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                  C.POINTER(C.c_uint32)]
+        L.emu_color_matrix.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32]
         _lib = L
     return _lib
 
@@ -127,3 +128,10 @@ def resize_rgba8(img, req_w, req_h, scale_mode, filt, has_alpha=False):
     if st:
         return st
     return out[: dims[0] * dims[1] * 4].reshape(dims[1], dims[0], 4).copy()
+
+
+def color_matrix(jxl, rgba):
+    """api_level < 34 colour pass (csrc/color_matrix.cc) on a copy of rgba [h,w,4] u8.  Returns (status, array)."""
+    a = np.ascontiguousarray(rgba, dtype=np.uint8).copy()
+    st = lib().emu_color_matrix(bytes(jxl), len(jxl), a.ctypes.data, a.shape[1], a.shape[0])
+    return st, a

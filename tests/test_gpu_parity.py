@@ -353,3 +353,47 @@ def test_config2_full_size_1080p_f16(J, ref):
     a = np.ascontiguousarray(got.pixels[:, : 1920 * 8]).view(np.float16).astype(np.float32)
     b = np.ascontiguousarray(r["pixels"][:, : 1920 * 8]).view(np.float16).astype(np.float32)
     assert np.abs(a - b).max() <= 1.0 / 255 + 1e-3 and (a == b).mean() > 0.97
+
+
+# ---- api_level < 34 colour pass (applyColorMatrix) ----
+@pytest.mark.parametrize("enc", __import__("test_color_matrix_host").ENCODINGS, ids=[e[0] for e in __import__("test_color_matrix_host").ENCODINGS])
+def test_api33_color_pass_matches_reference(J, ref, enc):
+    import test_color_matrix_host as T
+    name, prim, tf = enc
+    img, data = T.encoded(ref, name, prim, tf)
+    h, w, _ = img.shape
+    want = ref.decode_sampled(data, cfg=2, api_level=33)
+    old = J.JxlCoder.api_level
+    J.JxlCoder.api_level = 33
+    try:
+        got = J.JxlCoder.decode(data, 2)
+        assert got.color_space == ""  # no ColorSpace tag below API 34 (JniDecoding.cpp:236)
+        d = np.abs(got.as_array().astype(int) - want["pixels"][:, : w * 4].reshape(h, w, 4).astype(int))
+        assert d.max() <= 1 and (d != 0).mean() < 1e-4
+        if prim == 1:
+            assert d.max() == 0
+        # after the rescale, before the reformat (1010102)
+        r = ref.decode_sampled(data, w=40, h=30, cfg=2, scale_mode=3, filt=1, api_level=33)
+        g2 = J.JxlCoder.decode_sampled(data, 40, 30, 2, 3, 1).as_array()
+        d = np.abs(g2.astype(int) - r["pixels"][:, : 40 * 4].reshape(30, 40, 4).astype(int))
+        assert d.max() <= 1 and (d != 0).mean() < 1e-3
+    finally:
+        J.JxlCoder.api_level = old
+
+
+def test_api33_on_lossy_and_refusals(J, ref):
+    data = cases.get("rgb_lossy_256x200")
+    want = ref.decode_sampled(data, cfg=2, api_level=33)["pixels"][:, : 256 * 4].reshape(200, 256, 4)
+    old = J.JxlCoder.api_level
+    J.JxlCoder.api_level = 33
+    try:
+        got = J.JxlCoder.decode(data, 2).as_array()
+        d = np.abs(got.astype(int) - want.astype(int))
+        assert d.max() <= 2 and (d == 0).mean() > 0.97  # 1 LSB of the lossy decode through the 2048-level requantisation
+        import test_color_matrix_host as T
+        img = T._source()
+        pq = cases._cached("cm_tf16", lambda: ref.encode_ex(img.reshape(-1), img.shape[1], img.shape[0], 3, lossless=True, primaries=9, transfer=16))
+        with pytest.raises(J.UnsupportedJXLException):
+            J.JxlCoder.decode(pq, 2)
+    finally:
+        J.JxlCoder.api_level = old
