@@ -400,6 +400,18 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
     Fail(p, JXLB_UNSUPPORTED, "more than 4 extra channels");
     return;
   }
+  // DecodeJpegXlOneShot keeps the enum colour encoding only for these transfer functions (interop/JxlDecoding.cpp:125-133,
+  // operator precedence as written there); every other image gets libjxl's synthesised ICC profile and is converted to
+  // sRGB by lcms2 (convertUseDefinedColorSpace, JniDecoding.cpp:104-114) -- not restated, so refused rather than handed
+  // back unconverted
+  {
+    const uint32_t tf = md.color.have_gamma ? 0xFFFFu : md.color.transfer;
+    const bool prefer = (md.color.color_space == 0 && tf == 18) || tf == 16 || tf == 17 || tf == 1 || tf == 13 || tf == 0xFFFFu;
+    if (!prefer) {
+      Fail(p, JXLB_UNSUPPORTED, "colour encoding that the reference converts through its ICC path (lcms2)");
+      return;
+    }
+  }
   // rescale (JniDecoding.cpp:116-136)
   const bool use_sampler = (r.width > 0 || r.height > 0) && (r.width != 0 && r.height != 0);
   p->out_w = md.xsize;
