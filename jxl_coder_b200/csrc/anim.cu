@@ -77,8 +77,8 @@ int32_t jxlb_anim_frame_duration_ms(const jxlb_anim* a, int32_t frame) {
   return a->durations_ms[frame];
 }
 int32_t jxlb_anim_loops(const jxlb_anim* a) { return a ? (int32_t) a->md.num_loops : 0; }
-int32_t jxlb_anim_width(const jxlb_anim* a) { return a ? (int32_t) a->md.xsize : 0; }
-int32_t jxlb_anim_height(const jxlb_anim* a) { return a ? (int32_t) a->md.ysize : 0; }
+int32_t jxlb_anim_width(const jxlb_anim* a) { return a ? (int32_t) (a->md.orientation >= 5 ? a->md.ysize : a->md.xsize) : 0; }
+int32_t jxlb_anim_height(const jxlb_anim* a) { return a ? (int32_t) (a->md.orientation >= 5 ? a->md.xsize : a->md.ysize) : 0; }
 int jxlb_anim_get_frame(jxlb_anim* a, int32_t frame, int32_t width, int32_t height, jxlb_image* out) {
   if (!out) return JXLB_BAD_ARG;
   memset(out, 0, sizeof *out);
@@ -88,7 +88,7 @@ int jxlb_anim_get_frame(jxlb_anim* a, int32_t frame, int32_t width, int32_t heig
     return JXLB_BAD_ARG;
   }
   // JxlAnimatedDecoderCoordinator.cpp:162-: rescale only when both target dimensions are positive
-  const bool rescale = width > 0 && height > 0 && ((uint32_t) width != a->md.xsize || (uint32_t) height != a->md.ysize);
+  const bool rescale = width > 0 && height > 0 && (width != jxlb_anim_width(a) || height != jxlb_anim_height(a));
   // RescaleImage with the coordinator's scale mode and sampler (same refusals as decodeSampled: resize.h)
   jxlb_request r{a->cs.data(), a->cs_len, rescale ? width : -1, rescale ? height : -1, a->cfg, a->scale_mode, a->filter};
   std::vector<DecodedImage> res;

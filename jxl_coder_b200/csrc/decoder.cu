@@ -256,6 +256,9 @@ struct Parsed {
   size_t rs_table_off = 0, rs_table_bytes = 0, rs_work_off = 0, rs_mid_bytes = 0, rs_scaled_bytes = 0;
   uint32_t out_w = 0, out_h = 0;   // size of the picture handed back
   // api_level < 34 colour pass (color_matrix.h): tables live in the const region
+  // orientation (applied right after the decode stage): oriented size and the offset of the oriented image (work region)
+  uint32_t orient = 1, ow = 0, oh = 0;
+  size_t or_off = 0;
   bool color_matrix = false;
   ColorMatrixPlan cmp;
   size_t cm_off = 0;
@@ -336,10 +339,11 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
       p->alpha_premultiplied = md.extra[ai].alpha_premultiplied;
     }
   }
-  if (md.orientation != 1) {
-    Fail(p, JXLB_UNSUPPORTED, "non-identity orientation");
-    return;
-  }
+  // libjxl applies the codestream orientation to the pixels it hands out (keep_orientation is never set by
+  // DecodeJpegXlOneShot): the decoded picture is ow x oh
+  p->orient = md.orientation;
+  p->ow = md.orientation >= 5 ? md.ysize : md.xsize;
+  p->oh = md.orientation >= 5 ? md.xsize : md.ysize;
   if (md.float_samples) {
     Fail(p, JXLB_UNSUPPORTED, "float samples");
     return;
@@ -414,15 +418,15 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
   }
   // rescale (JniDecoding.cpp:116-136)
   const bool use_sampler = (r.width > 0 || r.height > 0) && (r.width != 0 && r.height != 0);
-  p->out_w = md.xsize;
-  p->out_h = md.ysize;
+  p->out_w = p->ow;
+  p->out_h = p->oh;
   if (use_sampler) {
     // RescaleImage (SizeScaler.cpp:38-144) -> weave_scale_u8; the u16 path (f32 arithmetic) is not pinned and is refused
     if (p->out16) {
       Fail(p, JXLB_UNSUPPORTED, "rescale of 16-bit sources");
       return;
     }
-    const int rs = MakeResizePlan(md.xsize, md.ysize, r.width, r.height, r.scale_mode, r.filter, p->has_alpha, &p->rp);
+    const int rs = MakeResizePlan(p->ow, p->oh, r.width, r.height, r.scale_mode, r.filter, p->has_alpha, &p->rp);
     if (rs == kResizeUnsupported) {
       Fail(p, JXLB_UNSUPPORTED, "rescale configuration");
       return;
@@ -590,7 +594,11 @@ struct Batch {
       p.stage_stride = Align256((size_t) p.md.xsize * 4 * (p.out16 ? 2 : 1));
       p.stage_off = stage_total;
       // the fused VarDCT kernel packs straight into final_out; only modular frames (and the unfused debug path) stage RGBA
-      if (p.plan.proto.encoding != 0 || UseUnfusedFilters() || p.resize || p.color_matrix) stage_total += Align256(p.stage_stride * p.md.ysize);
+      if (p.plan.proto.encoding != 0 || UseUnfusedFilters() || p.resize || p.color_matrix || p.orient != 1) stage_total += Align256(p.stage_stride * p.md.ysize);
+      if (p.orient != 1) {
+        p.or_off = work_total;
+        work_total += Align256((size_t) p.ow * p.oh * 4 * (p.out16 ? 2 : 1));
+      }
       if (p.color_matrix) {
         p.cm_off = const_total;
         const_total += Align256(sizeof(ColorMatrixPlan));
@@ -853,7 +861,7 @@ struct Batch {
       pk.dst_stride = pk.width * FormatBytesPerPixel(pk.format);
       pk.dst = buf->final_out.p + final_off[i];
       const PackParams pk_final = pk;
-      const bool post = p.resize || p.color_matrix;
+      const bool post = p.resize || p.color_matrix || p.orient != 1;
       if (post) {  // the decode stage hands straight RGBA8 to the rescaler / colour pass; ReformatColorConfig runs on their result
         pk.format = JXLB_FORMAT_RGBA_8888;
         pk.associate = 0;
@@ -884,11 +892,18 @@ struct Batch {
       const uint8_t* res = od.data;
       uint32_t res_stride = od.stride_bytes;
       const ColorMatrixPlan* cm_dev = reinterpret_cast<const ColorMatrixPlan*>(buf->const_buf.p + p.cm_off);
-      if (p.color_matrix && p.matrix_before_resize) LaunchColorMatrix(od.data, od.stride_bytes, p.md.xsize, p.md.ysize, cm_dev, s);
+      if (p.orient != 1) {
+        uint8_t* dst = buf->work_buf.p + p.or_off;
+        const uint32_t bpp = p.out16 ? 8 : 4;
+        LaunchOrient(od.data, od.stride_bytes, p.md.xsize, p.md.ysize, bpp, p.orient, dst, p.ow * bpp, s);
+        res = dst;
+        res_stride = p.ow * bpp;
+      }
+      if (p.color_matrix && p.matrix_before_resize) LaunchColorMatrix(const_cast<uint8_t*>(res), res_stride, p.ow, p.oh, cm_dev, s);
       if (p.resize) {
         ResizeDev rd{};
-        rd.src = od.data;
-        rd.src_stride = od.stride_bytes;
+        rd.src = res;
+        rd.src_stride = res_stride;
         rd.src_w = p.rp.src_w;
         rd.src_h = p.rp.src_h;
         rd.scaled_w = p.rp.scaled_w;

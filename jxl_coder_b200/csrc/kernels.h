@@ -61,6 +61,11 @@ struct ResizeDev {
 // Returns the pointer holding the result: r.scaled, r.mid (horizontal pass skipped; row stride src_w * 4) or r.src.
 const uint8_t* LaunchResize(const ResizeDev& r, cudaStream_t stream);
 
+// Codestream orientation (EXIF numbering 2..8) applied to an interleaved image of bpp (4 or 8) bytes per pixel; src is w x h,
+// dst is w x h (2..4) or h x w (5..8).
+void LaunchOrient(const uint8_t* src, uint32_t src_stride, uint32_t w, uint32_t h, uint32_t bpp, uint32_t orientation, uint8_t* dst,
+                  uint32_t dst_stride, cudaStream_t stream);
+
 // api_level < 34 colour pass (kernels_colormatrix.cu), in place on straight RGBA8; plan_dev: a ColorMatrixPlan in device memory.
 struct ColorMatrixPlan;
 void LaunchColorMatrix(uint8_t* img, uint32_t stride, uint32_t width, uint32_t height, const ColorMatrixPlan* plan_dev, cudaStream_t stream);

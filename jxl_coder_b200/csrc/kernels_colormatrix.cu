@@ -1,4 +1,4 @@
-// api_level < 34 colour pass (color_matrix.h): in place on straight RGBA8, one thread per pixel, both LUTs staged in
+// Post-decode passes on interleaved pixels: codestream orientation, and the api_level < 34 colour pass (color_matrix.h): in place on straight RGBA8, one thread per pixel, both LUTs staged in
 // shared memory (1 KB + 2 KB).  HBM-bound: 4 B read + 4 B written per pixel.
 #include <atomic>
 
@@ -37,7 +37,39 @@ __global__ void __launch_bounds__(256) ColorMatrixKernel(uint8_t* __restrict__ i
   }
 }
 
+// Orientation: thread per OUTPUT pixel (coalesced stores; the transposing cases read with a stride, served by L2 -- the
+// pass only runs for files that carry a non-identity orientation).
+template <typename Pixel>
+__global__ void __launch_bounds__(256) OrientKernel(const uint8_t* __restrict__ src, uint32_t src_stride, uint32_t w, uint32_t h,
+                                                    uint32_t orientation, uint8_t* __restrict__ dst, uint32_t dst_stride) {
+  const uint32_t ow = orientation >= 5 ? h : w, oh = orientation >= 5 ? w : h;
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= ow || y >= oh) return;
+  uint32_t sx, sy;
+  switch (orientation) {
+    case 2: sx = w - 1 - x; sy = y; break;          // flip horizontal
+    case 3: sx = w - 1 - x; sy = h - 1 - y; break;  // rotate 180
+    case 4: sx = x; sy = h - 1 - y; break;          // flip vertical
+    case 5: sx = y; sy = x; break;                  // transpose
+    case 6: sx = y; sy = h - 1 - x; break;          // rotate 90 clockwise
+    case 7: sx = w - 1 - y; sy = h - 1 - x; break;  // anti-transpose
+    case 8: sx = w - 1 - y; sy = x; break;          // rotate 90 counter-clockwise
+    default: sx = x; sy = y; break;
+  }
+  reinterpret_cast<Pixel*>(dst + (size_t) y * dst_stride)[x] = reinterpret_cast<const Pixel*>(src + (size_t) sy * src_stride)[sx];
+}
+
 }  // namespace
+
+void LaunchOrient(const uint8_t* src, uint32_t src_stride, uint32_t w, uint32_t h, uint32_t bpp, uint32_t orientation, uint8_t* dst,
+                  uint32_t dst_stride, cudaStream_t stream) {
+  if (!w || !h) return;
+  const uint32_t ow = orientation >= 5 ? h : w, oh = orientation >= 5 ? w : h;
+  dim3 grid((ow + 255) / 256, oh, 1);
+  if (bpp == 8) OrientKernel<uint2><<<grid, 256, 0, stream>>>(src, src_stride, w, h, orientation, dst, dst_stride);
+  else OrientKernel<uint32_t><<<grid, 256, 0, stream>>>(src, src_stride, w, h, orientation, dst, dst_stride);
+  ++g_launches_ac;
+}
 
 void LaunchColorMatrix(uint8_t* img, uint32_t stride, uint32_t width, uint32_t height, const ColorMatrixPlan* plan_dev, cudaStream_t stream) {
   if (!width || !height) return;

@@ -401,3 +401,32 @@ def test_api33_on_lossy_and_refusals(J, ref):
             J.JxlCoder.decode(pq, 2)
     finally:
         J.JxlCoder.api_level = old
+
+
+# ---- codestream orientation ----
+@pytest.mark.parametrize("o", range(2, 9))
+def test_orientation_matches_reference(J, ref, o):
+    import test_orientation_host as T
+    for alpha in (False, True):
+        img, data = T.encoded(ref, o, alpha)
+        r = ref.decode_sampled(data, cfg=2)
+        want = r["pixels"][:, : r["width"] * 4].reshape(r["height"], r["width"], 4)
+        got = J.JxlCoder.decode(data, 2)
+        assert (got.width, got.height) == (r["width"], r["height"]) == J.JxlCoder.get_size(data)
+        assert (got.as_array() == want).all()
+    # orientation, then rescale, then reformat
+    img, data = T.encoded(ref, o, False)
+    r = ref.decode_sampled(data, w=20, h=30, cfg=5, scale_mode=3, filt=1)
+    got = J.JxlCoder.decode_sampled(data, 20, 30, 5, 3, 1)
+    assert (got.pixels[:, : 20 * 4] == r["pixels"][:, : 20 * 4]).all()
+
+
+def test_orientation_on_lossy(J, ref):
+    from oracle import synth
+    w, h = 200, 136
+    img = synth.synth_image(w, h, 5)
+    data = cases._cached("orient6_lossy", lambda: ref.encode_ex(img, w, h, 3, distance=1.0, orientation=6))
+    r = ref.decode_sampled(data, cfg=2)
+    assert (r["width"], r["height"]) == (h, w)
+    got = J.JxlCoder.decode(data, 2).as_array()
+    golden_lib.lossy_close(got, r["pixels"][:, : h * 4].reshape(w, h, 4), "orientation 6 lossy")
