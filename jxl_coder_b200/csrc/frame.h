@@ -96,6 +96,7 @@ struct OrderTableIndex {
 struct FrameDev {
   // geometry of the coded frame
   uint32_t width, height;          // pixels
+  uint32_t orientation;            // codestream orientation (1..8): the 8-bit dither pattern is indexed by OUTPUT position
   uint32_t w8, h8;                 // 8x8 cells
   uint32_t w64, h64;               // CfL tiles
   uint32_t ngx, ngy, nlfx, nlfy;

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kFilterThreads) FilterColorKernel(const FrameD
         v[c] = (uint32_t) rintf(s);
       }
     } else {
-      const float d = nt->dither[(y & 31) * 32 + (x & 31)];
+      const float d = nt->dither[DitherIndex(f, (uint32_t) x, (uint32_t) y)];
       for (int c = 0; c < 3; ++c) v[c] = ToU8Dithered(rgb[c], d);
     }
     if (fp.cp.grey) v[0] = v[2] = v[1];
@@ -347,8 +347,13 @@ __global__ void __launch_bounds__(kFilterThreads, 3) FilterColorFastKernel(const
   uint32_t px[4][4];
   float dith[4] = {0.f, 0.f, 0.f, 0.f};
   if (!fp.out16) {
-    const float4 d = *reinterpret_cast<const float4*>(nt->dither + (y & 31) * 32 + (x0 & 31));
-    dith[0] = d.x; dith[1] = d.y; dith[2] = d.z; dith[3] = d.w;
+    if (f.orientation == 1) {
+      const float4 d = *reinterpret_cast<const float4*>(nt->dither + (y & 31) * 32 + (x0 & 31));
+      dith[0] = d.x; dith[1] = d.y; dith[2] = d.z; dith[3] = d.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dith[j] = nt->dither[DitherIndex(f, (uint32_t) (x0 + j), (uint32_t) y)];
+    }
   }
   const uint32_t maxout = fp.out16 ? 65535u : 255u;
 #pragma unroll

@@ -78,6 +78,16 @@ JXLB_HD uint32_t AlphaAt(const FrameDev& f, const OutputDesc& out, int x, int y)
   return ScaleSample(a, out.alpha_bits, maxout);
 }
 
+// libjxl dithers after it has FLIPPED the picture for its orientation but before the transposition of orientations 5..8
+// (found by trying all index maps against the reference, tests/test_orientation_host.py): the 32x32 pattern is indexed
+// by the position in the flipped, untransposed image.  (x, y) are coded coordinates.
+JXLB_HD uint32_t DitherIndex(const FrameDev& f, uint32_t x, uint32_t y) {
+  const uint32_t o = f.orientation;
+  const bool flip_x = o == 2 || o == 3 || o == 7 || o == 8, flip_y = o == 3 || o == 4 || o == 6 || o == 7;
+  const uint32_t ox = flip_x ? f.width - 1 - x : x, oy = flip_y ? f.height - 1 - y : y;
+  return (oy & 31) * 32 + (ox & 31);
+}
+
 JXLB_HD void StageColorToRgba(const FrameDev& f, const ColorParams& cp, const NumericTables& nt, const float* src,
                               const OutputDesc& out, int x, int y) {
   const size_t plane = (size_t) f.plane_h * f.plane_stride, o = (size_t) y * f.plane_stride + x;
@@ -91,7 +101,7 @@ JXLB_HD void StageColorToRgba(const FrameDev& f, const ColorParams& cp, const Nu
       v[c] = (uint32_t) rintf(s);
     }
   } else {
-    const float d = nt.dither[(y & 31) * 32 + (x & 31)];
+    const float d = nt.dither[DitherIndex(f, (uint32_t) x, (uint32_t) y)];
     for (int c = 0; c < 3; ++c) v[c] = ToU8Dithered(rgb[c], d);
   }
   if (cp.grey) v[0] = v[2] = v[1];

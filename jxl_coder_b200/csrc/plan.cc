@@ -24,6 +24,7 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
   FrameDev& f = p.proto;
   memset(&f, 0, sizeof f);
   f.width = fh.coded_w;
+  f.orientation = md.orientation;
   f.height = fh.coded_h;
   f.w8 = (f.width + 7) / 8;
   f.h8 = (f.height + 7) / 8;

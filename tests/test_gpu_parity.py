@@ -421,12 +421,13 @@ def test_orientation_matches_reference(J, ref, o):
     assert (got.pixels[:, : 20 * 4] == r["pixels"][:, : 20 * 4]).all()
 
 
-def test_orientation_on_lossy(J, ref):
+@pytest.mark.parametrize("o", range(2, 9))
+def test_orientation_on_lossy(J, ref, o):
     from oracle import synth
     w, h = 200, 136
     img = synth.synth_image(w, h, 5)
-    data = cases._cached("orient6_lossy", lambda: ref.encode_ex(img, w, h, 3, distance=1.0, orientation=6))
+    data = cases._cached("orient%d_lossy" % o, lambda: ref.encode_ex(img, w, h, 3, distance=1.0, orientation=o))
     r = ref.decode_sampled(data, cfg=2)
-    assert (r["width"], r["height"]) == (h, w)
-    got = J.JxlCoder.decode(data, 2).as_array()
-    golden_lib.lossy_close(got, r["pixels"][:, : h * 4].reshape(w, h, 4), "orientation 6 lossy")
+    got = J.JxlCoder.decode(data, 2)
+    assert (got.width, got.height) == (r["width"], r["height"])
+    golden_lib.lossy_close(got.as_array(), r["pixels"][:, : r["width"] * 4].reshape(r["height"], r["width"], 4), "orientation %d lossy" % o)

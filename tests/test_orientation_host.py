@@ -46,3 +46,21 @@ def test_orientation_table_matches_reference(o, ref):
     assert want.shape[:2] == mine.shape[:2]
     assert (want[..., :3] == mine).all()
     assert ref.get_size(data) == (mine.shape[1], mine.shape[0])
+
+
+@pytest.mark.parametrize("o", range(2, 9))
+def test_lossy_dither_follows_orientation(o, ref):
+    """Lossy (XYB, 8-bit dithered) frames: the CPU emulation of the kernel code, oriented, against the reference.  Pins
+    DitherIndex (csrc/pixel_stages.h): flips happen before libjxl's dither, the transposition after it."""
+    import hostemu_lib as H
+    from oracle import synth
+    import golden_lib
+    w, h = 200, 136
+    img = synth.synth_image(w, h, 5)
+    data = cases._cached("orient%d_lossy" % o, lambda: ref.encode_ex(img, w, h, 3, distance=1.0, orientation=o))
+    r = ref.decode_sampled(data, cfg=2)
+    want = r["pixels"][:, : r["width"] * 4].reshape(r["height"], r["width"], 4)
+    e = H.Decoded(data)
+    emu = e.render()
+    e.close()
+    golden_lib.lossy_close(orient(emu, o), want, "orientation %d" % o)
