@@ -431,3 +431,28 @@ def test_orientation_on_lossy(J, ref, o):
     got = J.JxlCoder.decode(data, 2)
     assert (got.width, got.height) == (r["width"], r["height"])
     golden_lib.lossy_close(got.as_array(), r["pixels"][:, : r["width"] * 4].reshape(r["height"], r["width"], 4), "orientation %d lossy" % o)
+
+
+# ---- the 13 JXL files the reference's demo app ships (app/src/main/assets; copied into tests/_cache/assets, not committed) ----
+def _assets():
+    import glob
+    import os
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_cache", "assets")
+    return sorted(glob.glob(os.path.join(d, "*.jxl")))
+
+
+@pytest.mark.parametrize("path", _assets(), ids=[__import__("os").path.basename(p) for p in _assets()])
+def test_reference_app_assets(J, ref, path):
+    """Every file either decodes to the reference's pixels (lossless exact / lossy bound) or is refused with
+    UnsupportedJXLException -- never a different picture."""
+    data = open(path, "rb").read()
+    r = ref.decode_sampled(data, cfg=2)
+    want = r["pixels"][:, : r["width"] * 4].reshape(r["height"], r["width"], 4)
+    assert J.JxlCoder.get_size(data) == (r["width"], r["height"])
+    try:
+        got = J.JxlCoder.decode(data, 2)
+    except J.UnsupportedJXLException as e:
+        pytest.skip("refused: %s" % e)
+    assert (got.width, got.height) == (r["width"], r["height"])
+    d = np.abs(got.as_array().astype(int) - want.astype(int))
+    assert d.max() <= 1 and (d == 0).mean() > 0.97, (d.max(), (d == 0).mean())
