@@ -868,6 +868,7 @@ struct Batch {
         pk.dst = od.data;
         pk.dst_stride = od.stride_bytes;
       }
+      if (f.sq_nch) LaunchUnsqueeze(f, p.g.sq.steps.data(), s);
       if (f.encoding == 0) {
         const bool timed = (vd++ % kTimeEvery) == 0;
         LaunchLfFinal(f, s);

@@ -3,6 +3,7 @@
 // Format digest: SURVEY.md App. B.2-B.7.
 #pragma once
 #include "hd.h"
+#include "squeeze.h"
 #include "entropy.h"
 #include "modular.h"
 
@@ -161,6 +162,12 @@ struct FrameDev {
   float* xyb1;
   uint32_t plane_stride, plane_h;
   int32_t* mod;                    // [num_mod_channels][height][mod_stride]
+  // squeezed extra channels (squeeze.h): pyramid channel table, inverse steps, host-decoded global-stream samples, buffer
+  const SqChannel* sq_ch;
+  const SqStep* sq_steps;
+  const int32_t* sq_global_data;
+  int32_t* sq_buf;
+  uint32_t sq_nch, sq_global, sq_nsteps, sq_pad;
   uint32_t mod_stride;
   int32_t* status;                 // [num_streams] per-stream status (see StreamStatus)
 };

@@ -1,5 +1,7 @@
 // Host-side header parsing; see frame_parser.h.
+#include <algorithm>
 #include "frame_parser.h"
+#include "modular_fast.h"
 
 #include <cmath>
 #include <cstring>
@@ -541,8 +543,74 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
       if (ec.dim_shift != 0) JXLB_FAIL(kParseUnsupported, "subsampled extra channel");
     if (nmod > 0 && fh.toc_entries > 1) {
       int st = ReadModularHeader(br, &g->global_mh);
-      if (st == kErrUnsupported) JXLB_FAIL(kParseUnsupported, "palette / squeeze transform");
+      if (st == kErrUnsupported) JXLB_FAIL(kParseUnsupported, "palette transform");
       if (st != kOk || br.Overrun()) JXLB_FAIL(kParseInvalid, "global modular header");
+      if (g->global_mh.has_squeeze) {
+        // lossy extra channels of a VarDCT frame (squeeze.h); anything wider is refused
+        if (fh.encoding != 0 || g->global_mh.nb_transforms != 1) JXLB_FAIL(kParseUnsupported, "squeeze transform outside a VarDCT frame's extra channels");
+        std::vector<SqueezeParam> params;
+        if (g->global_mh.nb_squeeze == 0) {
+          params = DefaultSqueezeParams(nmod, fh.coded_w, fh.coded_h);
+        } else {
+          for (uint32_t k = 0; k < g->global_mh.nb_squeeze; ++k)
+            params.push_back({g->global_mh.sq[k].horizontal != 0, g->global_mh.sq[k].in_place != 0, g->global_mh.sq[k].begin_c, g->global_mh.sq[k].num_c});
+        }
+        if (!SqueezeLayout(params, nmod, fh.coded_w, fh.coded_h, &g->sq)) JXLB_FAIL(kParseInvalid, "squeeze parameters");
+        g->squeeze = true;
+        const uint32_t gd = fh.group_dim;
+        uint32_t ng = 0;
+        while (ng < g->sq.channels.size() && g->sq.channels[ng].w <= gd && g->sq.channels[ng].h <= gd) ++ng;
+        g->sq_global = ng;
+        uint32_t per_group = 0;
+        for (uint32_t c = ng; c < g->sq.channels.size(); ++c) {
+          const SqChannel& sc = g->sq.channels[c];
+          if (std::min(sc.hshift, sc.vshift) >= 3) JXLB_FAIL(kParseUnsupported, "squeezed channel coded in the LF groups (image larger than 2048 pixels)");
+          ++per_group;
+        }
+        if (per_group > 8) JXLB_FAIL(kParseUnsupported, "more than 8 squeezed channels per group");
+        // the global stream's channels follow the header: decode them here
+        ModularContext mc{};
+        Arena a2;
+        std::vector<uint8_t> amem(4u << 20);
+        a2.Init(amem.data(), (uint32_t) amem.size());
+        if (g->global_mh.use_global_tree) {
+          if (!g->has_global_tree) JXLB_FAIL(kParseInvalid, "global tree missing");
+          mc.tree = reinterpret_cast<const TreeNode*>(g->tree_blob.data());
+          mc.num_nodes = g->tree_nodes;
+          mc.uses_wp = g->tree_uses_wp;
+          mc.max_property = g->tree_max_property;
+          mc.code.Bind(g->tree_code.data());
+        } else {
+          uint32_t toff, nn, wp, maxp, coff;
+          st = DecodeTree(br, a2, 1u << 16, &toff, &nn, &wp, &maxp);
+          if (st == kOk) st = ParseCode<false>(br, (nn + 1) / 2, true, a2, &coff);
+          if (st != kOk) JXLB_FAIL(st == kErrBadStream ? kParseInvalid : kParseUnsupported, "global modular stream tree");
+          mc.tree = reinterpret_cast<const TreeNode*>(a2.base + toff);
+          mc.num_nodes = nn;
+          mc.uses_wp = wp;
+          mc.max_property = maxp;
+          mc.code.Bind(a2.base + coff);
+        }
+        size_t total = 0;
+        for (uint32_t c = 0; c < ng; ++c) total += (size_t) g->sq.channels[c].w * g->sq.channels[c].h;
+        g->sq_global_data.assign(total + 1, 0);
+        std::vector<ModChannel> chs(ng);
+        size_t o = 0;
+        for (uint32_t c = 0; c < ng; ++c) {
+          chs[c].data = g->sq_global_data.data() + o;
+          chs[c].w = g->sq.channels[c].w;
+          chs[c].h = g->sq.channels[c].h;
+          chs[c].stride = chs[c].w;
+          o += (size_t) chs[c].w * chs[c].h;
+        }
+        std::vector<int32_t> scratch(ModFastScratch::Ints(gd + 8));
+        std::vector<uint32_t> lz(1u << 20);
+        if (ng) {
+          st = DecodeModularChannelsFast(br, mc, g->global_mh.wp, chs.data(), ng, 0, scratch.data(), lz.data(), (1u << 20) - 1);
+          if (st == kErrUnsupported || st == kErrScratch) JXLB_FAIL(kParseUnsupported, "global modular stream");
+          if (st != kOk || br.Overrun()) JXLB_FAIL(kParseInvalid, "global modular stream");
+        }
+      }
     }
   }
   // HfGlobal for multi-section VarDCT frames

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include "frame.h"
+#include "squeeze.h"
 
 namespace jxlb {
 
@@ -116,6 +117,12 @@ struct FrameGlobals {
   std::vector<uint8_t> tree_code;     // code blob for the tree's leaf contexts
   uint64_t global_modular_bit = 0;    // where the global modular GroupHeader starts
   ModularHeader global_mh{};          // parsed for multi-section frames with a modular image
+  // squeezed extra channels (squeeze.h): channel pyramid, inverse steps, and the samples of the channels that live in
+  // the global stream (decoded on the host: they are at most group_dim x group_dim), concatenated in channel order
+  bool squeeze = false;
+  SqueezeLayoutOut sq;
+  uint32_t sq_global = 0;
+  std::vector<int32_t> sq_global_data;
   // HfGlobal
   bool hf_parsed = false;
   uint32_t num_hf_presets = 1, used_orders = 0;

@@ -61,6 +61,10 @@ struct ResizeDev {
 // Returns the pointer holding the result: r.scaled, r.mid (horizontal pass skipped; row stride src_w * 4) or r.src.
 const uint8_t* LaunchResize(const ResizeDev& r, cudaStream_t stream);
 
+// Inverse squeeze of a frame's lossy extra channels (squeeze.h) into f.mod, after every group section has been decoded;
+// steps_host: the host copy of f.sq_steps (launch geometry).
+void LaunchUnsqueeze(const FrameDev& f, const SqStep* steps_host, cudaStream_t stream);
+
 // Codestream orientation (EXIF numbering 2..8) applied to an interleaved image of bpp (4 or 8) bytes per pixel; src is w x h,
 // dst is w x h (2..4) or h x w (5..8).
 void LaunchOrient(const uint8_t* src, uint32_t src_stride, uint32_t w, uint32_t h, uint32_t bpp, uint32_t orientation, uint8_t* dst,

@@ -1,9 +1,10 @@
-// Post-decode passes on interleaved pixels: codestream orientation, and the api_level < 34 colour pass (color_matrix.h): in place on straight RGBA8, one thread per pixel, both LUTs staged in
+// Inverse squeeze of lossy extra channels, and the post-decode passes on interleaved pixels: codestream orientation and the api_level < 34 colour pass (color_matrix.h): in place on straight RGBA8, one thread per pixel, both LUTs staged in
 // shared memory (1 KB + 2 KB).  HBM-bound: 4 B read + 4 B written per pixel.
 #include <atomic>
 
 #include "color_matrix.h"
 #include "kernels.h"
+#include "squeeze.h"
 
 namespace jxlb {
 
@@ -59,7 +60,53 @@ __global__ void __launch_bounds__(256) OrientKernel(const uint8_t* __restrict__ 
   reinterpret_cast<Pixel*>(dst + (size_t) y * dst_stride)[x] = reinterpret_cast<const Pixel*>(src + (size_t) sy * src_stride)[sx];
 }
 
+// ---- inverse squeeze of lossy extra channels (squeeze.h) ----
+// The channels of the global stream were decoded on the host (they are tiny) and arrive in the const region: one CTA
+// per channel copies them to their place in the squeeze buffer.
+__global__ void __launch_bounds__(256) SqueezeScatterGlobalKernel(const FrameDev f) {
+  const uint32_t c = blockIdx.x;
+  if (c >= f.sq_global) return;
+  size_t o = 0;
+  for (uint32_t k = 0; k < c; ++k) o += (size_t) f.sq_ch[k].w * f.sq_ch[k].h;
+  const SqChannel sc = f.sq_ch[c];
+  const size_t n = (size_t) sc.w * sc.h;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) f.sq_buf[sc.off + i] = f.sq_global_data[o + i];
+}
+
+// One inverse step: a thread per row (horizontal step: serial along x because the tendency term looks at the pixel
+// just reconstructed) or per column (vertical step, coalesced).  A 4096^2 alpha plane takes ~20 steps of at most
+// 4096 threads each: latency-bound, a few hundred microseconds in total, off the colour path.
+__global__ void __launch_bounds__(128) SqueezeStepKernel(const FrameDev f, uint32_t k) {
+  const SqStep st = f.sq_steps[k];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool final_plane = st.out_off == 0xFFFFFFFFu;
+  int32_t* out = final_plane ? f.mod + (size_t) st.final_channel * f.height * f.mod_stride : f.sq_buf + st.out_off;
+  const uint32_t ow = st.horizontal ? st.avg_w + st.res_w : st.avg_w;
+  const uint32_t ostride = final_plane ? f.mod_stride : ow;
+  if (st.horizontal) {
+    if (i >= st.avg_h) return;
+    InvSqueezeRow(f.sq_buf + st.avg_off + (size_t) i * st.avg_w, f.sq_buf + st.res_off + (size_t) i * st.res_w, out + (size_t) i * ostride,
+                  st.avg_w, st.res_w);
+  } else {
+    if (i >= st.avg_w) return;
+    InvSqueezeColumn(f.sq_buf + st.avg_off + i, st.avg_w, f.sq_buf + st.res_off + i, st.res_w, out + i, ostride, st.avg_h, st.res_h);
+  }
+}
+
 }  // namespace
+
+void LaunchUnsqueeze(const FrameDev& f, const SqStep* steps_host, cudaStream_t stream) {
+  if (!f.sq_nch) return;
+  if (f.sq_global) {
+    SqueezeScatterGlobalKernel<<<f.sq_global, 256, 0, stream>>>(f);
+    ++g_launches_ac;
+  }
+  for (uint32_t k = 0; k < f.sq_nsteps; ++k) {
+    const uint32_t n = steps_host[k].horizontal ? steps_host[k].avg_h : steps_host[k].avg_w;
+    SqueezeStepKernel<<<(n + 127) / 128, 128, 0, stream>>>(f, k);
+    ++g_launches_ac;
+  }
+}
 
 void LaunchOrient(const uint8_t* src, uint32_t src_stride, uint32_t w, uint32_t h, uint32_t bpp, uint32_t orientation, uint8_t* dst,
                   uint32_t dst_stride, cudaStream_t stream) {

@@ -39,10 +39,19 @@ struct ModTransform {
 };
 static constexpr int kMaxTransforms = 8;
 
+struct ModSqueezeParam {
+  uint8_t horizontal, in_place;
+  uint16_t pad;
+  uint32_t begin_c, num_c;
+};
+static constexpr int kMaxSqueezeParams = 24;
+
 struct ModularHeader {
   uint8_t use_global_tree;
   uint8_t nb_transforms;
-  uint16_t pad;
+  uint8_t has_squeeze;     // a squeeze transform is present (only accepted in a frame's global header, squeeze.h)
+  uint8_t nb_squeeze;      // explicit parameter count (0: default parameters)
+  ModSqueezeParam sq[kMaxSqueezeParams];
   WPHeader wp;
   ModTransform tr[kMaxTransforms];
 };
@@ -59,6 +68,8 @@ JXLB_HD_NOINLINE int ReadModularHeader(BitReader& br, ModularHeader* h) {
   uint32_t nt = br.U32(0, 0, 1, 0, 2, 4, 18, 8);
   if (nt > (uint32_t) kMaxTransforms) return kErrUnsupported;
   h->nb_transforms = (uint8_t) nt;
+  h->has_squeeze = 0;
+  h->nb_squeeze = 0;
   for (uint32_t i = 0; i < nt; ++i) {
     ModTransform& t = h->tr[i];
     t.id = (uint8_t) br.Read(2);
@@ -77,7 +88,18 @@ JXLB_HD_NOINLINE int ReadModularHeader(BitReader& br, ModularHeader* h) {
       t.d_pred = br.Read(4);
       return kErrUnsupported;  // palette: not on the round-1 path
     } else if (t.id == 2) {
-      return kErrUnsupported;  // squeeze: not on the round-1 path
+      if (h->has_squeeze) return kErrUnsupported;  // one squeeze transform per header
+      h->has_squeeze = 1;
+      const uint32_t nsq = br.U32(0, 0, 1, 4, 9, 6, 41, 8);
+      if (nsq > (uint32_t) kMaxSqueezeParams) return kErrUnsupported;
+      h->nb_squeeze = (uint8_t) nsq;
+      for (uint32_t k = 0; k < nsq; ++k) {
+        h->sq[k].horizontal = (uint8_t) br.Read(1);
+        h->sq[k].in_place = (uint8_t) br.Read(1);
+        h->sq[k].pad = 0;
+        h->sq[k].begin_c = br.U32(0, 3, 8, 6, 72, 10, 1096, 13);
+        h->sq[k].num_c = br.U32(1, 0, 2, 0, 3, 0, 4, 4);
+      }
     } else {
       return kErrBadStream;
     }

@@ -82,6 +82,14 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
   p.off_ac_code = take(g.ac_code.size());
   p.off_order_pool = take(g.order_pool.size() * sizeof(uint16_t));
   p.off_blockinfo_off = take(fh.num_lf_groups * sizeof(uint32_t));
+  if (g.squeeze) {
+    f.sq_nch = (uint32_t) g.sq.channels.size();
+    f.sq_global = g.sq_global;
+    f.sq_nsteps = (uint32_t) g.sq.steps.size();
+    p.off_sq_ch = take(g.sq.channels.size() * sizeof(SqChannel));
+    p.off_sq_steps = take(g.sq.steps.size() * sizeof(SqStep));
+    p.off_sq_global = take(g.sq_global_data.size() * sizeof(int32_t));
+  }
   p.const_bytes = o;
 
   // ---- work region
@@ -123,6 +131,7 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
     p.xyb_bytes = (size_t) 3 * f.plane_h * f.plane_stride * 4;
   }
   if (f.num_mod_channels) p.off_mod = take((size_t) f.num_mod_channels * f.height * f.mod_stride * 4);
+  if (g.squeeze) p.off_sq_buf = take(g.sq.buffer_ints * sizeof(int32_t));
   p.work_bytes = o;
 }
 
@@ -136,6 +145,11 @@ void FillConstRegion(const FramePlan& plan, const uint8_t* cs_padded, const Fram
   if (!g.tree_code.empty()) memcpy(dst + plan.off_tree_code, g.tree_code.data(), g.tree_code.size());
   if (!g.ac_code.empty()) memcpy(dst + plan.off_ac_code, g.ac_code.data(), g.ac_code.size());
   if (!g.order_pool.empty()) memcpy(dst + plan.off_order_pool, g.order_pool.data(), g.order_pool.size() * 2);
+  if (g.squeeze) {
+    memcpy(dst + plan.off_sq_ch, g.sq.channels.data(), g.sq.channels.size() * sizeof(SqChannel));
+    memcpy(dst + plan.off_sq_steps, g.sq.steps.data(), g.sq.steps.size() * sizeof(SqStep));
+    memcpy(dst + plan.off_sq_global, g.sq_global_data.data(), g.sq_global_data.size() * sizeof(int32_t));
+  }
   uint32_t* bo = reinterpret_cast<uint32_t*>(dst + plan.off_blockinfo_off);
   size_t acc = 0;
   for (uint32_t l = 0; l < fh.num_lf_groups; ++l) {
@@ -179,6 +193,12 @@ FrameDev BindFrameDev(const FramePlan& p, const uint8_t* cb, uint8_t* wb) {
     f.xyb1 = nullptr;
   }
   if (f.num_mod_channels) f.mod = reinterpret_cast<int32_t*>(wb + p.off_mod);
+  if (f.sq_nch) {
+    f.sq_ch = reinterpret_cast<const SqChannel*>(cb + p.off_sq_ch);
+    f.sq_steps = reinterpret_cast<const SqStep*>(cb + p.off_sq_steps);
+    f.sq_global_data = reinterpret_cast<const int32_t*>(cb + p.off_sq_global);
+    f.sq_buf = reinterpret_cast<int32_t*>(wb + p.off_sq_buf);
+  }
   return f;
 }
 

@@ -103,6 +103,7 @@ JXLB_HD_NOINLINE int BeginModularStream(BitReader& br, const FrameDev& f, Stream
                                         ModularHeader* mh, ModularContext* mc) {
   int st = ReadModularHeader(br, mh);
   if (st != kOk) return st;
+  if (mh->has_squeeze) return kErrUnsupported;  // squeeze is only handled in a frame's global header (host)
   if (mh->use_global_tree) {
     if (!f.global_tree || !f.global_code) return kErrBadStream;
     mc->tree = f.global_tree;
@@ -388,21 +389,46 @@ JXLB_HD_NOINLINE int DecodeAcGroup(BitReader& br_io, const FrameDev& f, uint32_t
 // Per-group modular data of group g (the tail of a PassGroup section, or the whole section of a modular frame):
 // all channels of the frame's modular image that were not decoded globally, restricted to the group's rectangle.
 JXLB_HD_NOINLINE int DecodeModularGroup(BitReader& br, const FrameDev& f, uint32_t g, StreamScratch& s, uint32_t max_local_nodes) {
-  const uint32_t first = f.global_mod_decoded;
-  if (first >= f.num_mod_channels) return kOk;
   const uint32_t gd = f.group_dim;
   const uint32_t gx = g % f.ngx, gy = g / f.ngx;
   const uint32_t x0 = gx * gd, y0 = gy * gd;
   ModChannel ch[8];
-  uint32_t nch = f.num_mod_channels - first;
-  if (nch > 8) return kErrUnsupported;
-  const uint32_t w = f.width - x0 < gd ? f.width - x0 : gd;
-  const uint32_t h = f.height - y0 < gd ? f.height - y0 : gd;
-  for (uint32_t i = 0; i < nch; ++i) {
-    ch[i].data = f.mod + (size_t) (first + i) * f.height * f.mod_stride + (size_t) y0 * f.mod_stride + x0;
-    ch[i].w = w;
-    ch[i].h = h;
-    ch[i].stride = f.mod_stride;
+  uint32_t nch = 0;
+  if (f.sq_nch) {
+    // squeezed extra channels (squeeze.h): the pyramid channels with min(hshift, vshift) <= 2 that are not in the global
+    // stream, each restricted to the group's rectangle scaled by the channel's shifts; a group that no channel
+    // reaches codes nothing, not even a header
+    for (uint32_t c = f.sq_global; c < f.sq_nch; ++c) {
+      const SqChannel sc = f.sq_ch[c];
+      const uint32_t shift = sc.hshift < sc.vshift ? sc.hshift : sc.vshift;
+      if (shift > 2) continue;
+      const uint32_t rx = x0 >> sc.hshift, ry = y0 >> sc.vshift;
+      if (rx >= sc.w || ry >= sc.h) continue;
+      uint32_t rw = gd >> sc.hshift, rh = gd >> sc.vshift;
+      if (rw > sc.w - rx) rw = sc.w - rx;
+      if (rh > sc.h - ry) rh = sc.h - ry;
+      if (!rw || !rh) continue;
+      if (nch == 8) return kErrUnsupported;
+      ch[nch].data = f.sq_buf + sc.off + (size_t) ry * sc.w + rx;
+      ch[nch].w = rw;
+      ch[nch].h = rh;
+      ch[nch].stride = sc.w;
+      ++nch;
+    }
+    if (!nch) return kOk;
+  } else {
+    const uint32_t first = f.global_mod_decoded;
+    if (first >= f.num_mod_channels) return kOk;
+    nch = f.num_mod_channels - first;
+    if (nch > 8) return kErrUnsupported;
+    const uint32_t w = f.width - x0 < gd ? f.width - x0 : gd;
+    const uint32_t h = f.height - y0 < gd ? f.height - y0 : gd;
+    for (uint32_t i = 0; i < nch; ++i) {
+      ch[i].data = f.mod + (size_t) (first + i) * f.height * f.mod_stride + (size_t) y0 * f.mod_stride + x0;
+      ch[i].w = w;
+      ch[i].h = h;
+      ch[i].stride = f.mod_stride;
+    }
   }
   ModularHeader mh;
   ModularContext mc;
@@ -413,10 +439,36 @@ JXLB_HD_NOINLINE int DecodeModularGroup(BitReader& br, const FrameDev& f, uint32
   st = DecodeModularChannelsFast(br, mc, mh.wp, ch, nch, stream_id, s.wp, s.lz77, s.lz77_mask,
                                  s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
   if (st != kOk) return st;
-  ApplyInverseRcts(mh, ch, nch);
+  if (!f.sq_nch) ApplyInverseRcts(mh, ch, nch);
+  else if (mh.nb_transforms) return kErrUnsupported;
   s.arena.used = arena_mark;
   if (br.Overrun()) return kErrTruncated;
   return kOk;
+}
+
+// Undoes the squeeze of a frame's extra channels once every group has been decoded (serial version for the CPU
+// emulation; the device runs one kernel per step, kernels_colormatrix.cu).
+inline void UnsqueezeAllSerial(const FrameDev& f) {
+  size_t o = 0;
+  for (uint32_t c = 0; c < f.sq_global; ++c) {
+    const SqChannel sc = f.sq_ch[c];
+    for (size_t i = 0; i < (size_t) sc.w * sc.h; ++i) f.sq_buf[sc.off + i] = f.sq_global_data[o + i];
+    o += (size_t) sc.w * sc.h;
+  }
+  for (uint32_t k = 0; k < f.sq_nsteps; ++k) {
+    const SqStep st = f.sq_steps[k];
+    int32_t* out = st.out_off == 0xFFFFFFFFu ? f.mod + (size_t) st.final_channel * f.height * f.mod_stride : f.sq_buf + st.out_off;
+    const uint32_t ow = st.horizontal ? st.avg_w + st.res_w : st.avg_w;
+    const uint32_t ostride = st.out_off == 0xFFFFFFFFu ? f.mod_stride : ow;
+    if (st.horizontal) {
+      for (uint32_t y = 0; y < st.avg_h; ++y)
+        InvSqueezeRow(f.sq_buf + st.avg_off + (size_t) y * st.avg_w, f.sq_buf + st.res_off + (size_t) y * st.res_w, out + (size_t) y * ostride,
+                      st.avg_w, st.res_w);
+    } else {
+      for (uint32_t x = 0; x < st.avg_w; ++x)
+        InvSqueezeColumn(f.sq_buf + st.avg_off + x, st.avg_w, f.sq_buf + st.res_off + x, st.res_w, out + x, ostride, st.avg_h, st.res_h);
+    }
+  }
 }
 
 // Channels of the frame's modular image decoded inside the global stream (single-section frames: all of them).

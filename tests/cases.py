@@ -69,11 +69,11 @@ ANIM_W, ANIM_H, ANIM_N = 320, 264, 4
 
 
 def anim_case(kind):
-    """kind: "rgb_lossy" | "rgba_lossless"."""
-    alpha = kind == "rgba_lossless"
+    """kind: "rgb_lossy" | "rgba_lossless" | "rgba_lossy" (alpha coded with the squeeze transform)."""
+    alpha = kind in ("rgba_lossless", "rgba_lossy")
 
     def make():
         ch = 4 if alpha else 3
         frames = np.stack([synth.synth_image(ANIM_W, ANIM_H, 40 + i, alpha=alpha).reshape(ANIM_H, ANIM_W, ch) for i in range(ANIM_N)])
-        return refjxl.anim_encode(frames, ANIM_W, ANIM_H, colorspace=2 if alpha else 1, compression=1 if alpha else 2, duration=40)
+        return refjxl.anim_encode(frames, ANIM_W, ANIM_H, colorspace=2 if alpha else 1, compression=1 if kind == "rgba_lossless" else 2, duration=40)
     return _cached("anim_%s_%dx%dx%d" % (kind, ANIM_W, ANIM_H, ANIM_N), make)

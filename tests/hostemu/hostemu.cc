@@ -121,6 +121,7 @@ void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, si
       if (!e->status) e->status = DecodeModularGroup(br, f, gi, s, kMaxNodes);
       if (e->status) e->failed_stream = (int) (f.num_lf_groups + gi);
     }
+    if (!e->status && f.sq_nch) UnsqueezeAllSerial(f);
   }
   return e;
 }

@@ -189,12 +189,12 @@ def test_f16_and_1010102_on_lossy(J, ref, cfg):
         assert ((a >> 30) == (b >> 30)).all()
 
 
-@pytest.mark.parametrize("kind", ["rgb_lossy", "rgba_lossless"])
+@pytest.mark.parametrize("kind", ["rgb_lossy", "rgba_lossless", "rgba_lossy"])
 def test_animated_frames_match_reference(J, ref, kind):
     """JxlAnimatedImage.getFrame(i) on animations written by the reference's own JxlAnimatedEncoder (full-canvas kReplace
     frames, configs[4] shape): frame table identical; lossy RGB frames within the lossy tolerance of the reference's
-    coalesced frames, lossless RGBA frames bit-exact.  (Lossy RGBA animations code alpha with the squeeze transform,
-    which this round reports as unsupported.)"""
+    coalesced frames (lossy RGBA -- configs[4]'s content, alpha coded with the squeeze transform -- with a bit-exact alpha
+    plane), lossless RGBA frames bit-exact."""
     data = cases.anim_case(kind)
     w, h, n = cases.ANIM_W, cases.ANIM_H, cases.ANIM_N
     ra = ref.Anim(data, cfg=2)
@@ -207,6 +207,9 @@ def test_animated_frames_match_reference(J, ref, kind):
         got = a.get_frame(i).as_array()
         if kind == "rgba_lossless":
             assert (got == want).all()
+        elif kind == "rgba_lossy":
+            assert (got[..., 3] == want[..., 3]).all()
+            golden_lib.lossy_close(got, want, "anim frame %d" % i)
         else:
             golden_lib.lossy_close(got, want, "anim frame %d" % i)
     with pytest.raises(J.JxlCoderError):
@@ -456,3 +459,32 @@ def test_reference_app_assets(J, ref, path):
     assert (got.width, got.height) == (r["width"], r["height"])
     d = np.abs(got.as_array().astype(int) - want.astype(int))
     assert d.max() <= 1 and (d == 0).mean() > 0.97, (d.max(), (d == 0).mean())
+
+
+# ---- lossy alpha: squeeze transform ----
+@pytest.mark.parametrize("shape", [(320, 264, 41, 1.0), (257, 300, 42, 2.0), (700, 520, 43, 0.5), (1024, 300, 44, 1.0)])
+def test_squeezed_alpha_matches_reference(J, ref, shape):
+    import test_squeeze_host as T
+    w, h, seed, ad = shape
+    data = T.rgba_lossy(ref, w, h, seed, ad)
+    r = ref.decode_sampled(data, cfg=2)
+    want = r["pixels"][:, : w * 4].reshape(h, w, 4)
+    got = J.JxlCoder.decode(data, 2)
+    assert got.premultiplied
+    out = got.as_array()
+    assert (out[..., 3] == want[..., 3]).all()
+    golden_lib.lossy_close(out, want, "squeezed alpha %dx%d" % (w, h))
+    # rescale of a source with alpha (premultiply around the passes), then reformat
+    r = ref.decode_sampled(data, w=w // 3, h=h // 3, cfg=3, scale_mode=3, filt=1)
+    g2 = J.JxlCoder.decode_sampled(data, w // 3, h // 3, 3, 3, 1)
+    a = np.ascontiguousarray(g2.pixels[:, : (w // 3) * 8]).view(np.float16).astype(np.float32)
+    b = np.ascontiguousarray(r["pixels"][:, : (w // 3) * 8]).view(np.float16).astype(np.float32)
+    assert np.abs(a - b).max() <= 2.0 / 255 + 1e-3 and (a == b).mean() > 0.9
+
+
+def test_squeezed_alpha_wider_than_2048_is_refused(J, ref):
+    """Channels of the pyramid that would be coded in the LF groups (image side > 2048) are not handled: refused."""
+    import test_squeeze_host as T
+    data = T.rgba_lossy(ref, 2304, 40, 45, 1.0)
+    with pytest.raises(J.UnsupportedJXLException):
+        J.JxlCoder.decode(data, 2)
