@@ -561,13 +561,13 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
         uint32_t ng = 0;
         while (ng < g->sq.channels.size() && g->sq.channels[ng].w <= gd && g->sq.channels[ng].h <= gd) ++ng;
         g->sq_global = ng;
-        uint32_t per_group = 0;
+        uint32_t per_group = 0, per_lf_group = 0;
         for (uint32_t c = ng; c < g->sq.channels.size(); ++c) {
           const SqChannel& sc = g->sq.channels[c];
-          if (std::min(sc.hshift, sc.vshift) >= 3) JXLB_FAIL(kParseUnsupported, "squeezed channel coded in the LF groups (image larger than 2048 pixels)");
-          ++per_group;
+          if (std::min(sc.hshift, sc.vshift) >= 3) ++per_lf_group;
+          else ++per_group;
         }
-        if (per_group > 8) JXLB_FAIL(kParseUnsupported, "more than 8 squeezed channels per group");
+        if (per_group > 8 || per_lf_group > 8) JXLB_FAIL(kParseUnsupported, "more than 8 squeezed channels per group");
         // the global stream's channels follow the header: decode them here
         ModularContext mc{};
         Arena a2;

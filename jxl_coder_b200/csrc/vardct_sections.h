@@ -177,6 +177,33 @@ JXLB_HD void LfGroupRect(const FrameDev& f, uint32_t lfg, uint32_t* cx0, uint32_
   *h64 = (ph + 63) / 64;
 }
 
+// Squeezed extra channels (squeeze.h) that a modular sub-stream covering the pixel rectangle (x0, y0, dim x dim) codes:
+// the pyramid channels outside the global stream with min_shift <= min(hshift, vshift) <= max_shift, each restricted to
+// the rectangle scaled by its shifts.  LF groups carry shifts >= 3, pass groups (single pass) shifts 0..2.
+JXLB_HD int CollectSqueezeChannels(const FrameDev& f, uint32_t x0, uint32_t y0, uint32_t dim, uint32_t min_shift, uint32_t max_shift,
+                                   ModChannel* ch, uint32_t* nch_out) {
+  uint32_t nch = 0;
+  for (uint32_t c = f.sq_global; c < f.sq_nch; ++c) {
+    const SqChannel sc = f.sq_ch[c];
+    const uint32_t shift = sc.hshift < sc.vshift ? sc.hshift : sc.vshift;
+    if (shift < min_shift || shift > max_shift) continue;
+    const uint32_t rx = x0 >> sc.hshift, ry = y0 >> sc.vshift;
+    if (rx >= sc.w || ry >= sc.h) continue;
+    uint32_t rw = dim >> sc.hshift, rh = dim >> sc.vshift;
+    if (rw > sc.w - rx) rw = sc.w - rx;
+    if (rh > sc.h - ry) rh = sc.h - ry;
+    if (!rw || !rh) continue;
+    if (nch == 8) return kErrUnsupported;
+    ch[nch].data = f.sq_buf + sc.off + (size_t) ry * sc.w + rx;
+    ch[nch].w = rw;
+    ch[nch].h = rh;
+    ch[nch].stride = sc.w;
+    ++nch;
+  }
+  *nch_out = nch;
+  return kOk;
+}
+
 // LfGroup section of a VarDCT frame (App. B.7): LF coefficients, HF metadata, block placement.
 // place_blocks = false: stop after the entropy-coded data (the CUDA kernel then places the blocks with the whole warp,
 // PlaceBlocksWarp in kernels.cu, which must produce exactly what the serial loop below produces).
@@ -204,7 +231,22 @@ JXLB_HD_NOINLINE int DecodeLfGroupSection(BitReader& br, const FrameDev& f, uint
   if (st != kOk) return st;
   ApplyInverseRcts(mh, ch, 3);
   s.arena.used = arena_mark;
-  // (modular LF-group data for channels with dim_shift >= 3: none on the supported path)
+  // ---- ModularLfGroup: squeezed extra channels with both shifts >= 3 (images wider or taller than 2048 pixels)
+  if (f.sq_nch) {
+    ModChannel sch[8];
+    uint32_t nsq = 0;
+    st = CollectSqueezeChannels(f, cx0 * 8, cy0 * 8, kLfGroupCells * 8, 3, 1000, sch, &nsq);
+    if (st != kOk) return st;
+    if (nsq) {
+      st = BeginModularStream(br, f, s, max_local_nodes, &mh, &mc);
+      if (st != kOk) return st;
+      if (mh.nb_transforms) return kErrUnsupported;
+      st = DecodeModularChannelsFast(br, mc, mh.wp, sch, nsq, 1 + nlf + lfg, s.wp, s.lz77, s.lz77_mask,
+                                     s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
+      if (st != kOk) return st;
+      s.arena.used = arena_mark;
+    }
+  }
   // ---- HF metadata
   uint32_t nb_blocks = br.Read(CeilLog2(w8 * h8)) + 1;
   if (nb_blocks > w8 * h8) return kErrBadStream;
@@ -395,26 +437,9 @@ JXLB_HD_NOINLINE int DecodeModularGroup(BitReader& br, const FrameDev& f, uint32
   ModChannel ch[8];
   uint32_t nch = 0;
   if (f.sq_nch) {
-    // squeezed extra channels (squeeze.h): the pyramid channels with min(hshift, vshift) <= 2 that are not in the global
-    // stream, each restricted to the group's rectangle scaled by the channel's shifts; a group that no channel
-    // reaches codes nothing, not even a header
-    for (uint32_t c = f.sq_global; c < f.sq_nch; ++c) {
-      const SqChannel sc = f.sq_ch[c];
-      const uint32_t shift = sc.hshift < sc.vshift ? sc.hshift : sc.vshift;
-      if (shift > 2) continue;
-      const uint32_t rx = x0 >> sc.hshift, ry = y0 >> sc.vshift;
-      if (rx >= sc.w || ry >= sc.h) continue;
-      uint32_t rw = gd >> sc.hshift, rh = gd >> sc.vshift;
-      if (rw > sc.w - rx) rw = sc.w - rx;
-      if (rh > sc.h - ry) rh = sc.h - ry;
-      if (!rw || !rh) continue;
-      if (nch == 8) return kErrUnsupported;
-      ch[nch].data = f.sq_buf + sc.off + (size_t) ry * sc.w + rx;
-      ch[nch].w = rw;
-      ch[nch].h = rh;
-      ch[nch].stride = sc.w;
-      ++nch;
-    }
+    // squeezed extra channels (squeeze.h); a group that no channel reaches codes nothing, not even a header
+    const int cst = CollectSqueezeChannels(f, x0, y0, gd, 0, 2, ch, &nch);
+    if (cst != kOk) return cst;
     if (!nch) return kOk;
   } else {
     const uint32_t first = f.global_mod_decoded;

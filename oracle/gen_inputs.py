@@ -45,6 +45,14 @@ def c4_image():
     return cached("c4_8k.jxl", lambda: refjxl.encode(synth.synth_image(7680, 4320, 200), 7680, 4320))
 
 
+def c5_animation(frames=120, size=1024):
+    """configs[4]: 120-frame 1024x1024 RGBA lossy animation written like the reference's JxlAnimatedEncoder (40 ms frames)."""
+    def make():
+        fr = np.stack([synth.synth_image(size, size, 300 + i, alpha=True).reshape(size, size, 4) for i in range(frames)])
+        return refjxl.anim_encode(fr, size, size, colorspace=2, compression=2, duration=40)
+    return cached("c5_anim_%dx%dx%d.jxl" % (size, size, frames), make)
+
+
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     for i in range(n):

@@ -52,5 +52,28 @@ def main():
           (b * 1e3, mp / b, m * 1e3, rt * 1e3, 1920 * 1080 / 1e6 / rt), flush=True)
 
 
+def c5():
+    # configs[4]: every frame of a 120-frame 1024x1024 RGBA lossy animation through JxlAnimatedImage.getFrame(i)
+    d = gen_inputs.c5_animation()
+    a = J.JxlAnimatedImage(d, 2)
+    n = a.number_of_frames
+    a.get_frame(0)
+    t = time.time()
+    for i in range(n):
+        a.get_frame(i)
+    dt = time.time() - t
+    a.close()
+    ra = refjxl.Anim(d, cfg=2)
+    rt = {}
+    for i in (0, 10, 40, n - 1):
+        t0 = time.time()
+        ra.frame(i)
+        rt[i] = time.time() - t0
+    ra.close()
+    print("C5 %d-frame 1024x1024 RGBA lossy animation, getFrame(i) for every i: gpu %.1f ms per frame (%.0f MP/s) | reference getFrame(i) "
+          "re-decodes frames 0..i: %s ms" % (n, dt / n * 1e3, n * 1.048576 / dt, {k: round(v * 1e3, 1) for k, v in rt.items()}), flush=True)
+
+
 if __name__ == "__main__":
+    c5()
     main()

@@ -462,7 +462,7 @@ def test_reference_app_assets(J, ref, path):
 
 
 # ---- lossy alpha: squeeze transform ----
-@pytest.mark.parametrize("shape", [(320, 264, 41, 1.0), (257, 300, 42, 2.0), (700, 520, 43, 0.5), (1024, 300, 44, 1.0)])
+@pytest.mark.parametrize("shape", [(320, 264, 41, 1.0), (257, 300, 42, 2.0), (700, 520, 43, 0.5), (1024, 300, 44, 1.0), (2304, 300, 45, 1.0), (520, 4200, 46, 1.0)])
 def test_squeezed_alpha_matches_reference(J, ref, shape):
     import test_squeeze_host as T
     w, h, seed, ad = shape
@@ -480,11 +480,3 @@ def test_squeezed_alpha_matches_reference(J, ref, shape):
     a = np.ascontiguousarray(g2.pixels[:, : (w // 3) * 8]).view(np.float16).astype(np.float32)
     b = np.ascontiguousarray(r["pixels"][:, : (w // 3) * 8]).view(np.float16).astype(np.float32)
     assert np.abs(a - b).max() <= 2.0 / 255 + 1e-3 and (a == b).mean() > 0.9
-
-
-def test_squeezed_alpha_wider_than_2048_is_refused(J, ref):
-    """Channels of the pyramid that would be coded in the LF groups (image side > 2048) are not handled: refused."""
-    import test_squeeze_host as T
-    data = T.rgba_lossy(ref, 2304, 40, 45, 1.0)
-    with pytest.raises(J.UnsupportedJXLException):
-        J.JxlCoder.decode(data, 2)
