@@ -6,6 +6,10 @@
 // frame (which is also what lets a 120-frame animation spread over several GPUs).  Frames that need composition
 // (crops, blending, reference slots) report JXLB_UNSUPPORTED.
 #include <cmath>
+#include <cstdlib>
+#include <deque>
+#include <map>
+#include <mutex>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -23,6 +27,23 @@ struct jxlb_anim {
   std::vector<FrameHeader> frames;       // displayed frames (regular / skip-progressive)
   std::vector<int32_t> durations_ms;
   int32_t cfg = 1, scale_mode = 1, filter = 1, api_level = 34;
+  // Frames are independent pictures and a single small frame leaves the GPU almost idle (its entropy stage is a handful
+  // of serial chains), so getFrame(i) decodes frames i .. i + prefetch - 1 in ONE batch and keeps the others for the
+  // calls that follow -- players ask for the frames in order.  Each request is a mini codestream: the image header
+  // followed by that frame's bytes only (frames are byte-aligned).
+  size_t header_bytes = 0;
+  std::vector<std::pair<size_t, size_t>> frame_bytes;   // [begin, end) of every displayed frame
+  int prefetch = 16;
+  std::mutex mu;
+  struct Key {
+    int32_t frame, w, h;
+    bool operator<(const Key& o) const { return frame != o.frame ? frame < o.frame : w != o.w ? w < o.w : h < o.h; }
+  };
+  std::map<Key, DecodedImage> cache;
+  std::deque<Key> cache_order;
+  ~jxlb_anim() {
+    for (auto& kv : cache) FreeImageMemory(kv.second.data, kv.second.device);
+  }
 };
 
 extern "C" {
@@ -49,8 +70,12 @@ jxlb_anim* jxlb_anim_open(const uint8_t* data, size_t len, int32_t color_config,
     set(JXLB_INVALID_JXL);
     return nullptr;
   }
+  a->header_bytes = (size_t) ((fb + 7) / 8);
+  const bool byte_aligned_header = fb % 8 == 0;
+  if (const char* e = getenv("JXLB_ANIM_PREFETCH")) a->prefetch = std::max(1, atoi(e));
   for (;;) {
     FrameHeader fh;
+    const uint64_t frame_begin_bit = fb;
     if (ParseFrameHeader(a->cs.data(), a->cs.size(), a->cs_len, a->md, fb, &fh, &err)) {
       delete a;
       set(JXLB_INVALID_JXL);
@@ -63,6 +88,13 @@ jxlb_anim* jxlb_anim_open(const uint8_t* data, size_t len, int32_t color_config,
         ms = roundf(1000.0f * (float) fh.duration * (float) a->md.tps_den / (float) a->md.tps_num);
       a->durations_ms.push_back((int32_t) ms);
       a->frames.push_back(fh);
+      a->frame_bytes.emplace_back((size_t) (frame_begin_bit / 8), (size_t) fh.end_byte);
+      if (!byte_aligned_header || frame_begin_bit % 8 != 0) a->prefetch = 0;  // fall back to whole-file requests
+      // a frame that needs the canvas of earlier frames (crop, blending) is not an independent picture: the whole-file
+      // path below refuses those
+      if (fh.blend.mode != 0 || fh.have_crop || fh.coded_w != a->md.xsize || fh.coded_h != a->md.ysize) a->prefetch = 0;
+    } else {
+      a->prefetch = 0;  // invisible (reference-only) frames: displayed frames are not self-contained
     }
     if (fh.is_last) break;
     fb = fh.end_byte * 8;
@@ -90,12 +122,57 @@ int jxlb_anim_get_frame(jxlb_anim* a, int32_t frame, int32_t width, int32_t heig
   // JxlAnimatedDecoderCoordinator.cpp:162-: rescale only when both target dimensions are positive
   const bool rescale = width > 0 && height > 0 && (width != jxlb_anim_width(a) || height != jxlb_anim_height(a));
   // RescaleImage with the coordinator's scale mode and sampler (same refusals as decodeSampled: resize.h)
-  jxlb_request r{a->cs.data(), a->cs_len, rescale ? width : -1, rescale ? height : -1, a->cfg, a->scale_mode, a->filter};
-  std::vector<DecodedImage> res;
-  BatchTimings tm;
-  const int32_t fi = frame;
-  DecodeBatch(&r, 1, a->api_level, -1, -1, &res, &tm, &fi);
-  const DecodedImage& d = res[0];
+  const int32_t rw = rescale ? width : -1, rh = rescale ? height : -1;
+  DecodedImage d;
+  {
+    std::lock_guard<std::mutex> lock(a->mu);
+    const jxlb_anim::Key key{frame, rw, rh};
+    auto it = a->cache.find(key);
+    if (it != a->cache.end()) {
+      d = it->second;  // ownership moves to the caller
+      a->cache.erase(it);
+    } else if (a->prefetch <= 0) {
+      jxlb_request r{a->cs.data(), a->cs_len, rw, rh, a->cfg, a->scale_mode, a->filter};
+      std::vector<DecodedImage> res;
+      BatchTimings tm;
+      const int32_t fi = frame;
+      DecodeBatch(&r, 1, a->api_level, -1, -1, &res, &tm, &fi);
+      d = res[0];
+    } else {
+      const int32_t n = std::min<int32_t>(a->prefetch, (int32_t) a->frames.size() - frame);
+      std::vector<std::vector<uint8_t>> mini(n);
+      std::vector<jxlb_request> reqs(n);
+      std::vector<int32_t> fidx(n, 0);
+      for (int32_t k = 0; k < n; ++k) {
+        const auto& fb = a->frame_bytes[frame + k];
+        mini[k].reserve(a->header_bytes + (fb.second - fb.first));
+        mini[k].assign(a->cs.begin(), a->cs.begin() + a->header_bytes);
+        mini[k].insert(mini[k].end(), a->cs.begin() + fb.first, a->cs.begin() + fb.second);
+        reqs[k] = jxlb_request{mini[k].data(), mini[k].size(), rw, rh, a->cfg, a->scale_mode, a->filter};
+      }
+      std::vector<DecodedImage> res;
+      BatchTimings tm;
+      DecodeBatch(reqs.data(), (size_t) n, a->api_level, -1, -1, &res, &tm, fidx.data());
+      d = res[0];
+      for (int32_t k = 1; k < n; ++k) {
+        const jxlb_anim::Key kk{frame + k, rw, rh};
+        if (res[k].status != JXLB_OK || a->cache.count(kk)) {
+          FreeImageMemory(res[k].data, res[k].device);
+          continue;
+        }
+        a->cache[kk] = res[k];
+        a->cache_order.push_back(kk);
+      }
+      while (a->cache.size() > (size_t) 2 * a->prefetch && !a->cache_order.empty()) {  // bounded: drop the oldest leftovers
+        auto old = a->cache.find(a->cache_order.front());
+        a->cache_order.pop_front();
+        if (old != a->cache.end()) {
+          FreeImageMemory(old->second.data, old->second.device);
+          a->cache.erase(old);
+        }
+      }
+    }
+  }
   out->data = d.data;
   out->width = d.width;
   out->height = d.height;
