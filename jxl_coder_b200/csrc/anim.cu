@@ -33,7 +33,7 @@ struct jxlb_anim {
   // followed by that frame's bytes only (frames are byte-aligned).
   size_t header_bytes = 0;
   std::vector<std::pair<size_t, size_t>> frame_bytes;   // [begin, end) of every displayed frame
-  int prefetch = 16;
+  int prefetch = 32;   // capped so that the prefetched pictures stay below ~256 MB (jxlb_anim_open)
   std::mutex mu;
   struct Key {
     int32_t frame, w, h;
@@ -72,6 +72,10 @@ jxlb_anim* jxlb_anim_open(const uint8_t* data, size_t len, int32_t color_config,
   }
   a->header_bytes = (size_t) ((fb + 7) / 8);
   const bool byte_aligned_header = fb % 8 == 0;
+  {
+    const uint64_t frame_out = (uint64_t) a->md.xsize * a->md.ysize * 4;
+    a->prefetch = (int) std::min<uint64_t>(32, std::max<uint64_t>(1, (256ull << 20) / std::max<uint64_t>(frame_out, 1)));
+  }
   if (const char* e = getenv("JXLB_ANIM_PREFETCH")) a->prefetch = std::max(1, atoi(e));
   for (;;) {
     FrameHeader fh;
