@@ -480,3 +480,15 @@ def test_squeezed_alpha_matches_reference(J, ref, shape):
     a = np.ascontiguousarray(g2.pixels[:, : (w // 3) * 8]).view(np.float16).astype(np.float32)
     b = np.ascontiguousarray(r["pixels"][:, : (w // 3) * 8]).view(np.float16).astype(np.float32)
     assert np.abs(a - b).max() <= 2.0 / 255 + 1e-3 and (a == b).mean() > 0.9
+
+
+def test_corrupt_inputs_never_hang(J):
+    """168 mutated / truncated files through jxlb_decode_batch in a subprocess under a timeout: each comes back as a picture
+    or as an error, nothing hangs or crashes, and the library still decodes afterwards."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "gpu_fuzz.py"), "7"], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "fuzz ok=" in r.stdout
