@@ -828,6 +828,7 @@ struct Batch {
     LaunchBuildGroupBlocks(frames_d, jobs_lane_groups_d, (uint32_t) jobs_lane_groups.size(), s);
     LaunchAcLanes(frames_d, jobs_ac_cta_d, (uint32_t) jobs_ac_cta.size(), ctx->nat_dev, ac_smem_code_bytes, ac_fast, s);
     LaunchGroupModular(frames_d, jobs_lane_mod_d, (uint32_t) jobs_lane_mod.size(), sl_grp, s);
+    LaunchFrameStatus(frames_d, nframes, s);
     CUDA_OK(cudaEventRecord(ev[4], s));
     EnsureSampleEvents();
     cudaEvent_t* sev = sample_ev[run_index].data();

@@ -161,6 +161,8 @@ struct FrameDev {
   float* xyb0;                     // [3][plane_h][plane_stride]
   float* xyb1;
   uint32_t plane_stride, plane_h;
+  int32_t* frame_bad;              // [1] set by FrameStatusKernel when any entropy-coded section of the frame failed: the
+                                   // reconstruction kernels then skip the frame (its metadata planes are garbage)
   int32_t* mod;                    // [num_mod_channels][height][mod_stride]
   // squeezed extra channels (squeeze.h): pyramid channel table, inverse steps, host-decoded global-stream samples, buffer
   const SqChannel* sq_ch;

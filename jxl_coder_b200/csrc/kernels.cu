@@ -187,13 +187,36 @@ __global__ void __launch_bounds__(kStreamBlockThreads) PassGroupKernel(const Fra
   const uint32_t sec = 1 + f.num_lf_groups + 1 + job.index;
   br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);
   int st = kOk;
-  if (f.encoding == 0) st = DecodeAcGroup(br, f, job.index, nat, sc);
+  if (f.encoding == 0) {
+    // the group's blocks come from its LF group's placement: unusable when that section failed
+    const uint32_t lfg = (job.index / f.ngx / 8) * f.nlfx + (job.index % f.ngx) / 8;
+    st = f.status[lfg] == kOk ? DecodeAcGroup(br, f, job.index, nat, sc) : (int) kErrBadStream;
+  }
   if (st == kOk) st = DecodeModularGroup(br, f, job.index, sc, scratch.max_local_nodes);
   f.status[job.status_slot] = st;
 }
 
+// One warp per frame, after every entropy-coded section of the batch has been decoded: any section that failed (or was
+// never reached) marks the frame bad.  The reconstruction kernels below skip bad frames -- their strategy / offset /
+// multiplier planes are partly written garbage that must not drive loops or addresses.  (The host resolves the same
+// statuses into the per-image error after the run, Batch::Finish.)
+__global__ void __launch_bounds__(32) FrameStatusKernel(const FrameDev* frames, uint32_t nframes) {
+  if (blockIdx.x >= nframes) return;
+  const FrameDev& f = frames[blockIdx.x];
+  int bad = 0;
+  if (f.single_section) {
+    if (threadIdx.x == 0) bad = f.status[f.num_lf_groups + f.num_groups] != kOk;
+  } else {
+    const uint32_t first = f.encoding == 0 ? 0u : f.num_lf_groups, last = f.num_lf_groups + f.num_groups;
+    for (uint32_t i = first + threadIdx.x; i < last; i += 32) bad |= f.status[i] != kOk;
+  }
+  bad = __any_sync(0xFFFFFFFFu, bad);
+  if (threadIdx.x == 0) *f.frame_bad = bad;
+}
+
 // ---- numeric ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) LfFinalKernel(const FrameDev f) {
+  if (*f.frame_bad) return;
   const uint32_t cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y;
   if (cx >= f.w8 || cy >= f.h8) return;
   const LfMul m = MakeLfMul(f);
@@ -208,6 +231,7 @@ __global__ void __launch_bounds__(256) LfFinalKernel(const FrameDev f) {
 constexpr int kReconThreads = 192;  // 3 channels x 64 columns/rows
 
 __global__ void __launch_bounds__(kReconThreads, 4) ReconRegionKernel(const FrameDev f, const NumericTables* nt) {
+  if (*f.frame_bad) return;
   extern __shared__ __align__(16) uint8_t smem[];
   RegionShared& sh = *reinterpret_cast<RegionShared*>(smem);
   ReconRegion(f, *nt, blockIdx.x, blockIdx.y, sh, (int) threadIdx.x, (int) blockDim.x, SyncThreads());
@@ -218,6 +242,7 @@ __global__ void __launch_bounds__(kReconThreads, 4) ReconRegionKernel(const Fram
 // 128 threads x <= 128 registers: a CTA must fit beside the LF-group CTAs of another batch that overlap it (a 256-thread
 // CTA at 254 registers needs a whole SM's register file and would stall its stream until an SM drains).
 __global__ void __launch_bounds__(128, 4) ReconLargeKernel(const FrameDev f, const NumericTables* nt) {
+  if (*f.frame_bad) return;
   __shared__ uint32_t todo[64];
   __shared__ uint32_t ntodo;
   if (threadIdx.x == 0) ntodo = 0;
@@ -239,12 +264,14 @@ __global__ void __launch_bounds__(128, 4) ReconLargeKernel(const FrameDev f, con
 }
 
 __global__ void __launch_bounds__(256) GaborishKernel(const FrameDev f, const float* src, float* dst) {
+  if (*f.frame_bad) return;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= (int) f.width || y >= (int) f.height) return;
   StageGaborish(f, src, dst, x, y);
 }
 
 __global__ void __launch_bounds__(256) EpfKernel(const FrameDev f, int stage, const float* src, float* dst) {
+  if (*f.frame_bad) return;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= (int) f.width || y >= (int) f.height) return;
   StageEpf(f, stage, src, dst, x, y);
@@ -252,12 +279,14 @@ __global__ void __launch_bounds__(256) EpfKernel(const FrameDev f, int stage, co
 
 __global__ void __launch_bounds__(256) ColorKernel(const FrameDev f, const ColorParams cp, const NumericTables* nt, const float* src,
                                                    OutputDesc out) {
+  if (*f.frame_bad) return;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= (int) f.width || y >= (int) f.height) return;
   StageColorToRgba(f, cp, *nt, src, out, x, y);
 }
 
 __global__ void __launch_bounds__(256) ModularToRgbaKernel(const FrameDev f, OutputDesc out) {
+  if (*f.frame_bad) return;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= (int) f.width || y >= (int) f.height) return;
   if (!f.single_section) StageGlobalInverseRct(f, x, y);
@@ -322,6 +351,12 @@ void LaunchPassGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t nj
                       cudaStream_t stream) {
   if (!njobs) return;
   PassGroupKernel<<<njobs, kStreamBlockThreads, 0, stream>>>(frames, jobs, njobs, nat, scratch);
+  ++g_launches;
+}
+
+void LaunchFrameStatus(const FrameDev* frames, uint32_t nframes, cudaStream_t stream) {
+  if (!nframes) return;
+  FrameStatusKernel<<<nframes, 32, 0, stream>>>(frames, nframes);
   ++g_launches;
 }
 

@@ -30,6 +30,8 @@ struct ScratchLayout {
 
 void LaunchSingleSectionFrames(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat,
                                ScratchLayout scratch, cudaStream_t stream);
+// After all entropy kernels of a batch: marks the frames with a failed section (FrameDev::frame_bad).
+void LaunchFrameStatus(const FrameDev* frames, uint32_t nframes, cudaStream_t stream);
 void LaunchLfGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, ScratchLayout scratch, cudaStream_t stream);
 void LaunchPassGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat, ScratchLayout scratch,
                       cudaStream_t stream);

@@ -36,6 +36,10 @@ __global__ void __launch_bounds__(128) BuildGroupBlocksKernel(const FrameDev* fr
   const uint32_t bh = f.h8 - by0 < kGroupCells ? f.h8 - by0 : kGroupCells;
   uint32_t* out = f.group_blocks + (size_t) g * 1024;
   uint32_t n = 0;
+  if (f.status[(gy / 8) * f.nlfx + gx / 8] != kOk) {  // the LF group's placement is unusable: the group decodes nothing
+    f.group_nblocks[g] = 0;
+    return;
+  }
   for (uint32_t by = 0; by < bh; ++by) {
     const uint8_t* srow = f.cell_strategy + (size_t) (by0 + by) * f.w8 + bx0;
     const uint16_t* qrow = f.cell_hfmul + (size_t) (by0 + by) * f.w8 + bx0;

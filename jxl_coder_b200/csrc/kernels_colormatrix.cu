@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) OrientKernel(const uint8_t* __restrict__ 
 // The channels of the global stream were decoded on the host (they are tiny) and arrive in the const region: one CTA
 // per channel copies them to their place in the squeeze buffer.
 __global__ void __launch_bounds__(256) SqueezeScatterGlobalKernel(const FrameDev f) {
+  if (*f.frame_bad) return;
   const uint32_t c = blockIdx.x;
   if (c >= f.sq_global) return;
   size_t o = 0;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) SqueezeScatterGlobalKernel(const FrameDev
 // just reconstructed) or per column (vertical step, coalesced).  A 4096^2 alpha plane takes ~20 steps of at most
 // 4096 threads each: latency-bound, a few hundred microseconds in total, off the colour path.
 __global__ void __launch_bounds__(128) SqueezeStepKernel(const FrameDev f, uint32_t k) {
+  if (*f.frame_bad) return;
   const SqStep st = f.sq_steps[k];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool final_plane = st.out_off == 0xFFFFFFFFu;

@@ -56,6 +56,7 @@ struct FilterParams {
 
 __global__ void __launch_bounds__(kFilterThreads) FilterColorKernel(const FrameDev f, const FilterParams fp, const NumericTables* nt,
                                                                     int halo) {
+  if (*f.frame_bad) return;
   extern __shared__ __align__(16) float fsm[];
   const int bw = kTW + 2 * halo, bh = kTH + 2 * halo;
   const int stride = bw | 1;  // odd row stride
@@ -160,6 +161,7 @@ __device__ __forceinline__ float4 Lds4(const float* p) { return *reinterpret_cas
 __device__ __forceinline__ float2 Lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 
 __global__ void __launch_bounds__(kFilterThreads, 3) FilterColorFastKernel(const FrameDev f, const FilterParams fp, const NumericTables* nt) {
+  if (*f.frame_bad) return;
   extern __shared__ __align__(16) float fsm[];
   float* in0 = fsm;                  // [3][kSH][kSW] input XYB (rows ty0-3 .., cols tx0-8 ..)
   float* gb = fsm + 3 * kSPlane;     // Gaborish output, same geometry

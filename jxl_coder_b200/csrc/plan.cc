@@ -103,6 +103,7 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
   f.mod_stride = RoundUp(f.width, 32);
   p.num_streams = fh.num_lf_groups + fh.num_groups + 1;
   p.off_status = take(p.num_streams * sizeof(int32_t));
+  p.off_frame_bad = take(sizeof(int32_t));
   if (vardct) {
     p.off_lf_quant = take((size_t) 3 * f.h8 * f.lf_stride * 4);
     p.off_xfromy = take((size_t) f.h64 * f.w64 * 4);
@@ -172,6 +173,7 @@ FrameDev BindFrameDev(const FramePlan& p, const uint8_t* cb, uint8_t* wb) {
   f.order_pool = reinterpret_cast<const uint16_t*>(cb + p.off_order_pool);
   f.blockinfo_off = reinterpret_cast<const uint32_t*>(cb + p.off_blockinfo_off);
   f.status = reinterpret_cast<int32_t*>(wb + p.off_status);
+  f.frame_bad = reinterpret_cast<int32_t*>(wb + p.off_frame_bad);
   if (f.encoding == 0) {
     f.lf_quant = reinterpret_cast<int32_t*>(wb + p.off_lf_quant);
     f.xfromy = reinterpret_cast<int32_t*>(wb + p.off_xfromy);
