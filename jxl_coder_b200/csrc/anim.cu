@@ -77,6 +77,7 @@ jxlb_anim* jxlb_anim_open(const uint8_t* data, size_t len, int32_t color_config,
     a->prefetch = (int) std::min<uint64_t>(32, std::max<uint64_t>(1, (256ull << 20) / std::max<uint64_t>(frame_out, 1)));
   }
   if (const char* e = getenv("JXLB_ANIM_PREFETCH")) a->prefetch = std::max(1, atoi(e));
+  bool saved[4] = {false, false, false, false};  // reference slots written so far (same rule as ParseRequest, decoder.cu)
   for (;;) {
     FrameHeader fh;
     const uint64_t frame_begin_bit = fb;
@@ -94,13 +95,21 @@ jxlb_anim* jxlb_anim_open(const uint8_t* data, size_t len, int32_t color_config,
       a->frames.push_back(fh);
       a->frame_bytes.emplace_back((size_t) (frame_begin_bit / 8), (size_t) fh.end_byte);
       if (!byte_aligned_header || frame_begin_bit % 8 != 0) a->prefetch = 0;  // fall back to whole-file requests
-      // a frame that needs the canvas of earlier frames (crop, blending) is not an independent picture: the whole-file
-      // path below refuses those
-      if (fh.blend.mode != 0 || fh.have_crop || fh.coded_w != a->md.xsize || fh.coded_h != a->md.ysize) a->prefetch = 0;
+      // a frame that needs the canvas of earlier frames is not an independent picture: the whole-file path below refuses
+      // those (a cropped kReplace frame over never-written slots is independent: decoder.cu places it on a cleared canvas)
+      const bool covers = !fh.have_crop && fh.coded_w == a->md.xsize && fh.coded_h == a->md.ysize;
+      bool independent = fh.blend.mode == 0;
+      for (const BlendingInfo& b : fh.ec_blend) independent = independent && b.mode == 0;
+      if (!covers) {
+        independent = independent && !saved[fh.blend.source & 3];
+        for (const BlendingInfo& b : fh.ec_blend) independent = independent && !saved[b.source & 3];
+      }
+      if (!independent) a->prefetch = 0;
     } else {
       a->prefetch = 0;  // invisible (reference-only) frames: displayed frames are not self-contained
     }
     if (fh.is_last) break;
+    if (fh.frame_type == 2 || (fh.frame_type != 1 && (fh.duration == 0 || fh.save_as_reference != 0))) saved[fh.save_as_reference & 3] = true;
     fb = fh.end_byte * 8;
   }
   set(JXLB_OK);

@@ -256,6 +256,12 @@ struct Parsed {
   size_t rs_table_off = 0, rs_table_bytes = 0, rs_work_off = 0, rs_mid_bytes = 0, rs_scaled_bytes = 0;
   uint32_t out_w = 0, out_h = 0;   // size of the picture handed back
   // api_level < 34 colour pass (color_matrix.h): tables live in the const region
+  // a cropped kReplace frame over an empty canvas (animations that store only each frame's bounding box): the frame is
+  // decoded at its own size fw x fh and placed at (place_x0, place_y0) on a cleared canvas of the image size
+  bool placed = false;
+  int32_t place_x0 = 0, place_y0 = 0;
+  uint32_t fw = 0, fh_ = 0;
+  size_t place_off = 0;
   // orientation (applied right after the decode stage): oriented size and the offset of the oriented image (work region)
   uint32_t orient = 1, ow = 0, oh = 0;
   size_t or_off = 0;
@@ -350,6 +356,7 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
   }
   // frames: decode the last one (or displayed frame `target_frame`); earlier frames must not be needed
   int nframes = 0, displayed = 0;
+  bool saved[4] = {false, false, false, false};  // reference slots written by the frames before the target
   for (;;) {
     p->fh = FrameHeader();
     st = ParseFrameHeader(p->cs.data(), p->cs.size(), p->cs_len, md, frame_bit, &p->fh, &err);
@@ -365,16 +372,37 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
       Fail(p, JXLB_BAD_ARG, "frame index out of range");
       return;
     }
+    if (p->fh.frame_type == 2 || (p->fh.frame_type != 1 && (p->fh.duration == 0 || p->fh.save_as_reference != 0)))
+      saved[p->fh.save_as_reference & 3] = true;
     frame_bit = p->fh.end_byte * 8;
   }
   const FrameHeader& fh = p->fh;
-  if (nframes > 1 && (fh.blend.mode != 0 || fh.have_crop)) {
-    Fail(p, JXLB_UNSUPPORTED, "multi-frame image needing composition");
-    return;
+  p->fw = fh.coded_w;
+  p->fh_ = fh.coded_h;
+  const bool covers_canvas = !fh.have_crop && fh.coded_w == md.xsize && fh.coded_h == md.ysize;
+  if (nframes > 1 || !covers_canvas) {
+    // Frames are decoded as independent pictures.  That is what a kReplace frame is when it covers the canvas, or when
+    // the canvas it is laid over is empty (its source slots were never written): then the picture is the frame at its
+    // crop position over cleared pixels.  Anything else needs the earlier frames (composition): refused.
+    bool independent = fh.blend.mode == 0;
+    for (const BlendingInfo& b : fh.ec_blend) independent = independent && b.mode == 0;
+    if (!covers_canvas) {
+      independent = independent && !saved[fh.blend.source & 3];
+      for (const BlendingInfo& b : fh.ec_blend) independent = independent && !saved[b.source & 3];
+    }
+    if (!independent) {
+      Fail(p, JXLB_UNSUPPORTED, "multi-frame image needing composition");
+      return;
+    }
   }
-  if (fh.have_crop || fh.coded_w != md.xsize || fh.coded_h != md.ysize) {
-    Fail(p, JXLB_UNSUPPORTED, "cropped frame");
-    return;
+  if (!covers_canvas) {
+    if (md.orientation != 1 || fh.upsampling != 1) {
+      Fail(p, JXLB_UNSUPPORTED, "cropped frame with orientation or upsampling");
+      return;
+    }
+    p->placed = true;
+    p->place_x0 = fh.have_crop ? fh.x0 : 0;
+    p->place_y0 = fh.have_crop ? fh.y0 : 0;
   }
   st = ParseFrameGlobals(p->cs.data(), p->cs.size(), md, fh, &p->g, &err);
   if (st) {
@@ -591,10 +619,14 @@ struct Batch {
       const_total += Align256(p.plan.const_bytes);
       p.work_off = work_total;
       work_total += Align256(p.plan.work_bytes);
-      p.stage_stride = Align256((size_t) p.md.xsize * 4 * (p.out16 ? 2 : 1));
+      p.stage_stride = Align256((size_t) p.fw * 4 * (p.out16 ? 2 : 1));
       p.stage_off = stage_total;
       // the fused VarDCT kernel packs straight into final_out; only modular frames (and the unfused debug path) stage RGBA
-      if (p.plan.proto.encoding != 0 || UseUnfusedFilters() || p.resize || p.color_matrix || p.orient != 1) stage_total += Align256(p.stage_stride * p.md.ysize);
+      if (p.plan.proto.encoding != 0 || UseUnfusedFilters() || p.resize || p.color_matrix || p.orient != 1 || p.placed) stage_total += Align256(p.stage_stride * p.fh_);
+      if (p.placed) {
+        p.place_off = work_total;
+        work_total += Align256((size_t) p.md.xsize * p.md.ysize * 4 * (p.out16 ? 2 : 1));
+      }
       if (p.orient != 1) {
         p.or_off = work_total;
         work_total += Align256((size_t) p.ow * p.oh * 4 * (p.out16 ? 2 : 1));
@@ -852,8 +884,8 @@ struct Batch {
       PackParams pk;  // ReformatColorConfig
       pk.src = od.data;
       pk.src_stride = od.stride_bytes;
-      pk.width = p.md.xsize;
-      pk.height = p.md.ysize;
+      pk.width = p.fw;
+      pk.height = p.fh_;
       pk.src16 = p.out16;
       pk.depth = p.depth;
       pk.format = (uint32_t) p.format;
@@ -862,7 +894,7 @@ struct Batch {
       pk.dst_stride = pk.width * FormatBytesPerPixel(pk.format);
       pk.dst = buf->final_out.p + final_off[i];
       const PackParams pk_final = pk;
-      const bool post = p.resize || p.color_matrix || p.orient != 1;
+      const bool post = p.resize || p.color_matrix || p.orient != 1 || p.placed;
       if (post) {  // the decode stage hands straight RGBA8 to the rescaler / colour pass; ReformatColorConfig runs on their result
         pk.format = JXLB_FORMAT_RGBA_8888;
         pk.associate = 0;
@@ -894,10 +926,18 @@ struct Batch {
       const uint8_t* res = od.data;
       uint32_t res_stride = od.stride_bytes;
       const ColorMatrixPlan* cm_dev = reinterpret_cast<const ColorMatrixPlan*>(buf->const_buf.p + p.cm_off);
+      if (p.placed) {
+        uint8_t* dst = buf->work_buf.p + p.place_off;
+        const uint32_t bpp = p.out16 ? 8 : 4;
+        LaunchPlace(od.data, od.stride_bytes, p.fw, p.fh_, bpp, p.place_x0, p.place_y0, p.has_alpha ? 0u : (p.out16 ? 0xFFFFu : 0xFFu), dst,
+                    p.md.xsize * bpp, p.md.xsize, p.md.ysize, s);
+        res = dst;
+        res_stride = p.md.xsize * bpp;
+      }
       if (p.orient != 1) {
         uint8_t* dst = buf->work_buf.p + p.or_off;
         const uint32_t bpp = p.out16 ? 8 : 4;
-        LaunchOrient(od.data, od.stride_bytes, p.md.xsize, p.md.ysize, bpp, p.orient, dst, p.ow * bpp, s);
+        LaunchOrient(res, res_stride, p.md.xsize, p.md.ysize, bpp, p.orient, dst, p.ow * bpp, s);
         res = dst;
         res_stride = p.ow * bpp;
       }

@@ -98,6 +98,7 @@ struct FrameDev {
   // geometry of the coded frame
   uint32_t width, height;          // pixels
   uint32_t orientation;            // codestream orientation (1..8): the 8-bit dither pattern is indexed by OUTPUT position
+  uint32_t dither_x0, dither_y0;   // position of a cropped frame on the canvas, mod 32 (the dither pattern is canvas-anchored)
   uint32_t w8, h8;                 // 8x8 cells
   uint32_t w64, h64;               // CfL tiles
   uint32_t ngx, ngy, nlfx, nlfy;

@@ -67,6 +67,10 @@ const uint8_t* LaunchResize(const ResizeDev& r, cudaStream_t stream);
 // steps_host: the host copy of f.sq_steps (launch geometry).
 void LaunchUnsqueeze(const FrameDev& f, const SqStep* steps_host, cudaStream_t stream);
 
+// Lays an fw x fh frame at (x0, y0) over a cleared cw x ch canvas (colour 0, alpha fill_alpha in the sample depth).
+void LaunchPlace(const uint8_t* src, uint32_t src_stride, uint32_t fw, uint32_t fh, uint32_t bpp, int32_t x0, int32_t y0, uint32_t fill_alpha,
+                 uint8_t* dst, uint32_t dst_stride, uint32_t cw, uint32_t ch, cudaStream_t stream);
+
 // Codestream orientation (EXIF numbering 2..8) applied to an interleaved image of bpp (4 or 8) bytes per pixel; src is w x h,
 // dst is w x h (2..4) or h x w (5..8).
 void LaunchOrient(const uint8_t* src, uint32_t src_stride, uint32_t w, uint32_t h, uint32_t bpp, uint32_t orientation, uint8_t* dst,

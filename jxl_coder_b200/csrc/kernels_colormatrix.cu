@@ -95,7 +95,28 @@ __global__ void __launch_bounds__(128) SqueezeStepKernel(const FrameDev f, uint3
   }
 }
 
+// A cropped frame laid over a cleared canvas: thread per canvas pixel.
+template <typename Pixel>
+__global__ void __launch_bounds__(256) PlaceKernel(const uint8_t* __restrict__ src, uint32_t src_stride, uint32_t fw, uint32_t fh, int32_t x0,
+                                                   int32_t y0, Pixel fill, uint8_t* __restrict__ dst, uint32_t dst_stride, uint32_t cw, uint32_t ch) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= cw || y >= ch) return;
+  const int64_t fx = (int64_t) x - x0, fy = (int64_t) y - y0;
+  Pixel v = fill;
+  if (fx >= 0 && fy >= 0 && fx < (int64_t) fw && fy < (int64_t) fh) v = reinterpret_cast<const Pixel*>(src + (size_t) fy * src_stride)[fx];
+  reinterpret_cast<Pixel*>(dst + (size_t) y * dst_stride)[x] = v;
+}
+
 }  // namespace
+
+void LaunchPlace(const uint8_t* src, uint32_t src_stride, uint32_t fw, uint32_t fh, uint32_t bpp, int32_t x0, int32_t y0, uint32_t fill_alpha,
+                 uint8_t* dst, uint32_t dst_stride, uint32_t cw, uint32_t ch, cudaStream_t stream) {
+  if (!cw || !ch) return;
+  dim3 grid((cw + 255) / 256, ch, 1);
+  if (bpp == 8) PlaceKernel<uint2><<<grid, 256, 0, stream>>>(src, src_stride, fw, fh, x0, y0, make_uint2(0u, fill_alpha << 16), dst, dst_stride, cw, ch);
+  else PlaceKernel<uint32_t><<<grid, 256, 0, stream>>>(src, src_stride, fw, fh, x0, y0, fill_alpha << 24, dst, dst_stride, cw, ch);
+  ++g_launches_ac;
+}
 
 void LaunchUnsqueeze(const FrameDev& f, const SqStep* steps_host, cudaStream_t stream) {
   if (!f.sq_nch) return;

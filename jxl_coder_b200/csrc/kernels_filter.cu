@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kFilterThreads, 3) FilterColorFastKernel(const
   uint32_t px[4][4];
   float dith[4] = {0.f, 0.f, 0.f, 0.f};
   if (!fp.out16) {
-    if (f.orientation == 1) {
+    if (f.orientation == 1 && (f.dither_x0 | f.dither_y0) == 0) {
       const float4 d = *reinterpret_cast<const float4*>(nt->dither + (y & 31) * 32 + (x0 & 31));
       dith[0] = d.x; dith[1] = d.y; dith[2] = d.z; dith[3] = d.w;
     } else {

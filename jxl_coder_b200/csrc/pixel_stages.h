@@ -85,7 +85,7 @@ JXLB_HD uint32_t DitherIndex(const FrameDev& f, uint32_t x, uint32_t y) {
   const uint32_t o = f.orientation;
   const bool flip_x = o == 2 || o == 3 || o == 7 || o == 8, flip_y = o == 3 || o == 4 || o == 6 || o == 7;
   const uint32_t ox = flip_x ? f.width - 1 - x : x, oy = flip_y ? f.height - 1 - y : y;
-  return (oy & 31) * 32 + (ox & 31);
+  return ((oy + f.dither_y0) & 31) * 32 + ((ox + f.dither_x0) & 31);
 }
 
 JXLB_HD void StageColorToRgba(const FrameDev& f, const ColorParams& cp, const NumericTables& nt, const float* src,

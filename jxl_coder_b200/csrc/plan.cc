@@ -25,6 +25,8 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
   memset(&f, 0, sizeof f);
   f.width = fh.coded_w;
   f.orientation = md.orientation;
+  f.dither_x0 = fh.have_crop ? (uint32_t) (((fh.x0 % 32) + 32) % 32) : 0u;
+  f.dither_y0 = fh.have_crop ? (uint32_t) (((fh.y0 % 32) + 32) % 32) : 0u;
   f.height = fh.coded_h;
   f.w8 = (f.width + 7) / 8;
   f.h8 = (f.height + 7) / 8;

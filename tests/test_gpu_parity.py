@@ -492,3 +492,26 @@ def test_corrupt_inputs_never_hang(J):
     r = subprocess.run([sys.executable, os.path.join(here, "gpu_fuzz.py"), "7"], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "fuzz ok=" in r.stdout
+
+
+def test_cropped_frames_over_empty_canvas(J, ref):
+    """The reference's animated demo asset: every frame after the first is a cropped kReplace frame whose source slot was
+    never written, i.e. the frame's bounding box over a cleared canvas.  All frames against the reference's coalesced ones."""
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_cache", "assets", "animated_jxl.jxl")
+    if not os.path.exists(p):
+        pytest.skip("asset not cached")
+    data = open(p, "rb").read()
+    ra = ref.Anim(data, cfg=2)
+    a = J.JxlAnimatedImage(data, J.PreferredColorConfig.RGBA_8888)
+    assert a.number_of_frames == len(ra) and (a.get_width(), a.get_height()) == ra.size
+    w, h = ra.size
+    for i in range(len(ra)):
+        want = ra.frame(i)["pixels"][:, : w * 4].reshape(h, w, 4)
+        got = a.get_frame(i).as_array()
+        assert a.get_frame_duration(i) == ra.duration(i)
+        assert (got[..., 3] == want[..., 3]).all(), i
+        d = np.abs(got.astype(int) - want.astype(int))
+        assert d.max() <= 1 and (d == 0).mean() > 0.97, (i, d.max(), (d == 0).mean())
+    a.close()
+    ra.close()
