@@ -171,6 +171,7 @@ struct FrameDev {
   const int32_t* sq_global_data;
   int32_t* sq_buf;
   uint32_t sq_nch, sq_global, sq_nsteps, sq_pad;
+  uint64_t sq_end_bit;             // single-section frames: where the lane resumes after the host-decoded global modular stream
   uint32_t mod_stride;
   int32_t* status;                 // [num_streams] per-stream status (see StreamStatus)
 };

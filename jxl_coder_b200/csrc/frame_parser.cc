@@ -541,7 +541,16 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
     const uint32_t nmod = (fh.encoding == 1 ? (md.color.color_space == 1 ? 1u : 3u) : 0u) + (uint32_t) md.extra.size();
     for (const ExtraChannelInfo& ec : md.extra)
       if (ec.dim_shift != 0) JXLB_FAIL(kParseUnsupported, "subsampled extra channel");
-    if (nmod > 0 && fh.toc_entries > 1) {
+    // Multi-section frames: the header is parsed here.  Single-section frames are walked by one device lane from this
+    // position on -- unless their extra channels are squeezed, which is handled on the host (below), the lane resuming
+    // after the global modular stream (sq_end_bit).
+    bool parse_here = nmod > 0 && fh.toc_entries > 1;
+    if (nmod > 0 && fh.toc_entries == 1 && fh.encoding == 0) {
+      BitReader peek = br;
+      ModularHeader mh;
+      if (ReadModularHeader(peek, &mh) == kOk && mh.has_squeeze) parse_here = true;
+    }
+    if (parse_here) {
       int st = ReadModularHeader(br, &g->global_mh);
       if (st == kErrUnsupported) JXLB_FAIL(kParseUnsupported, "palette transform");
       if (st != kOk || br.Overrun()) JXLB_FAIL(kParseInvalid, "global modular header");
@@ -610,6 +619,7 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
           if (st == kErrUnsupported || st == kErrScratch) JXLB_FAIL(kParseUnsupported, "global modular stream");
           if (st != kOk || br.Overrun()) JXLB_FAIL(kParseInvalid, "global modular stream");
         }
+        g->sq_end_bit = br.Position();
       }
     }
   }

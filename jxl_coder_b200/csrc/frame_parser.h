@@ -122,6 +122,7 @@ struct FrameGlobals {
   bool squeeze = false;
   SqueezeLayoutOut sq;
   uint32_t sq_global = 0;
+  uint64_t sq_end_bit = 0;            // first bit after the global modular stream (single-section frames resume here)
   std::vector<int32_t> sq_global_data;
   // HfGlobal
   bool hf_parsed = false;

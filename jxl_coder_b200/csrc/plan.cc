@@ -88,6 +88,7 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
     f.sq_nch = (uint32_t) g.sq.channels.size();
     f.sq_global = g.sq_global;
     f.sq_nsteps = (uint32_t) g.sq.steps.size();
+    f.sq_end_bit = g.sq_end_bit;
     p.off_sq_ch = take(g.sq.channels.size() * sizeof(SqChannel));
     p.off_sq_steps = take(g.sq.steps.size() * sizeof(SqStep));
     p.off_sq_global = take(g.sq_global_data.size() * sizeof(int32_t));

@@ -528,9 +528,14 @@ JXLB_HD_NOINLINE int DecodeSingleSectionFrame(const FrameDev& f_in, const Natura
                                               uint32_t* perm_scratch, uint32_t max_local_nodes) {
   FrameDev f = f_in;
   BitReader br;
-  br.Init(f.cs, f.cs_bytes, f.global_modular_bit, f.sec_bit_end[0]);
-  int st = DecodeGlobalModular(br, f, s, max_local_nodes);
-  if (st != kOk) return st;
+  int st = kOk;
+  if (f.sq_nch) {  // squeezed extra channels: the host decoded the global modular stream (frame_parser.cc)
+    br.Init(f.cs, f.cs_bytes, f.sq_end_bit, f.sec_bit_end[0]);
+  } else {
+    br.Init(f.cs, f.cs_bytes, f.global_modular_bit, f.sec_bit_end[0]);
+    st = DecodeGlobalModular(br, f, s, max_local_nodes);
+    if (st != kOk) return st;
+  }
   if (f.encoding == 0) {
     st = DecodeLfGroupSection(br, f, 0, s, max_local_nodes);
     if (st != kOk) return st;

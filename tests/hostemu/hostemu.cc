@@ -104,6 +104,7 @@ void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, si
     hf.Init(hf_mem.data(), (uint32_t) hf_mem.size());
     e->status = DecodeSingleSectionFrame(f, nat, s, hf, perm.data(), kMaxNodes);
     if (e->status) e->failed_stream = 0;
+    if (!e->status && f.sq_nch) UnsqueezeAllSerial(f);
   } else {
     for (uint32_t l = 0; l < f.num_lf_groups && !e->status && f.encoding == 0; ++l) {
       BitReader br;

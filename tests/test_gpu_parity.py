@@ -462,7 +462,7 @@ def test_reference_app_assets(J, ref, path):
 
 
 # ---- lossy alpha: squeeze transform ----
-@pytest.mark.parametrize("shape", [(320, 264, 41, 1.0), (257, 300, 42, 2.0), (700, 520, 43, 0.5), (1024, 300, 44, 1.0), (2304, 300, 45, 1.0), (520, 4200, 46, 1.0)])
+@pytest.mark.parametrize("shape", [(120, 90, 40, 1.0), (320, 264, 41, 1.0), (257, 300, 42, 2.0), (700, 520, 43, 0.5), (1024, 300, 44, 1.0), (2304, 300, 45, 1.0), (520, 4200, 46, 1.0)])
 def test_squeezed_alpha_matches_reference(J, ref, shape):
     import test_squeeze_host as T
     w, h, seed, ad = shape
