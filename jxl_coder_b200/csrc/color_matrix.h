@@ -7,7 +7,7 @@
 //   2049-entry sRGB LUT (toGamma, round(v * 255)); alpha untouched.
 // It runs even for plain sRGB images (identity-like matrix: a lossy 2048-level requantisation).
 // The tables and the matrix are built on the host in f32 with the reference's operation order (Eigen's 3x3 cofactor
-// inverse); kernels_colormatrix.cu applies them.  PQ / HLG sources (Rec.2408 tone mapping) and 16-bit sources
+// inverse); kernels_post.cu applies them.  PQ / HLG sources (Rec.2408 tone mapping) and 16-bit sources
 // (applyColorMatrix16Bit) are not restated: MakeColorMatrixPlan returns false and the decoder reports JXLB_UNSUPPORTED.
 #pragma once
 #include <cstdint>

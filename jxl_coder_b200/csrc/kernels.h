@@ -76,7 +76,7 @@ void LaunchPlace(const uint8_t* src, uint32_t src_stride, uint32_t fw, uint32_t 
 void LaunchOrient(const uint8_t* src, uint32_t src_stride, uint32_t w, uint32_t h, uint32_t bpp, uint32_t orientation, uint8_t* dst,
                   uint32_t dst_stride, cudaStream_t stream);
 
-// api_level < 34 colour pass (kernels_colormatrix.cu), in place on straight RGBA8; plan_dev: a ColorMatrixPlan in device memory.
+// api_level < 34 colour pass (kernels_post.cu), in place on straight RGBA8; plan_dev: a ColorMatrixPlan in device memory.
 struct ColorMatrixPlan;
 void LaunchColorMatrix(uint8_t* img, uint32_t stride, uint32_t width, uint32_t height, const ColorMatrixPlan* plan_dev, cudaStream_t stream);
 

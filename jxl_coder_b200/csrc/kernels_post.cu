@@ -1,5 +1,9 @@
-// Inverse squeeze of lossy extra channels, and the post-decode passes on interleaved pixels: codestream orientation and the api_level < 34 colour pass (color_matrix.h): in place on straight RGBA8, one thread per pixel, both LUTs staged in
-// shared memory (1 KB + 2 KB).  HBM-bound: 4 B read + 4 B written per pixel.
+// Kernels around the main decode chain (sm_100a), all simple and HBM- or latency-bound:
+//   * ColorMatrixKernel   -- the api_level < 34 colour pass (color_matrix.h): in place on straight RGBA8, one thread per
+//                            pixel, both LUTs (1 KB + 2 KB) staged in shared memory; 4 B read + 4 B written per pixel;
+//   * OrientKernel        -- codestream orientation 2..8 on the decoded picture;
+//   * PlaceKernel         -- a cropped frame laid over a cleared canvas;
+//   * Squeeze*Kernel      -- inverse squeeze of lossy extra channels (squeeze.h), one launch per step.
 #include <atomic>
 
 #include "color_matrix.h"

@@ -472,7 +472,7 @@ JXLB_HD_NOINLINE int DecodeModularGroup(BitReader& br, const FrameDev& f, uint32
 }
 
 // Undoes the squeeze of a frame's extra channels once every group has been decoded (serial version for the CPU
-// emulation; the device runs one kernel per step, kernels_colormatrix.cu).
+// emulation; the device runs one kernel per step, kernels_post.cu).
 inline void UnsqueezeAllSerial(const FrameDev& f) {
   size_t o = 0;
   for (uint32_t c = 0; c < f.sq_global; ++c) {

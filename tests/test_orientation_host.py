@@ -1,4 +1,4 @@
-"""Pins the orientation mapping used by OrientKernel (csrc/kernels_colormatrix.cu) against the reference: libjxl applies
+"""Pins the orientation mapping used by OrientKernel (csrc/kernels_post.cu) against the reference: libjxl applies
 the codestream orientation to the pixels DecodeJpegXlOneShot receives (interop/JxlDecoding.cpp:36-176 never sets
 keep_orientation).  `orient` below is the same table in numpy."""
 import numpy as np
