@@ -896,7 +896,7 @@ struct Batch {
       const PackParams pk_final = pk;
       const bool post = p.resize || p.color_matrix || p.orient != 1 || p.placed;
       if (post) {  // the decode stage hands straight RGBA8 to the rescaler / colour pass; ReformatColorConfig runs on their result
-        pk.format = JXLB_FORMAT_RGBA_8888;
+        pk.format = 4;  // staging: samples as decoded (RGBA8, or RGBA16 for sources deeper than 8 bits)
         pk.associate = 0;
         pk.dst = od.data;
         pk.dst_stride = od.stride_bytes;

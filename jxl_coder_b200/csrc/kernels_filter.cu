@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(kFilterThreads, 3) FilterColorFastKernel(const
     for (int j = 0; j < 4; ++j)
       if (x0 + j < W) px[j][3] = ScaleSample(arow[x0 + j], fp.alpha_bits, maxout);
   }
-  if (!fp.out16 && fp.pack.format == 0 && !fp.pack.associate && x0 + 3 < W) {
+  if (!fp.out16 && (fp.pack.format == 0 || fp.pack.format == 4) && !fp.pack.associate && x0 + 3 < W) {
     uint4 o;
     o.x = px[0][0] | (px[0][1] << 8) | (px[0][2] << 16) | (px[0][3] << 24);
     o.y = px[1][0] | (px[1][1] << 8) | (px[1][2] << 16) | (px[1][3] << 24);

@@ -25,7 +25,8 @@ struct PackParams {
   uint32_t width, height;
   uint32_t src16;          // source samples are uint16
   uint32_t depth;          // 8 or 16 (bit depth the reference tracks)
-  uint32_t format;         // jxlb_format: 0 8888, 1 F16, 2 565, 3 1010102
+  uint32_t format;         // jxlb_format: 0 8888, 1 F16, 2 565, 3 1010102; 4 (internal): the samples as they are, RGBA8 or
+                           // RGBA16 -- the staging image in front of the orientation / rescale / colour passes
   uint32_t associate;      // step 1: !alphaPremultiplied && hasAlphaInOrigin
   uint32_t attenuate;      // step 2 (8-bit sources only): !alphaPremultiplied
 };
@@ -60,6 +61,19 @@ JXLB_HD uint16_t FloatToHalfBits(float f) {
 
 // Packs one decoded pixel (r, g, b, a at the decode stage's depth: 8-bit, or 16-bit when p.src16) into the output.
 JXLB_HD void PackRgba(const PackParams& p, uint32_t x, uint32_t y, uint32_t r, uint32_t g, uint32_t b, uint32_t a) {
+  if (p.format == 4) {  // staging: no association, no conversion
+    uint8_t* drow = p.dst + (size_t) y * p.dst_stride;
+    if (p.src16) {
+      uint16_t* o = reinterpret_cast<uint16_t*>(drow) + 4 * (size_t) x;
+      o[0] = (uint16_t) r;
+      o[1] = (uint16_t) g;
+      o[2] = (uint16_t) b;
+      o[3] = (uint16_t) a;
+    } else {
+      reinterpret_cast<uint32_t*>(drow)[x] = (r & 0xFFu) | ((g & 0xFFu) << 8) | ((b & 0xFFu) << 16) | ((a & 0xFFu) << 24);
+    }
+    return;
+  }
   if (p.src16) {
     if (p.associate) {
       const uint32_t maxc = (1u << p.depth) - 1;
@@ -139,6 +153,6 @@ JXLB_HD void PackPixel(const PackParams& p, uint32_t x, uint32_t y) {
   }
 }
 
-JXLB_HD uint32_t FormatBytesPerPixel(uint32_t format) { return format == 1 ? 8u : format == 2 ? 2u : 4u; }
+JXLB_HD uint32_t FormatBytesPerPixel(uint32_t format) { return format == 1 ? 8u : format == 2 ? 2u : 4u; }  // not for the staging format
 
 }  // namespace jxlb

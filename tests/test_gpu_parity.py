@@ -515,3 +515,28 @@ def test_cropped_frames_over_empty_canvas(J, ref):
         assert d.max() <= 1 and (d == 0).mean() > 0.97, (i, d.max(), (d == 0).mean())
     a.close()
     ra.close()
+
+
+@pytest.mark.parametrize("o", [3, 6, 7])
+@pytest.mark.parametrize("cfg", [1, 2, 3])
+def test_orientation_on_16bit_lossy(J, ref, o, cfg):
+    """Sources deeper than 8 bits are staged as RGBA16 in front of the orientation pass (found by tests/gpu_sweep.py)."""
+    from oracle import synth
+    w, h = 218, 155
+    img = synth.synth_image(w, h, 8).astype(np.uint16) * 257
+    data = cases._cached("orient%d_lossy16" % o, lambda: ref.encode_ex(img, w, h, 3, bits=16, distance=1.0, orientation=o))
+    r = ref.decode_sampled(data, cfg=cfg)
+    got = J.JxlCoder.decode(data, cfg)
+    assert (got.width, got.height) == (r["width"], r["height"])
+    if cfg == 2:
+        golden_lib.lossy_close(got.as_array(), r["pixels"][:, : got.width * 4].reshape(got.height, got.width, 4), "16-bit orientation %d" % o)
+    elif cfg == 3:
+        a = np.ascontiguousarray(got.pixels[:, : got.width * 8]).view(np.float16).astype(np.float32)
+        b = np.ascontiguousarray(r["pixels"][:, : got.width * 8]).view(np.float16).astype(np.float32)
+        assert np.abs(a - b).max() <= 1.0 / 255
+    else:  # DEFAULT -> RGBA_1010102 (depth > 8, no alpha, api >= 33)
+        assert got.config == "RGBA_1010102"
+        a = np.ascontiguousarray(got.pixels[:, : got.width * 4]).view(np.uint32)
+        b = np.ascontiguousarray(r["pixels"][:, : got.width * 4]).view(np.uint32)
+        for sh in (0, 10, 20):
+            assert np.abs(((a >> sh) & 0x3FF).astype(int) - ((b >> sh) & 0x3FF).astype(int)).max() <= 4
