@@ -422,6 +422,11 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
   } else if (md.xyb_encoded) {
     Fail(p, JXLB_UNSUPPORTED, "XYB-encoded modular frame");
     return;
+  } else if (fh.rf.gab || fh.rf.epf_iters) {
+    // libjxl runs Gaborish / EPF on modular frames too when the frame header asks for them (its encoder never does for
+    // lossless); the modular path here has no filter stage
+    Fail(p, JXLB_UNSUPPORTED, "restoration filters on a modular frame");
+    return;
   }
   for (const ExtraChannelInfo& ec : md.extra)
     if (ec.bits > 16 || ec.is_float) {
