@@ -916,7 +916,7 @@ struct Batch {
         if (!UseUnfusedFilters()) {
           LaunchFilterColorPack(f, p.cp, ctx->nt_dev, od, pk, s);
         } else {
-          int cur = LaunchFilters(f, s);
+          int cur = LaunchFilters(f, ctx->nt_dev, s);
           LaunchColor(f, p.cp, ctx->nt_dev, cur ? f.xyb1 : f.xyb0, od, s);
           LaunchPack(pk, s);
         }

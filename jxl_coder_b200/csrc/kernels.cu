@@ -270,11 +270,11 @@ __global__ void __launch_bounds__(256) GaborishKernel(const FrameDev f, const fl
   StageGaborish(f, src, dst, x, y);
 }
 
-__global__ void __launch_bounds__(256) EpfKernel(const FrameDev f, int stage, const float* src, float* dst) {
+__global__ void __launch_bounds__(256) EpfKernel(const FrameDev f, const NumericTables* nt, int stage, const float* src, float* dst) {
   if (*f.frame_bad) return;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= (int) f.width || y >= (int) f.height) return;
-  StageEpf(f, stage, src, dst, x, y);
+  StageEpf(f, *nt, stage, src, dst, x, y);
 }
 
 __global__ void __launch_bounds__(256) ColorKernel(const FrameDev f, const ColorParams cp, const NumericTables* nt, const float* src,
@@ -386,7 +386,7 @@ void LaunchRecon(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t st
   g_launches += 2;
 }
 
-int LaunchFilters(const FrameDev& f, cudaStream_t stream) {
+int LaunchFilters(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t stream) {
   float* buf[2] = {f.xyb0, f.xyb1};
   int cur = 0;
   const dim3 grid = PixelGrid(f.width, f.height, 256);
@@ -399,7 +399,7 @@ int LaunchFilters(const FrameDev& f, cudaStream_t stream) {
   for (int stage = 0; stage < 3; ++stage) {
     const bool run = (stage == 0 && iters == 3) || (stage == 1 && iters >= 1) || (stage == 2 && iters >= 2);
     if (!run) continue;
-    EpfKernel<<<grid, 256, 0, stream>>>(f, stage, buf[cur], buf[cur ^ 1]);
+    EpfKernel<<<grid, 256, 0, stream>>>(f, nt_dev, stage, buf[cur], buf[cur ^ 1]);
     cur ^= 1;
     ++g_launches;
   }

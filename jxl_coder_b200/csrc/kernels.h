@@ -92,7 +92,7 @@ void LaunchGroupModular(const FrameDev* frames, const StreamJob* jobs, uint32_t 
 void LaunchLfFinal(const FrameDev& f, cudaStream_t stream);
 void LaunchRecon(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t stream);
 // Gaborish + EPF stages as configured; returns which buffer (0 = xyb0, 1 = xyb1) holds the result.
-int LaunchFilters(const FrameDev& f, cudaStream_t stream);
+int LaunchFilters(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t stream);
 void LaunchColor(const FrameDev& f, const ColorParams& cp, const NumericTables* nt_dev, const float* src, OutputDesc out,
                  cudaStream_t stream);
 void LaunchModularToRgba(const FrameDev& f, OutputDesc out, cudaStream_t stream);

@@ -33,13 +33,14 @@ struct EpfTileArgs {
 };
 
 template <int kStage>
-__device__ __forceinline__ void RunEpfStage(const SmemTile& in, float* out, const RestorationFilter& rf, const EpfTileArgs& a, int tid) {
+__device__ __forceinline__ void RunEpfStage(const SmemTile& in, float* out, const RestorationFilter& rf, const uint32_t* rcp11,
+                                            const EpfTileArgs& a, int tid) {
   for (int i = tid; i < a.rw * a.rh; i += kFilterThreads) {
     const int lx = a.off + i % a.rw, ly = a.off + i / a.rw;
     const int mx = Mirror(a.gx0 + lx, a.W), my = Mirror(a.gy0 + ly, a.H);
     const float inv_sigma = a.sig[((my >> 3) - a.cy_lo) * a.ncx + (mx >> 3) - a.cx_lo];
     float o[3];
-    EpfPixelT<kStage>(in, rf, lx, ly, mx, my, inv_sigma, o);
+    EpfPixelT<kStage>(in, rf, rcp11, lx, ly, mx, my, inv_sigma, o);
     out[ly * a.stride + lx] = o[0];
     out[a.plane + ly * a.stride + lx] = o[1];
     out[2 * a.plane + ly * a.stride + lx] = o[2];
@@ -112,9 +113,9 @@ __global__ void __launch_bounds__(kFilterThreads) FilterColorKernel(const FrameD
       }
     } else {
       const EpfTileArgs ea{tx0 - halo, ty0 - halo, W, H, off, rw, rh, stride, plane, cx_lo, cy_lo, ncx, sig};
-      if (stage == 0) RunEpfStage<0>(in, out, f.rf, ea, tid);
-      else if (stage == 1) RunEpfStage<1>(in, out, f.rf, ea, tid);
-      else RunEpfStage<2>(in, out, f.rf, ea, tid);
+      if (stage == 0) RunEpfStage<0>(in, out, f.rf, nt->rcp11, ea, tid);
+      else if (stage == 1) RunEpfStage<1>(in, out, f.rf, nt->rcp11, ea, tid);
+      else RunEpfStage<2>(in, out, f.rf, nt->rcp11, ea, tid);
     }
     cur ^= 1;
     __syncthreads();
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(kFilterThreads, 3) FilterColorFastKernel(const
         wsum += w;
         wgt[j][i] = w;
       }
-      inv[j] = 1.0f / wsum;
+      inv[j] = ApproxRcp(nt->rcp11, wsum);  // libjxl's ApproximateReciprocal (JXL_HIGH_PRECISION=0)
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {

@@ -286,7 +286,22 @@ struct NumericTables {
   const float* llf[6];
   alignas(16) float dither[1024];                                // 32 x 32 (App. B.7)
   float afv_basis[256];
+  // The reference's libjxl is built with JXL_HIGH_PRECISION=0 (build_jxl.sh:36-37): its EPF normalises with
+  // ApproximateReciprocal, i.e. x86 RCPPS -- an 11-bit table lookup on the mantissa whose values are the CPU vendor's.
+  // rcp11[i] = bit pattern of rcpps(1 + i / 2048), filled from the host CPU's own instruction (numeric_tables.cc), so the
+  // pictures match what the reference produces on the same machine.
+  uint32_t rcp11[2048];
 };
+
+// rcpps(w) for a positive normal w, from the table above: the result depends on the top 11 mantissa bits only and scales
+// exactly with the exponent.
+JXLB_HD float ApproxRcp(const uint32_t* rcp11, float w) {
+  union { float f; uint32_t u; } v;
+  v.f = w;
+  const uint32_t e = (v.u >> 23) & 0xFFu;
+  v.u = rcp11[(v.u >> 12) & 0x7FFu] - ((e - 127u) << 23);
+  return v.f;
+}
 
 JXLB_HD int Mirror(int i, int n) {
   // symmetric extension without repeating the edge sample twice: -1 -> 0, -2 -> 1, n -> n-1
@@ -327,7 +342,8 @@ JXLB_HD float EpfInvSigma(const FrameDev& f, uint32_t hf_mul, uint32_t sharp) {
 // loops unroll completely and every tap becomes a fixed-offset load.
 // (px, py) = image coordinates deciding the 8x8-border weighting; (x, y) = coordinates inside `im`.
 template <int kStage, class Img>
-JXLB_HD void EpfPixelT(const Img& im, const RestorationFilter& rf, int x, int y, int px, int py, float inv_sigma, float out[3]) {
+JXLB_HD void EpfPixelT(const Img& im, const RestorationFilter& rf, const uint32_t* rcp11, int x, int y, int px, int py, float inv_sigma,
+                       float out[3]) {
   const float c0 = im.at(0, x, y), c1 = im.at(1, x, y), c2 = im.at(2, x, y);
   if (inv_sigma < kEpfSkipThreshold) {
     out[0] = c0;
@@ -387,17 +403,18 @@ JXLB_HD void EpfPixelT(const Img& im, const RestorationFilter& rf, int x, int y,
     a1 += w * nv[1];
     a2 += w * nv[2];
   }
-  const float inv = 1.0f / wsum;
+  const float inv = ApproxRcp(rcp11, wsum);  // libjxl's ApproximateReciprocal (JXL_HIGH_PRECISION=0)
   out[0] = a0 * inv;
   out[1] = a1 * inv;
   out[2] = a2 * inv;
 }
 
 template <class Img>
-JXLB_HD void EpfPixel(const Img& im, const RestorationFilter& rf, int stage, int x, int y, int px, int py, float inv_sigma, float out[3]) {
-  if (stage == 0) EpfPixelT<0>(im, rf, x, y, px, py, inv_sigma, out);
-  else if (stage == 1) EpfPixelT<1>(im, rf, x, y, px, py, inv_sigma, out);
-  else EpfPixelT<2>(im, rf, x, y, px, py, inv_sigma, out);
+JXLB_HD void EpfPixel(const Img& im, const RestorationFilter& rf, const uint32_t* rcp11, int stage, int x, int y, int px, int py,
+                      float inv_sigma, float out[3]) {
+  if (stage == 0) EpfPixelT<0>(im, rf, rcp11, x, y, px, py, inv_sigma, out);
+  else if (stage == 1) EpfPixelT<1>(im, rf, rcp11, x, y, px, py, inv_sigma, out);
+  else EpfPixelT<2>(im, rf, rcp11, x, y, px, py, inv_sigma, out);
 }
 
 // ---- colour ------------------------------------------------------------------------------------------------------------

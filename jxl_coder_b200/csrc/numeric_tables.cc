@@ -5,6 +5,33 @@
 #include <cmath>
 #include <mutex>
 
+#if defined(__x86_64__) || defined(__i386__)
+#include <xmmintrin.h>
+#endif
+
+namespace jxlb {
+namespace {
+// rcp11[i] = rcpps(1 + i / 2048) as the HOST CPU computes it (numeric.h: NumericTables::rcp11).  Checked: on this
+// machine RCPPS depends on the top 11 mantissa bits only and scales exactly with the exponent
+// (tests/test_numeric_host.py::test_rcp_table_reproduces_rcpps).
+void FillRcp11(uint32_t* out) {
+  for (uint32_t i = 0; i < 2048; ++i) {
+    union { float f; uint32_t u; } v, r;
+    v.u = 0x3F800000u | (i << 12);
+#if defined(__x86_64__) || defined(__i386__)
+    alignas(16) float in4[4] = {v.f, v.f, v.f, v.f}, out4[4];
+    _mm_store_ps(out4, _mm_rcp_ps(_mm_load_ps(in4)));
+    r.f = out4[0];
+#else
+    r.f = 1.0f / v.f;
+#endif
+    out[i] = r.u;
+  }
+}
+}  // namespace
+}  // namespace jxlb
+
+
 namespace jxlb {
 
 namespace {
@@ -228,6 +255,7 @@ const HostNumericTables& GetHostNumericTables() {
     t.tables.dequant = t.dequant_pool.data();
     for (int l = 0; l < 6; ++l) t.tables.llf[l] = t.llf_pool.data() + t.llf_off[l];
     for (int i = 0; i < 1024; ++i) t.tables.dither[i] = kDither[i];
+    FillRcp11(t.tables.rcp11);
     for (int i = 0; i < 256; ++i) t.tables.afv_basis[i] = kAfvBasis[i];
   });
   return t;

@@ -34,13 +34,13 @@ JXLB_HD void StageGaborish(const FrameDev& f, const float* src, float* dst, int 
   for (int c = 0; c < 3; ++c) dst[c * plane + o] = GaborishSample(im, c, x, y, f.rf.gab_w1[c], f.rf.gab_w2[c]);
 }
 
-JXLB_HD void StageEpf(const FrameDev& f, int stage, const float* src, float* dst, int x, int y) {
+JXLB_HD void StageEpf(const FrameDev& f, const NumericTables& nt, int stage, const float* src, float* dst, int x, int y) {
   const Planes3 im = ViewPlanes(f, src);
   const size_t plane = (size_t) f.plane_h * f.plane_stride, o = (size_t) y * f.plane_stride + x;
   const size_t ci = (size_t) (y >> 3) * f.w8 + (x >> 3);
   const float inv_sigma = EpfInvSigma(f, f.cell_hfmul[ci], f.cell_sharp[ci]);
   float out[3];
-  EpfPixel(im, f.rf, stage, x, y, x, y, inv_sigma, out);
+  EpfPixel(im, f.rf, nt.rcp11, stage, x, y, x, y, inv_sigma, out);
   dst[o] = out[0];
   dst[plane + o] = out[1];
   dst[2 * plane + o] = out[2];

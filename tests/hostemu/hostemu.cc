@@ -7,6 +7,9 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#if defined(__x86_64__) || defined(__i386__)
+#include <xmmintrin.h>
+#endif
 #include "../../jxl_coder_b200/csrc/resize.h"
 #include "../../jxl_coder_b200/csrc/color_matrix.h"
 
@@ -202,9 +205,9 @@ int emu_render(void* h, uint8_t* out, uint32_t stride_bytes, int bits16, float* 
       dst = t;
     };
     if (f.rf.gab) run([&](int x, int y) { StageGaborish(f, src, dst, x, y); });
-    if (f.rf.epf_iters == 3) run([&](int x, int y) { StageEpf(f, 0, src, dst, x, y); });
-    if (f.rf.epf_iters >= 1) run([&](int x, int y) { StageEpf(f, 1, src, dst, x, y); });
-    if (f.rf.epf_iters >= 2) run([&](int x, int y) { StageEpf(f, 2, src, dst, x, y); });
+    if (f.rf.epf_iters == 3) run([&](int x, int y) { StageEpf(f, nt, 0, src, dst, x, y); });
+    if (f.rf.epf_iters >= 1) run([&](int x, int y) { StageEpf(f, nt, 1, src, dst, x, y); });
+    if (f.rf.epf_iters >= 2) run([&](int x, int y) { StageEpf(f, nt, 2, src, dst, x, y); });
     if (xyb_final) memcpy(xyb_final, src, 3 * plane * sizeof(float));
     for (uint32_t y = 0; y < f.height; ++y)
       for (uint32_t x = 0; x < f.width; ++x) StageColorToRgba(f, cp, nt, src, od, (int) x, (int) y);
@@ -265,6 +268,29 @@ int emu_color_matrix(const uint8_t* jxl, size_t len, uint8_t* rgba, uint32_t w, 
   if (!needed) return 1;
   ApplyColorMatrixHost(plan, rgba, w * 4, w, h);
   return 0;
+}
+
+
+// ApproxRcp (numeric.h) against the host's RCPPS on n pseudo-random positive normal floats in [2^-20, 2^20): returns the
+// number of inputs whose results differ.
+long emu_rcp_check(long n) {
+#if defined(__x86_64__) || defined(__i386__)
+  const NumericTables& nt = GetHostNumericTables().tables;
+  long bad = 0;
+  uint32_t s = 12345u;
+  for (long i = 0; i < n; ++i) {
+    s = s * 1664525u + 1013904223u;
+    union { float f; uint32_t u; } v;
+    v.u = ((107u + (s >> 27) + ((s >> 7) & 7u)) << 23) | (s & 0x7FFFFFu);
+    alignas(16) float in4[4] = {v.f, v.f, v.f, v.f}, out4[4];
+    _mm_store_ps(out4, _mm_rcp_ps(_mm_load_ps(in4)));
+    if (out4[0] != ApproxRcp(nt.rcp11, v.f)) ++bad;
+  }
+  return bad;
+#else
+  (void) n;
+  return 0;
+#endif
 }
 
 }  // extern "C"

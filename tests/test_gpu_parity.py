@@ -540,3 +540,16 @@ def test_orientation_on_16bit_lossy(J, ref, o, cfg):
         b = np.ascontiguousarray(r["pixels"][:, : got.width * 4]).view(np.uint32)
         for sh in (0, 10, 20):
             assert np.abs(((a >> sh) & 0x3FF).astype(int) - ((b >> sh) & 0x3FF).astype(int)).max() <= 4
+
+
+@pytest.mark.parametrize("epf", [1, 2, 3])
+def test_epf_active_everywhere(J, ref, epf):
+    """Effort-2 encodes filter every cell (sharpness 4): pins the EPF normalisation (libjxl's approximate reciprocal)."""
+    from oracle import synth
+    w, h = 311, 231
+    img = synth.synth_image(w, h, 3)
+    data = cases._cached("epf%d_effort2_311x231" % epf, lambda: ref.encode_ex(img, w, h, 3, distance=1.0, options={"EFFORT": 2, "EPF": epf, "GABORISH": 1}))
+    want = ref.decode_sampled(data, cfg=2)["pixels"][:, : w * 4].reshape(h, w, 4)
+    got = J.JxlCoder.decode(data, 2).as_array()
+    d = np.abs(got[..., :3].astype(int) - want[..., :3].astype(int))
+    assert d.max() <= 1 and (d == 0).mean() > 0.985, (d.max(), (d == 0).mean())

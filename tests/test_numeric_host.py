@@ -33,3 +33,30 @@ def test_pipeline_matches_reference(name, ref):
     else:
         golden_lib.lossy_close(out, raw, name)
     e.close()
+
+
+def test_rcp_table_reproduces_rcpps():
+    """The EPF normalisation uses libjxl's ApproximateReciprocal (the reference is a JXL_HIGH_PRECISION=0 build), i.e. x86
+    RCPPS; the 2048-entry table built from the host CPU must reproduce the instruction for every input."""
+    import hostemu_lib as H
+    assert H.lib().emu_rcp_check(2_000_000) == 0
+
+
+def test_epf_matches_reference_where_it_is_active(ref):
+    """Effort-2 encodes give every 8x8 cell sharpness 4, so the edge-preserving filter acts on the whole picture (default
+    settings leave most cells at sharpness 0 = unfiltered).  Before the approximate reciprocal was restated this case was
+    only 89-95 % exact."""
+    import cases
+    import golden_lib
+    import hostemu_lib as H
+    from oracle import synth
+    w, h = 311, 231
+    img = synth.synth_image(w, h, 3)
+    for epf in (1, 2, 3):
+        data = cases._cached("epf%d_effort2_311x231" % epf, lambda: ref.encode_ex(img, w, h, 3, distance=1.0, options={"EFFORT": 2, "EPF": epf, "GABORISH": 1}))
+        want = ref.decode_sampled(data, cfg=2)["pixels"][:, : w * 4].reshape(h, w, 4)
+        e = H.Decoded(data)
+        emu = e.render()
+        e.close()
+        d = np.abs(emu[..., :3].astype(int) - want[..., :3].astype(int))
+        assert d.max() <= 1 and (d == 0).mean() > 0.985, (epf, d.max(), (d == 0).mean())
