@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <deque>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <cstring>
 #include <string>
@@ -48,8 +49,35 @@ struct jxlb_anim {
 
 extern "C" {
 
+static jxlb_anim* AnimOpen(const uint8_t* data, size_t len, int32_t color_config, int32_t scale_mode, int32_t filter,
+                           int32_t api_level, int32_t* status);
+static int AnimGetFrame(jxlb_anim* a, int32_t frame, int32_t width, int32_t height, jxlb_image* out);
+
+// nothing may unwind across the C boundary: allocation failures become JXLB_OOM (the reference's "not enough memory")
 jxlb_anim* jxlb_anim_open(const uint8_t* data, size_t len, int32_t color_config, int32_t scale_mode, int32_t filter,
                           int32_t api_level, int32_t* status) {
+  try {
+    return AnimOpen(data, len, color_config, scale_mode, filter, api_level, status);
+  } catch (...) {
+    if (status) *status = JXLB_OOM;
+    return nullptr;
+  }
+}
+int jxlb_anim_get_frame(jxlb_anim* a, int32_t frame, int32_t width, int32_t height, jxlb_image* out) {
+  try {
+    return AnimGetFrame(a, frame, width, height, out);
+  } catch (...) {
+    if (out) {
+      memset(out, 0, sizeof *out);
+      out->device = -1;
+      snprintf(out->message, sizeof out->message, "Not enough memory to decode this image");
+    }
+    return JXLB_OOM;
+  }
+}
+
+static jxlb_anim* AnimOpen(const uint8_t* data, size_t len, int32_t color_config, int32_t scale_mode, int32_t filter,
+                           int32_t api_level, int32_t* status) {
   auto set = [&](int s) {
     if (status) *status = s;
   };
@@ -57,7 +85,8 @@ jxlb_anim* jxlb_anim_open(const uint8_t* data, size_t len, int32_t color_config,
     set(JXLB_BAD_ARG);
     return nullptr;
   }
-  jxlb_anim* a = new jxlb_anim();
+  std::unique_ptr<jxlb_anim> holder(new jxlb_anim());
+  jxlb_anim* a = holder.get();
   a->cfg = color_config;
   a->scale_mode = scale_mode;
   a->filter = filter;
@@ -66,7 +95,6 @@ jxlb_anim* jxlb_anim_open(const uint8_t* data, size_t len, int32_t color_config,
   uint64_t fb = 0;
   if (!data || ExtractCodestream(data, len, &a->cs, &a->cs_len) ||
       ParseImageHeader(a->cs.data(), a->cs.size(), a->cs_len, &a->md, &fb, &err)) {
-    delete a;
     set(JXLB_INVALID_JXL);
     return nullptr;
   }
@@ -82,7 +110,6 @@ jxlb_anim* jxlb_anim_open(const uint8_t* data, size_t len, int32_t color_config,
     FrameHeader fh;
     const uint64_t frame_begin_bit = fb;
     if (ParseFrameHeader(a->cs.data(), a->cs.size(), a->cs_len, a->md, fb, &fh, &err)) {
-      delete a;
       set(JXLB_INVALID_JXL);
       return nullptr;
     }
@@ -113,7 +140,7 @@ jxlb_anim* jxlb_anim_open(const uint8_t* data, size_t len, int32_t color_config,
     fb = fh.end_byte * 8;
   }
   set(JXLB_OK);
-  return a;
+  return holder.release();
 }
 
 int32_t jxlb_anim_num_frames(const jxlb_anim* a) { return a ? (int32_t) a->frames.size() : 0; }
@@ -124,7 +151,7 @@ int32_t jxlb_anim_frame_duration_ms(const jxlb_anim* a, int32_t frame) {
 int32_t jxlb_anim_loops(const jxlb_anim* a) { return a ? (int32_t) a->md.num_loops : 0; }
 int32_t jxlb_anim_width(const jxlb_anim* a) { return a ? (int32_t) (a->md.orientation >= 5 ? a->md.ysize : a->md.xsize) : 0; }
 int32_t jxlb_anim_height(const jxlb_anim* a) { return a ? (int32_t) (a->md.orientation >= 5 ? a->md.xsize : a->md.ysize) : 0; }
-int jxlb_anim_get_frame(jxlb_anim* a, int32_t frame, int32_t width, int32_t height, jxlb_image* out) {
+static int AnimGetFrame(jxlb_anim* a, int32_t frame, int32_t width, int32_t height, jxlb_image* out) {
   if (!out) return JXLB_BAD_ARG;
   memset(out, 0, sizeof *out);
   out->device = -1;
@@ -144,6 +171,11 @@ int jxlb_anim_get_frame(jxlb_anim* a, int32_t frame, int32_t width, int32_t heig
     if (it != a->cache.end()) {
       d = it->second;  // ownership moves to the caller
       a->cache.erase(it);
+      for (auto ko = a->cache_order.begin(); ko != a->cache_order.end(); ++ko)  // no stale keys: eviction stays oldest-first
+        if (!(*ko < key) && !(key < *ko)) {
+          a->cache_order.erase(ko);
+          break;
+        }
     } else if (a->prefetch <= 0) {
       jxlb_request r{a->cs.data(), a->cs_len, rw, rh, a->cfg, a->scale_mode, a->filter};
       std::vector<DecodedImage> res;

@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -30,24 +31,44 @@ void FillImage(const DecodedImage& d, jxlb_image* out) {
 }
 }  // namespace
 
+namespace {
+int FailAll(jxlb_image* outs, int32_t* status, size_t n, int code, const char* msg) {
+  for (size_t i = 0; i < n; ++i) {
+    memset(&outs[i], 0, sizeof outs[i]);
+    outs[i].device = -1;
+    snprintf(outs[i].message, sizeof outs[i].message, "%s", msg);
+    if (status) status[i] = code;
+  }
+  return code;
+}
+}  // namespace
+
 extern "C" {
 
 int jxlb_decode_batch(const jxlb_request* reqs, size_t n, jxlb_image* outs, int32_t* status, const jxlb_batch_opts* opts) {
   if (!reqs || !outs) return JXLB_BAD_ARG;
   jxlb_batch_opts o{0, -1, -1, 0};
   if (opts) o = *opts;
-  std::vector<DecodedImage> res;
-  BatchTimings tm;
-  int rc = DecodeBatch(reqs, n, o.api_level, o.device, o.output_device, &res, &tm);
-  {
-    std::lock_guard<std::mutex> l(g_tm_mu);
-    g_last_timings = tm;
+  // nothing may unwind across the C boundary (the JNI entry points catch std::bad_alloc / std::runtime_error and throw
+  // Java exceptions instead, JniDecoding.cpp:81-93)
+  try {
+    std::vector<DecodedImage> res;
+    BatchTimings tm;
+    int rc = DecodeBatch(reqs, n, o.api_level, o.device, o.output_device, &res, &tm);
+    {
+      std::lock_guard<std::mutex> l(g_tm_mu);
+      g_last_timings = tm;
+    }
+    for (size_t i = 0; i < n; ++i) {
+      FillImage(res[i], &outs[i]);
+      if (status) status[i] = res[i].status;
+    }
+    return rc;
+  } catch (const std::bad_alloc&) {
+    return FailAll(outs, status, n, JXLB_OOM, "Not enough memory to decode this image");
+  } catch (...) {
+    return FailAll(outs, status, n, JXLB_ERROR, "Error while decoding");
   }
-  for (size_t i = 0; i < n; ++i) {
-    FillImage(res[i], &outs[i]);
-    if (status) status[i] = res[i].status;
-  }
-  return rc;
 }
 
 int jxlb_decode_sampled(const uint8_t* data, size_t len, int32_t width, int32_t height, int32_t color_config, int32_t scale_mode,
@@ -60,7 +81,7 @@ int jxlb_decode_sampled(const uint8_t* data, size_t len, int32_t width, int32_t 
   return st;
 }
 
-int jxlb_get_size(const uint8_t* data, size_t len, uint32_t* width, uint32_t* height) {
+int jxlb_get_size(const uint8_t* data, size_t len, uint32_t* width, uint32_t* height) try {
   // DecodeBasicInfo (interop/JxlDecoding.cpp:178-226): header-only, CPU.
   if (!data || !width || !height) return JXLB_BAD_ARG;
   std::vector<uint8_t> cs;
@@ -83,6 +104,8 @@ int jxlb_get_size(const uint8_t* data, size_t len, uint32_t* width, uint32_t* he
     *height = md.xsize;
   }
   return JXLB_OK;
+} catch (...) {
+  return JXLB_OOM;
 }
 
 void jxlb_image_free(jxlb_image* img) {
@@ -100,12 +123,18 @@ jxlb_batch* jxlb_batch_prepare(const jxlb_request* reqs, size_t n, const jxlb_ba
   if (!reqs || !n) return nullptr;
   jxlb_batch_opts o{0, -1, -1, 0};
   if (opts) o = *opts;
-  std::vector<int> st;
-  jxlb::Batch* b = PrepareBatch(reqs, n, o.api_level, o.device, &st);
-  if (status)
-    for (size_t i = 0; i < n; ++i) status[i] = st[i];
-  jxlb_batch* h = new jxlb_batch{b};
-  return h;
+  try {
+    std::vector<int> st;
+    jxlb::Batch* b = PrepareBatch(reqs, n, o.api_level, o.device, &st);
+    if (status)
+      for (size_t i = 0; i < n; ++i) status[i] = st[i];
+    jxlb_batch* h = new jxlb_batch{b};
+    return h;
+  } catch (...) {
+    if (status)
+      for (size_t i = 0; i < n; ++i) status[i] = JXLB_OOM;
+    return nullptr;
+  }
 }
 int jxlb_batch_run(jxlb_batch* b) { return b ? RunBatch(b->b, true) : JXLB_BAD_ARG; }
 int jxlb_batch_run_async(jxlb_batch* b) { return b ? RunBatch(b->b, false) : JXLB_BAD_ARG; }

@@ -18,6 +18,8 @@
 #include <memory>
 #include <atomic>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <thread>
 
 #include "color_matrix.h"
@@ -68,6 +70,7 @@ void ParallelFor(size_t n, Fn fn) {
   work();
   for (auto& t : ths) t.join();
 }
+constexpr size_t kMaxImageDeviceBytes = (size_t) 48 << 30;  // device planes of ONE image (a B200 has 180 GB)
 constexpr uint32_t kMaxAcSmemCode = 208u << 10;  // AC code blobs up to this size are staged in shared memory
 
 struct DevBuffer {
@@ -613,13 +616,31 @@ struct Batch {
     n = count;
     api_level = api <= 0 ? 34 : api;
     ps.assign(n, Parsed());
-    ParallelFor(n, [&](size_t i) { ParseRequest(reqs[i], api_level, &ps[i], frame_index ? frame_index[i] : -1); });
+    // One image's failure stays its own: an allocation failure while parsing (std::bad_alloc is what the reference maps to
+    // its "not enough memory" exception, JniDecoding.cpp:81-93) must neither unwind out of a worker thread
+    // (std::terminate) nor take the other images of the batch with it.
+    ParallelFor(n, [&](size_t i) {
+      try {
+        ParseRequest(reqs[i], api_level, &ps[i], frame_index ? frame_index[i] : -1);
+      } catch (const std::bad_alloc&) {
+        ps[i] = Parsed();
+        Fail(&ps[i], JXLB_OOM, "Not enough memory to decode this image");
+      } catch (const std::exception& e) {
+        ps[i] = Parsed();
+        Fail(&ps[i], JXLB_ERROR, std::string("Error while decoding: ") + e.what());
+      }
+    });
     frame_of.assign(n, 0);
     final_off.assign(n, 0);
     final_bytes.assign(n, 0);
     for (size_t i = 0; i < n; ++i) {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
+      // an image whose planes alone could not be allocated fails by itself instead of failing the batch's allocation
+      if (p.plan.work_bytes + p.plan.const_bytes + 3 * p.plan.xyb_bytes > kMaxImageDeviceBytes) {
+        Fail(&p, JXLB_OOM, "Not enough memory to decode this image");
+        continue;
+      }
       p.const_off = const_total;
       const_total += Align256(p.plan.const_bytes);
       p.work_off = work_total;
@@ -1248,6 +1269,12 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
     for (auto& p : b.ps)
       if (p.status == JXLB_OK) Fail(&p, JXLB_ERROR_NO_DEVICE, e.msg);
     cudaGetLastError();
+  } catch (const std::bad_alloc&) {
+    for (auto& p : b.ps)
+      if (p.status == JXLB_OK) Fail(&p, JXLB_OOM, "Not enough memory to decode this image");
+  } catch (const std::exception& e) {
+    for (auto& p : b.ps)
+      if (p.status == JXLB_OK) Fail(&p, JXLB_ERROR, std::string("Error while decoding: ") + e.what());
   }
   CopyStatuses(b, out, &overall);
   return overall;

@@ -747,6 +747,43 @@ JXLB_HD uint32_t PermCtx(uint32_t v) {
   uint32_t c = (uint32_t) FloorLog2(v) + 1;
   return c > 7 ? 7 : c;
 }
+// Lehmer digits temp[0 .. end) (temp[i] < size - i; digits from `end` on are zero) -> perm[0 .. size).  temp is
+// overwritten.  Returns kOk or kErrBadStream.
+JXLB_HD_NOINLINE int ExpandLehmer(uint32_t size, uint32_t end, uint32_t* perm, uint32_t* temp) {
+  // Lehmer code -> permutation: perm[i] = the temp[i]-th element still unused.  Done with a Fenwick tree of "unused"
+  // counts held in perm[] (k-th unused element and its removal in O(log size) each), the results written over the
+  // consumed digits in temp[]: O(size log size) whatever the digits are -- they are attacker-controlled, and a shifting
+  // list costs the sum of the digits (~10^10 moves for a crafted set of 65536-entry coefficient orders).
+  for (uint32_t j = 1; j <= size; ++j) perm[j - 1] = j & (0u - j);  // tree[j] = lowbit(j): all elements unused
+  uint32_t top = 1;
+  while ((top << 1) <= size) top <<= 1;
+  for (uint32_t i = 0; i < end; ++i) {
+    uint32_t k = temp[i], pos = 0;
+    for (uint32_t pw = top; pw; pw >>= 1) {
+      const uint32_t nx = pos + pw;
+      if (nx <= size && perm[nx - 1] <= k) {
+        pos = nx;
+        k -= perm[nx - 1];
+      }
+    }
+    if (pos >= size) return kErrBadStream;  // cannot happen: temp[i] < size - i was checked above
+    temp[i] = pos;                          // 0-based element
+    for (uint32_t j = pos + 1; j <= size; j += j & (0u - j)) --perm[j - 1];
+  }
+  // back from tree to per-element "unused" flags (inverse of the linear-time build), then the unused elements in order
+  for (uint32_t j = size; j >= 1; --j) {
+    const uint32_t parent = j + (j & (0u - j));
+    if (parent <= size) perm[parent - 1] -= perm[j - 1];
+  }
+  {
+    uint32_t p = end;
+    for (uint32_t e = 0; e < size; ++e)
+      if (perm[e]) temp[p++] = e;
+  }
+  for (uint32_t i = 0; i < size; ++i) perm[i] = temp[i];
+  return kOk;
+}
+
 JXLB_HD_NOINLINE int ReadPermutation(const CodeView& c, SymbolReader& r, BitReader& br, uint32_t size, uint32_t skip,
                                      uint32_t* perm, uint32_t* temp) {
   uint32_t end = ReadHybridUint(c, r, br, PermCtx(size));
@@ -760,17 +797,7 @@ JXLB_HD_NOINLINE int ReadPermutation(const CodeView& c, SymbolReader& r, BitRead
     temp[i] = v;
     last = v;
   }
-  // decode Lehmer code: perm[i] = temp[i]-th remaining element.  O(n * lehmer) with a simple shifting list;
-  // sizes on this path are <= 65536 and almost all Lehmer digits are zero.
-  for (uint32_t i = 0; i < size; ++i) perm[i] = i;
-  for (uint32_t i = 0; i < end; ++i) {
-    uint32_t k = temp[i];
-    if (k == 0) continue;
-    uint32_t v = perm[i + k];
-    for (uint32_t j = i + k; j > i; --j) perm[j] = perm[j - 1];
-    perm[i] = v;
-  }
-  return kOk;
+  return ExpandLehmer(size, end, perm, temp);
 }
 
 }  // namespace jxlb

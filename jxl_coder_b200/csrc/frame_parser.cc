@@ -228,6 +228,9 @@ int ParseImageHeader(const uint8_t* cs, size_t cs_padded, size_t cs_len, ImageMe
     }
   }
   if (md->color.want_icc) JXLB_FAIL(kParseUnsupported, "embedded ICC profile in codestream");
+  // a preview frame (own size, own frame-header layout) would precede the first frame: not handled, and parsing it as
+  // the main frame would give a corrupt-section error or a wrong picture
+  if (md->have_preview) JXLB_FAIL(kParseUnsupported, "preview frame");
   if (br.Overrun()) JXLB_FAIL(kParseInvalid, "truncated image header");
   br.AlignToByte();
   *frame_bit = br.Position();
@@ -372,6 +375,11 @@ int ParseFrameHeader(const uint8_t* cs, size_t cs_padded, size_t cs_len, const I
   fh->coded_w = W;
   fh->coded_h = H;
   if (W == 0 || H == 0) JXLB_FAIL(kParseInvalid, "empty frame");
+  // A crop rectangle comes straight from the bitstream (up to 2^30 + 18687 per side).  Frames are bounded like the image
+  // itself (DecodeJpegXlOneShot refuses pictures of 2^31 bytes or more, interop/JxlDecoding.cpp:103-109): nothing larger
+  // can be handed back, and the group counts below stay far from 32-bit overflow.
+  if (fh->width > (1u << 24) || fh->height > (1u << 24) || (uint64_t) fh->width * fh->height >= (1ull << 29))
+    JXLB_FAIL(kParseInvalid, "frame size exceeds the decodable image size");
   fh->group_dim = fh->encoding == 0 ? kGroupDim : (128u << fh->group_size_shift);
   const uint32_t gd = fh->group_dim;
   fh->ngx = (W + gd - 1) / gd;
@@ -380,7 +388,12 @@ int ParseFrameHeader(const uint8_t* cs, size_t cs_padded, size_t cs_len, const I
   fh->nlfy = (H + 8 * gd - 1) / (8 * gd);
   fh->num_groups = fh->ngx * fh->ngy;
   fh->num_lf_groups = fh->nlfx * fh->nlfy;
-  fh->toc_entries = (fh->num_groups == 1 && fh->num_passes == 1) ? 1 : 1 + fh->num_lf_groups + 1 + fh->num_groups * fh->num_passes;
+  const uint64_t toc64 = (fh->num_groups == 1 && fh->num_passes == 1) ? 1 : 1 + (uint64_t) fh->num_lf_groups + 1 + (uint64_t) fh->num_groups * fh->num_passes;
+  // every TOC entry takes at least 10 bits: a table that cannot fit in what is left of the input is refused before any
+  // allocation proportional to it
+  if (toc64 > (1u << 24) || toc64 * 10 > (uint64_t) cs_len * 8 - std::min<uint64_t>(br.Position(), (uint64_t) cs_len * 8))
+    JXLB_FAIL(kParseInvalid, "truncated TOC");
+  fh->toc_entries = (uint32_t) toc64;
   // ---- TOC
   const uint32_t n = fh->toc_entries;
   std::vector<uint32_t> perm;
@@ -462,6 +475,8 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
                       std::string* err) {
   if (fh.flags & ~(uint64_t) 0x80) JXLB_FAIL(kParseUnsupported, "noise / patches / splines / LF-frame flags");
   if (fh.upsampling != 1) JXLB_FAIL(kParseUnsupported, "upsampled frame");
+  for (uint32_t u : fh.ec_upsampling)
+    if (u != 1) JXLB_FAIL(kParseUnsupported, "upsampled extra channel");
   if (fh.num_passes != 1) JXLB_FAIL(kParseUnsupported, "progressive passes");
   if (fh.frame_type != 0) JXLB_FAIL(kParseUnsupported, "non-regular frame type");
   if (fh.do_ycbcr) JXLB_FAIL(kParseUnsupported, "YCbCr frame");

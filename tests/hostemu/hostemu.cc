@@ -227,6 +227,8 @@ uint32_t emu_plane_h(void* h) { return static_cast<Emu*>(h)->f.plane_h; }
 // Unit hooks for table checks.
 uint32_t emu_freq_ctx(uint32_t k) { return ZeroDensityFreqCtx(k); }
 uint32_t emu_nnz_ctx(uint32_t k) { return ZeroDensityNnzCtx(k); }
+// Lehmer digits -> permutation (entropy.h ExpandLehmer); digits is overwritten.
+int emu_expand_lehmer(uint32_t size, uint32_t end, uint32_t* perm, uint32_t* digits) { return ExpandLehmer(size, end, perm, digits); }
 void emu_logcount(uint32_t idx7, uint32_t* nb, uint32_t* sym) { LogCountLookup(idx7, nb, sym); }
 uint32_t emu_natural_order(uint32_t order_id, uint16_t* out) {
   const NaturalOrders& nat = NaturalOrderPoolHost();

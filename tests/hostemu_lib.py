@@ -44,6 +44,7 @@ def lib():
         L.emu_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                  C.POINTER(C.c_uint32)]
         L.emu_color_matrix.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.emu_expand_lehmer.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.emu_rcp_check.argtypes = [C.c_long]
         L.emu_rcp_check.restype = C.c_long
         _lib = L
