@@ -14,6 +14,38 @@ namespace jxlb {
 
 static constexpr float kSqrt2f = 1.41421356237f;
 
+// Separately rounded multiply / add / divide / square root: the reference's libjxl is an SSE2 build (build_jxl.sh:107-110),
+// whose MulAdd is a multiply followed by an add.  nvcc would contract a * b + c into one FMA.
+JXLB_HD float MulRn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+JXLB_HD float AddRn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+JXLB_HD float MulAddRn(float a, float b, float c) { return AddRn(MulRn(a, b), c); }
+JXLB_HD float SqrtRn(float a) {
+#ifdef __CUDA_ARCH__
+  return __fsqrt_rn(a);
+#else
+  return sqrtf(a);
+#endif
+}
+JXLB_HD float DivRn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+
 // ---- dequantisation ---------------------------------------------------------------------------------------------------
 JXLB_HD float AdjustQuantBias(int q, uint32_t c) {
   // biases {X, Y, B} for |q| == 1, and q - 0.145/q beyond (App. B.7 "HF dequant")
@@ -23,6 +55,25 @@ JXLB_HD float AdjustQuantBias(int q, uint32_t c) {
   if (q == -1) return -b;
   const float f = (float) q;
   return f - 0.145f / f;
+}
+// The same with libjxl's arithmetic (JXL_HIGH_PRECISION=0 build): q - 0.145 * ApproximateReciprocal(q), the reciprocal
+// being x86 RCPPS (rcp11: see NumericTables), multiply and subtract rounded separately.
+JXLB_HD float AdjustQuantBiasRcp(int q, uint32_t c, const uint32_t* rcp11) {
+  const float b = c == 0 ? 0.945349932f : c == 1 ? 0.929945469f : 0.950064898f;
+  if (q == 0) return 0.0f;
+  if (q == 1) return b;
+  if (q == -1) return -b;
+  const float f = (float) q;
+  union { float f; uint32_t u; } v;
+  v.f = fabsf(f);
+  const uint32_t e = (v.u >> 23) & 0xFFu;
+  v.u = rcp11[(v.u >> 12) & 0x7FFu] - ((e - 127u) << 23);
+  const float r = q < 0 ? -v.f : v.f;
+#ifdef __CUDA_ARCH__
+  return __fsub_rn(f, __fmul_rn(0.145f, r));
+#else
+  return f - 0.145f * r;
+#endif
 }
 
 // ---- inverse DCT: y[n] = sum_k c_k X[k] cos((2n+1) k pi / 2N), c_0 = 1, c_k = sqrt(2) ---------------------------------
@@ -419,8 +470,8 @@ JXLB_HD void EpfPixel(const Img& im, const RestorationFilter& rf, const uint32_t
 
 // ---- colour ------------------------------------------------------------------------------------------------------------
 struct ColorParams {
-  float opsin_inv[9];      // already scaled by 255 / intensity_target
-  float to_target[9];      // linear sRGB -> linear target primaries (identity for sRGB)
+  float opsin_inv[9];      // (linear sRGB -> target primaries) x inverse opsin matrix, scaled by 255 / intensity_target
+  float to_target[9];      // linear sRGB -> linear target primaries (identity for sRGB); folded into opsin_inv
   uint32_t apply_primaries;
   uint32_t transfer;       // jxl/color_encoding.h JxlTransferFunction; 0xFFFF = gamma
   float gamma;             // exponent for have_gamma (encoded = linear ^ gamma)
@@ -437,34 +488,77 @@ JXLB_HD float PowUnit(float v, float e) {
   return powf(v, e);
 #endif
 }
+// sRGB encode as the reference's libjxl computes it: the library is a JXL_HIGH_PRECISION=0 build (build_jxl.sh:36-37), whose
+// linear -> sRGB stage is FastLinearToSRGB, not the closed form: the mantissa is moved to [0.25, 0.5) and run through a
+// cubic, the exponent selects one of 16 multipliers 2 * 2^(5 e / 12) kept with a 13-bit mantissa, then * and - 0.055 are
+// rounded separately.  It is ~1e-4 away from 1.055 v^(1/2.4) - 0.055 -- enough to flip the 8-bit rounding of ~0.5 % of
+// the samples, which was the whole difference between this decoder and the reference on sRGB pictures.  Constants and
+// tables read out of the shipped lib/x86_64/libjxl.so (function at 0x2371c0: tables at .rodata 0x11f10 / 0x130f0).
 JXLB_HD float SrgbOetf(float v) {
-  if (v <= 0.0031308f) return 12.92f * v;
-  return 1.055f * PowUnit(v, 1.0f / 2.4f) - 0.055f;
+  if (v < 0.0031308f) return MulRn(v, 12.92f);
+  union { float f; uint32_t u; } in, m, mul;
+  in.f = v;
+  m.u = (in.u & 0x007FFFFFu) | 0x3E800000u;
+  const float x = m.f;
+  float d = MulAddRn(x, 0.059914046f, -0.108894556f);
+  d = MulAddRn(d, x, 0.107963754f);
+  d = MulAddRn(d, x, 0.018092343f);
+  // multipliers for exponents 118 .. 133 (v in [2^-9, 2^7)): bits 25-18 and 17-10 from the two byte tables
+  const uint32_t kHi[16] = {0x00, 0x0a, 0x19, 0x26, 0x32, 0x41, 0x4d, 0x5c, 0x68, 0x75, 0x83, 0x8f, 0xa0, 0xaa, 0xb9, 0xc6};
+  const uint32_t kLo[16] = {0x00, 0xb7, 0x04, 0x0d, 0xcb, 0xe7, 0x41, 0x68, 0x51, 0xd1, 0xeb, 0xf2, 0x00, 0xb7, 0x04, 0x0d};
+  const uint32_t e = ((in.u >> 23) - 118u) & 15u;
+  mul.u = (kHi[e] << 18) | (kLo[e] << 10) | 0x40000000u;
+  return MulAddRn(d, mul.f, -0.055f);
 }
 JXLB_HD float Rec709Oetf(float v) {
   if (v < 0.018f) return 4.5f * v;
   return 1.099f * powf(v, 0.45f) - 0.099f;
 }
+// PQ (SMPTE ST 2084) encode as libjxl 0.12.0 computes it for Rec.2100-PQ tagged pictures (TF_PQ::EncodedFromDisplay):
+// NOT the closed form with two powf calls, but a 4-over-4 rational polynomial in x^(1/4) (two square roots), one
+// coefficient set below 1e-4 and one above, Horner's scheme with separately rounded multiplies and adds, a true
+// division; the sign of the input is carried through.  `v` = linear light already scaled so that 1.0 = 10000 nits.
+// The 20 coefficients were read out of the reference's shipped lib/x86_64/libjxl.so (.rodata, each replicated four
+// times for the SSE2 lanes) -- libjxl's source is not part of /root/reference.  PQ's slope at black is ~10^6 code values
+// per unit of linear light, so the closed form and the approximation (max error 3e-6) disagree by many codes there.
 JXLB_HD float PqOetf(float v) {
-  const float m1 = 0.1593017578125f, m2 = 78.84375f, c1 = 0.8359375f, c2 = 18.8515625f, c3 = 18.6875f;
-  const float xp = powf(v < 0.0f ? 0.0f : v, m1);
-  return powf((c1 + c2 * xp) / (1.0f + c3 * xp), m2);
+  const float a = fabsf(v);
+  const float x = SqrtRn(SqrtRn(a));
+  float yp, yq;
+  if (a < 1e-4f) {
+    yp = MulAddRn(-2.864824e+05f, x, 6.889862e+04f);
+    yp = MulAddRn(yp, x, 1.352821e+02f);
+    yp = MulAddRn(yp, x, 3.881234e-01f);
+    yp = MulAddRn(yp, x, 9.863406e-06f);
+    yq = MulAddRn(-2.072546e+05f, x, -4.389884e+04f);
+    yq = MulAddRn(yq, x, 1.608477e+04f);
+    yq = MulAddRn(yq, x, 1.477719e+03f);
+    yq = MulAddRn(yq, x, 3.371868e+01f);
+  } else {
+    yp = MulAddRn(4.838434e+01f, x, 1.492516e+02f);
+    yp = MulAddRn(yp, x, 5.522776e+01f);
+    yp = MulAddRn(yp, x, -1.095778e+00f);
+    yp = MulAddRn(yp, x, 1.351392e-02f);
+    yq = MulAddRn(2.590418e+01f, x, 1.120607e+02f);
+    yq = MulAddRn(yq, x, 9.263710e+01f);
+    yq = MulAddRn(yq, x, 2.016708e+01f);
+    yq = MulAddRn(yq, x, 1.012416e+00f);
+  }
+  const float m = DivRn(yp, yq);
+  return v < 0.0f ? -m : m;
 }
 
 JXLB_HD void XybToEncodedRgb(float x, float y, float b, const ColorParams& cp, float rgb[3]) {
+  // libjxl's XybToRgb, operation by operation, with the separately rounded multiplies and adds of its SSE2 build:
+  // gamma = (y +- x) - cbrt(-bias); mixed = gamma^2 * gamma + (-bias); linear = M[.][0] * mr, then + M[.][1] * mg, then
+  // + M[.][2] * mb.  cp.opsin_inv already contains the primaries conversion and the 255 / intensity_target scale.
   const float kBias = 0.0037930732552754493f;
   const float kCbrtBias = 0.15595420054f;  // cbrt(kBias)
-  const float gr = y + x + kCbrtBias, gg = y - x + kCbrtBias, gb = b + kCbrtBias;
-  const float mr = gr * gr * gr - kBias, mg = gg * gg * gg - kBias, mb = gb * gb * gb - kBias;
+  const float gr = AddRn(AddRn(y, x), kCbrtBias), gg = AddRn(AddRn(y, -x), kCbrtBias), gb = AddRn(b, kCbrtBias);
+  const float mr = MulAddRn(MulRn(gr, gr), gr, -kBias), mg = MulAddRn(MulRn(gg, gg), gg, -kBias), mb = MulAddRn(MulRn(gb, gb), gb, -kBias);
   float lin[3];
-  for (int i = 0; i < 3; ++i) lin[i] = cp.opsin_inv[3 * i] * mr + cp.opsin_inv[3 * i + 1] * mg + cp.opsin_inv[3 * i + 2] * mb;
-  if (cp.apply_primaries) {
-    float t[3];
-    for (int i = 0; i < 3; ++i) t[i] = cp.to_target[3 * i] * lin[0] + cp.to_target[3 * i + 1] * lin[1] + cp.to_target[3 * i + 2] * lin[2];
-    lin[0] = t[0];
-    lin[1] = t[1];
-    lin[2] = t[2];
-  }
+  for (int i = 0; i < 3; ++i)
+    lin[i] = MulAddRn(cp.opsin_inv[3 * i + 2], mb, MulAddRn(cp.opsin_inv[3 * i + 1], mg, MulRn(cp.opsin_inv[3 * i], mr)));
   for (int i = 0; i < 3; ++i) {
     float v = lin[i];
     if (cp.transfer == 16) {

@@ -3,6 +3,7 @@
 #include "numeric_tables.h"
 
 #include <cmath>
+#include <cstring>
 #include <mutex>
 
 #if defined(__x86_64__) || defined(__i386__)
@@ -103,25 +104,97 @@ Bands DctParams(int q) {
   return b;
 }
 
-double Mult(double v) { return v > 0 ? 1 + v : 1 / (1 - v); }
+// libjxl computes its quant weights in float with FastPowf = FastPow2f(FastLog2f(b) * e), two small rational polynomials
+// (lib/jxl/base/fast_math-inl.h; L1 error ~4e-6 in the logarithm), not with pow(): the tables differ from the closed form
+// by up to ~1e-5 relative, which reaches the 8-bit rounding at higher distances.  Restated operation by operation
+// (separately rounded multiplies and adds: the reference's x86_64 library is an SSE2 build); the 13 polynomial constants
+// were checked against the shipped lib/x86_64/libjxl.so (each present as a 4-lane vector in .rodata).
+float Mult(float v) { return v > 0.0f ? 1.0f + v : 1.0f / (1.0f - v); }
 
-// weights of a rows x cols coefficient array from distance bands (App. B.7 "Quant weights")
+float FastLog2f(float x) {
+  int32_t xb;
+  memcpy(&xb, &x, 4);
+  const int32_t exp_bits = xb - 0x3f2aaaab;   // = 2/3
+  const int32_t exp_shifted = exp_bits >> 23;
+  const int32_t mb = xb - (int32_t) ((uint32_t) exp_shifted << 23);
+  float mantissa;
+  memcpy(&mantissa, &mb, 4);
+  const float t = mantissa - 1.0f;
+  volatile float yp = 7.4245873327820566E-01f, yq = 1.7409343003366853E-01f, m;
+  m = yp * t;
+  yp = m + 1.4287160470083755E+00f;
+  m = yp * t;
+  yp = m + -1.8503833400518310E-06f;
+  m = yq * t;
+  yq = m + 1.0096718572241148E+00f;
+  m = yq * t;
+  yq = m + 9.9032814277590719E-01f;
+  const float ratio = yp / yq;
+  return ratio + (float) exp_shifted;
+}
+
+float FastPow2f(float x) {
+  const float floorx = floorf(x);
+  const int32_t eb = (int32_t) ((uint32_t) ((int32_t) floorx + 127) << 23);
+  float ex;
+  memcpy(&ex, &eb, 4);
+  const float frac = x - floorx;
+  volatile float num = frac + 1.01749063e+01f, m, den;
+  m = num * frac;
+  num = m + 4.88687798e+01f;
+  m = num * frac;
+  num = m + 9.85506591e+01f;
+  num = num * ex;
+  m = frac * 2.10242958e-01f;
+  den = m + -2.22328856e-02f;
+  m = den * frac;
+  den = m + -1.94414990e+01f;
+  m = den * frac;
+  den = m + 9.85506633e+01f;
+  return num / den;
+}
+
+float FastPowf(float base, float exponent) {
+  volatile float l = FastLog2f(base);
+  volatile float le = l * exponent;
+  return FastPow2f(le);
+}
+
+// weights of a rows x cols coefficient array from distance bands (App. B.7 "Quant weights"; libjxl GetQuantWeights)
 void BandWeights(int rows, int cols, const double* params, int nb, std::vector<double>* w) {
-  double bands[8];
-  bands[0] = params[0];
-  for (int i = 1; i < nb; ++i) bands[i] = bands[i - 1] * Mult(params[i]);
-  const double scale = (nb - 1) / (std::sqrt(2.0) + 1e-6);
-  const double rc = scale / (cols - 1), rr = scale / (rows - 1);
+  float bands[17] = {};
+  bands[0] = (float) params[0];
+  for (int i = 1; i < nb; ++i) bands[i] = bands[i - 1] * Mult((float) params[i]);
+  const float scale = (float) (nb - 1) / (1.41421356237f + 1e-6f);
+  const float rc = scale / (float) (cols - 1), rr = scale / (float) (rows - 1);
   w->assign((size_t) rows * cols, 0.0);
-  for (int y = 0; y < rows; ++y)
+  for (int y = 0; y < rows; ++y) {
+    const float dy = (float) y * rr;
+    const float dy2 = dy * dy;
     for (int x = 0; x < cols; ++x) {
-      const double d = std::hypot(x * rc, y * rr);
-      int i = (int) d;
-      if (i > nb - 1) i = nb - 1;
-      const double fr = d - i;
-      const double a = bands[i], b = bands[i + 1 < nb ? i + 1 : nb - 1];
-      (*w)[(size_t) y * cols + x] = a * std::pow(b / a, fr);
+      const float dx = (float) x * rc;
+      volatile float dx2 = dx * dx;
+      const float dist = sqrtf(dx2 + dy2);
+      float weight = bands[0];
+      if (nb > 1) {
+        const int idx = (int) dist;
+        const float frac = dist - (float) idx;
+        const float a = bands[idx], b = bands[idx + 1];
+        volatile float p = FastPowf(b / a, frac);
+        weight = a * p;
+      }
+      (*w)[(size_t) y * cols + x] = weight;
     }
+  }
+}
+
+// libjxl's scalar Interpolate (AFV table)
+float InterpolateBands(float pos, float max, const float* array, int len) {
+  const float scaled_pos = pos * (float) (len - 1) / max;
+  const int idx = (int) scaled_pos;
+  const float a = array[idx], b = array[idx + 1];
+  volatile float p = FastPowf(b / a, scaled_pos - (float) idx);
+  return a * p;
 }
 
 const double kIdWeights[3][3] = {{280.0, 3160.0, 3160.0}, {60.0, 864.0, 864.0}, {18.0, 200.0, 200.0}};
@@ -176,10 +249,10 @@ void TableWeights(int q, int c, std::vector<double>* w, int* rows, int* cols) {
     std::vector<double> w48, w44;
     BandWeights(4, 8, b48.v[c], b48.n, &w48);
     BandWeights(4, 4, b44.v[c], b44.n, &w44);
-    const double lo = 0.8517778890324296, hi = 12.97166202570235 - lo + 1e-6;
-    double bands[4];
-    bands[0] = a[5];
-    for (int i = 1; i < 4; ++i) bands[i] = bands[i - 1] * Mult(a[i + 5]);
+    const float lo = 0.8517778890324296f, hi = 12.97166202570235f - lo + 1e-6f;
+    float bands[4];
+    bands[0] = (float) a[5];
+    for (int i = 1; i < 4; ++i) bands[i] = bands[i - 1] * Mult((float) a[i + 5]);
     w->assign(64, 0.0);
     (*w)[0] = 1.0;
     (*w)[1 * 8 + 0] = a[0];
@@ -190,10 +263,7 @@ void TableWeights(int q, int c, std::vector<double>* w, int* rows, int* cols) {
     for (int y = 0; y < 4; ++y)
       for (int x = 0; x < 4; ++x) {
         if (x < 2 && y < 2) continue;
-        const double pos = (kAfvFreqs[y * 4 + x] - lo) * 3 / hi;
-        int i = (int) pos;
-        if (i > 2) i = 2;
-        (*w)[(2 * y) * 8 + 2 * x] = bands[i] * std::pow(bands[i + 1] / bands[i], pos - i);
+        (*w)[(2 * y) * 8 + 2 * x] = InterpolateBands((float) kAfvFreqs[y * 4 + x] - lo, hi, bands, 4);
       }
     for (int y = 0; y < 4; ++y)
       for (int x = 0; x < 8; ++x) {
@@ -231,11 +301,11 @@ const HostNumericTables& GetHostNumericTables() {
         int rows, cols;
         TableWeights(q, c, &w, &rows, &cols);
         t.tables.dequant_off[q][c] = (uint32_t) t.dequant_pool.size();
-        for (double v : w) t.dequant_pool.push_back((float) (1.0 / v));
+        for (double v : w) t.dequant_pool.push_back(1.0f / (float) v);  // libjxl: table = 1.0f / weight
         if (rows != cols) symmetric = false;
         for (int a = 0; a < rows && symmetric; ++a)
           for (int b = 0; b < a; ++b)
-            if ((float) (1.0 / w[(size_t) a * cols + b]) != (float) (1.0 / w[(size_t) b * cols + a])) {
+            if ((float) w[(size_t) a * cols + b] != (float) w[(size_t) b * cols + a]) {
               symmetric = false;
               break;
             }

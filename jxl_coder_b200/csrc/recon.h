@@ -136,7 +136,7 @@ JXLB_HD float DequantAt(const FrameDev& f, const NumericTables& nt, uint32_t t, 
   const uint32_t kcols = 8 * (cx > cy ? cx : cy);
   const uint32_t kr = transposed ? pc : pr, kc = transposed ? pr : pc;
   const float w = nt.dequant[nt.dequant_off[StrategyQuantTable(t)][c] + kr * kcols + kc];
-  return AdjustQuantBias(q, c) * block_scale * w;
+  return MulRn(AdjustQuantBiasRcp(q, c, nt.rcp11), MulRn(w, block_scale));
 }
 
 // Reconstructs the blocks fully contained in region (rx, ry) into f.xyb0.  sh: shared memory of the CTA.
@@ -243,18 +243,18 @@ JXLB_HD void ReconRegion(const FrameDev& f, const NumericTables& nt, uint32_t rx
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int q = raw[r][1].Get(j);
-        vy[j] = (!zy && q) ? AdjustQuantBias(q, 1) * sy * nt.dequant[rc.dq_off[1] + k0 + j * kstep] : 0.0f;
+        vy[j] = (!zy && q) ? MulRn(AdjustQuantBiasRcp(q, 1, nt.rcp11), MulRn(nt.dequant[rc.dq_off[1] + k0 + j * kstep], sy)) : 0.0f;
         ty[j] = vy[j];
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int q = raw[r][0].Get(j);
-        tx[j] = ((!zx && q) ? AdjustQuantBias(q, 0) * sx * nt.dequant[rc.dq_off[0] + k0 + j * kstep] : 0.0f) + rc.kx * vy[j];
+        tx[j] = MulAddRn(rc.kx, vy[j], (!zx && q) ? MulRn(AdjustQuantBiasRcp(q, 0, nt.rcp11), MulRn(nt.dequant[rc.dq_off[0] + k0 + j * kstep], sx)) : 0.0f);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int q = raw[r][2].Get(j);
-        tb[j] = ((!zb && q) ? AdjustQuantBias(q, 2) * sb * nt.dequant[rc.dq_off[2] + k0 + j * kstep] : 0.0f) + rc.kb * vy[j];
+        tb[j] = MulAddRn(rc.kb, vy[j], (!zb && q) ? MulRn(AdjustQuantBiasRcp(q, 2, nt.rcp11), MulRn(nt.dequant[rc.dq_off[2] + k0 + j * kstep], sb)) : 0.0f);
       }
     }
   }

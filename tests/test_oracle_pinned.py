@@ -30,7 +30,7 @@ def test_restatement_matches_golden(name):
     if "lossless" in name:
         assert (r["rgba"] == g["raw"]).all()
     else:
-        golden_lib.lossy_close(r["rgba"], g["raw"], name)
+        golden_lib.restatement_close(r["rgba"], g["raw"], name)
 
 
 def test_inverse_transforms_match_reference_binary(ref):
