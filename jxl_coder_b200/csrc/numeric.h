@@ -503,11 +503,19 @@ JXLB_HD float SrgbOetf(float v) {
   float d = MulAddRn(x, 0.059914046f, -0.108894556f);
   d = MulAddRn(d, x, 0.107963754f);
   d = MulAddRn(d, x, 0.018092343f);
-  // multipliers for exponents 118 .. 133 (v in [2^-9, 2^7)): bits 25-18 and 17-10 from the two byte tables
-  const uint32_t kHi[16] = {0x00, 0x0a, 0x19, 0x26, 0x32, 0x41, 0x4d, 0x5c, 0x68, 0x75, 0x83, 0x8f, 0xa0, 0xaa, 0xb9, 0xc6};
-  const uint32_t kLo[16] = {0x00, 0xb7, 0x04, 0x0d, 0xcb, 0xe7, 0x41, 0x68, 0x51, 0xd1, 0xeb, 0xf2, 0x00, 0xb7, 0x04, 0x0d};
+  // multipliers for exponents 118 .. 133 (v in [2^-9, 2^7)): bits 25-18 and 17-10 from two 16-entry byte tables
+  // {00 0a 19 26 32 41 4d 5c 68 75 83 8f a0 aa b9 c6} and {00 b7 04 0d cb e7 41 68 51 d1 eb f2 00 b7 04 0d}
   const uint32_t e = ((in.u >> 23) - 118u) & 15u;
-  mul.u = (kHi[e] << 18) | (kLo[e] << 10) | 0x40000000u;
+#ifdef __CUDA_ARCH__
+  // byte-permute lookups (the tables live in immediates; an indexed local array would go through local memory)
+  const uint32_t hi = e < 8 ? __byte_perm(0x26190a00u, 0x5c4d4132u, e) : __byte_perm(0x8f837568u, 0xc6b9aaa0u, e - 8);
+  const uint32_t lo = e < 8 ? __byte_perm(0x0d04b700u, 0x6841e7cbu, e) : __byte_perm(0xf2ebd151u, 0x0d04b700u, e - 8);
+  mul.u = ((hi & 0xFFu) << 18) | ((lo & 0xFFu) << 10) | 0x40000000u;
+#else
+  static const uint8_t kHi[16] = {0x00, 0x0a, 0x19, 0x26, 0x32, 0x41, 0x4d, 0x5c, 0x68, 0x75, 0x83, 0x8f, 0xa0, 0xaa, 0xb9, 0xc6};
+  static const uint8_t kLo[16] = {0x00, 0xb7, 0x04, 0x0d, 0xcb, 0xe7, 0x41, 0x68, 0x51, 0xd1, 0xeb, 0xf2, 0x00, 0xb7, 0x04, 0x0d};
+  mul.u = ((uint32_t) kHi[e] << 18) | ((uint32_t) kLo[e] << 10) | 0x40000000u;
+#endif
   return MulAddRn(d, mul.f, -0.055f);
 }
 JXLB_HD float Rec709Oetf(float v) {
