@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libjxlb200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["kernels.cu", "kernels_ac.cu", "kernels_filter.cu", "kernels_resize.cu", "resize.cc", "kernels_post.cu", "color_matrix.cc", "decoder.cu", "c_api.cu", "anim.cu", "frame_parser.cc", "plan.cc", "natural_orders.cc", "numeric_tables.cc",
+SOURCES = ["kernels.cu", "kernels_ac.cu", "kernels_filter.cu", "kernels_recon.cu", "kernels_resize.cu", "resize.cc", "kernels_post.cu", "color_matrix.cc", "decoder.cu", "c_api.cu", "anim.cu", "frame_parser.cc", "plan.cc", "natural_orders.cc", "numeric_tables.cc",
            "color_params.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
               "-Xcompiler", "-Wno-unknown-pragmas"] + os.environ.get("JXLB_NVCC_EXTRA", "").split()

@@ -20,21 +20,21 @@ static constexpr uint32_t kNonZeroBuckets = 37;
 static constexpr uint32_t kContextsPerBlockCtx = 495;
 
 // cells covered (x, y), coefficient-order id, quant-table id per strategy (App. B.7 strategy table)
-JXLB_HD uint32_t StrategyCellsX(uint32_t s) {
-  const uint8_t k[kNumStrategies] = {1, 1, 1, 1, 2, 4, 1, 2, 1, 4, 2, 4, 1, 1, 1, 1, 1, 1, 8, 4, 8, 16, 8, 16, 32, 16, 32};
-  return k[s];
-}
-JXLB_HD uint32_t StrategyCellsY(uint32_t s) {
-  const uint8_t k[kNumStrategies] = {1, 1, 1, 1, 2, 4, 2, 1, 4, 1, 4, 2, 1, 1, 1, 1, 1, 1, 8, 8, 4, 16, 16, 8, 32, 32, 16};
-  return k[s];
-}
-JXLB_HD uint32_t StrategyOrder(uint32_t s) {
-  const uint8_t k[kNumStrategies] = {0, 1, 1, 1, 2, 3, 4, 4, 5, 5, 6, 6, 1, 1, 1, 1, 1, 1, 7, 8, 8, 9, 10, 10, 11, 12, 12};
-  return k[s];
-}
+// The tables are packed into 64-bit literals (4 or 8 bits per strategy): a local array indexed at run time would be
+// built on the stack of every device thread that calls these.
+//   cells x: {1, 1, 1, 1, 2, 4, 1, 2, 1, 4, 2, 4, 1, 1, 1, 1, 1, 1, 8, 4, 8, 16, 8, 16, 32, 16, 32}  (stored as log2)
+//   cells y: {1, 1, 1, 1, 2, 4, 2, 1, 4, 1, 4, 2, 1, 1, 1, 1, 1, 1, 8, 8, 4, 16, 16, 8, 32, 32, 16}
+//   order:   {0, 1, 1, 1, 2, 3, 4, 4, 5, 5, 6, 6, 1, 1, 1, 1, 1, 1, 7, 8, 8, 9, 10, 10, 11, 12, 12}
+//   quant:   {0, 1, 2, 3, 4, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 10, 10, 11, 12, 12, 13, 14, 14, 15, 16, 16}
+JXLB_HD uint32_t Packed4(uint32_t s, uint64_t lo, uint64_t hi) { return (uint32_t) ((s < 16 ? lo >> (4 * s) : hi >> (4 * (s - 16))) & 15u); }
+JXLB_HD uint32_t StrategyCellsXLog2(uint32_t s) { return Packed4(s, 0x212010210000ull, 0x54543432300ull); }
+JXLB_HD uint32_t StrategyCellsYLog2(uint32_t s) { return Packed4(s, 0x120201210000ull, 0x45534423300ull); }
+JXLB_HD uint32_t StrategyCellsX(uint32_t s) { return 1u << StrategyCellsXLog2(s); }
+JXLB_HD uint32_t StrategyCellsY(uint32_t s) { return 1u << StrategyCellsYLog2(s); }
+JXLB_HD uint32_t StrategyOrder(uint32_t s) { return Packed4(s, 0x1111665544321110ull, 0xccbaa988711ull); }
 JXLB_HD uint32_t StrategyQuantTable(uint32_t s) {
-  const uint8_t k[kNumStrategies] = {0, 1, 2, 3, 4, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 10, 10, 11, 12, 12, 13, 14, 14, 15, 16, 16};
-  return k[s];
+  const uint64_t w = s < 8 ? 0x606050403020100ull : s < 16 ? 0xa0a090908080707ull : s < 24 ? 0xe0e0d0c0c0b0a0aull : 0x10100full;
+  return (uint32_t) (w >> (8 * (s & 7u))) & 0xFFu;
 }
 // a representative strategy for each coefficient-order id
 JXLB_HD uint32_t OrderRepresentative(uint32_t o) {
@@ -159,6 +159,8 @@ struct FrameDev {
   int16_t* coef;                   // [3][coef_h][coef_stride] quantised coefficients (X, Y, B), block-rectangle layout
   uint32_t coef_stride, coef_h;
   float* lf;                       // [3][h8][lf_stride] dequantised (X, Y, B)
+  uint32_t* large_list;            // [0] = n, [1 .. n] = bx | by << 16: top-left cells of the blocks that no 64x64 region contains
+                                   // (reset by LfFinalKernel, filled by ReconRegionTmaKernel, consumed by ReconLargeListKernel)
   float* xyb0;                     // [3][plane_h][plane_stride]
   float* xyb1;
   uint32_t plane_stride, plane_h;

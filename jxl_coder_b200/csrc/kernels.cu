@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(256) LfFinalKernel(const FrameDev f) {
   if (*f.frame_bad) return;
   const uint32_t cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y;
   if (cx >= f.w8 || cy >= f.h8) return;
+  if (cx == 0 && cy == 0) f.large_list[0] = 0;  // the inverse-transform kernel that follows appends to the list
   const LfMul m = MakeLfMul(f);
   float v[3];
   LfFinalCell(f, m, cx, cy, v);
@@ -258,6 +259,18 @@ __global__ void __launch_bounds__(128, 4) ReconLargeKernel(const FrameDev f, con
   const uint32_t n = ntodo;
   for (uint32_t i = 0; i < n; ++i) {
     const uint32_t e = todo[i];
+    ReconLargeBlock(f, *nt, e & 0xFFFF, e >> 16, (int) threadIdx.x, (int) blockDim.x, SyncThreads());
+    __syncthreads();
+  }
+}
+
+// The same for the blocks ReconRegionTmaKernel listed (kernels_recon.cu): a fixed grid walks the list instead of 4096
+// CTAs scanning for the rare block.
+__global__ void __launch_bounds__(128, 4) ReconLargeListKernel(const FrameDev f, const NumericTables* nt) {
+  if (*f.frame_bad) return;
+  const uint32_t n = f.large_list[0];
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint32_t e = f.large_list[1 + i];
     ReconLargeBlock(f, *nt, e & 0xFFFF, e >> 16, (int) threadIdx.x, (int) blockDim.x, SyncThreads());
     __syncthreads();
   }
@@ -376,14 +389,22 @@ void LaunchRecon(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t st
   }
   dim3 grid((f.w8 + kRegionCells - 1) / kRegionCells, (f.h8 + kRegionCells - 1) / kRegionCells, 1);
   static bool large_configured = false;
+  bool tma_done = false;
   if (!large_configured) {
     cudaFuncSetAttribute(ReconLargeKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(ReconLargeListKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(LfFinalKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     large_configured = true;
   }
-  ReconRegionKernel<<<grid, kReconThreads, sizeof(RegionShared), stream>>>(f, nt_dev);
-  ReconLargeKernel<<<grid, 128, 0, stream>>>(f, nt_dev);
-  g_launches += 2;
+  // contained blocks: the persistent TMA kernel (kernels_recon.cu); the plain-load kernel above is its fallback
+  tma_done = LaunchReconTma(f, nt_dev, stream);
+  if (!tma_done) {
+    ReconRegionKernel<<<grid, kReconThreads, sizeof(RegionShared), stream>>>(f, nt_dev);
+    ++g_launches;
+  }
+  if (tma_done) ReconLargeListKernel<<<148 * 2, 128, 0, stream>>>(f, nt_dev);
+  else ReconLargeKernel<<<grid, 128, 0, stream>>>(f, nt_dev);
+  ++g_launches;
 }
 
 int LaunchFilters(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t stream) {

@@ -91,6 +91,8 @@ void LaunchGroupModular(const FrameDev* frames, const StreamJob* jobs, uint32_t 
 // Numeric stages of one VarDCT frame (FrameDev passed by value).
 void LaunchLfFinal(const FrameDev& f, cudaStream_t stream);
 void LaunchRecon(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t stream);
+// Contained blocks of every 64x64 region through the persistent TMA kernel (kernels_recon.cu); false = not usable here.
+bool LaunchReconTma(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t stream);
 // Gaborish + EPF stages as configured; returns which buffer (0 = xyb0, 1 = xyb1) holds the result.
 int LaunchFilters(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t stream);
 void LaunchColor(const FrameDev& f, const ColorParams& cp, const NumericTables* nt_dev, const float* src, OutputDesc out,

