@@ -28,9 +28,9 @@ MPIX_PER_IMAGE = SIZE * SIZE / 1e6
 # algorithmic bytes per pixel of the inverse-transform kernel (SURVEY.md §8d "if split: K_idct"):
 # 3 x int16 coefficients read (6 B) + per-cell metadata and LF (0.25 B) + 3 x f32 XYB samples written (12 B)
 IDCT_BYTES_PER_PIXEL = 18.25
-# dram__bytes_read.sum + dram__bytes_write.sum of one ReconRegionKernel launch (one 4096x4096 image), ncu --set full,
-# profiles/r1d_ncu_recon_filter.txt
-TRAFFIC_BYTES_PER_IMAGE = 269_600_000
+# dram__bytes_read.sum + dram__bytes_write.sum of the inverse-transform launches of one 4096x4096 image (ReconRegionTmaKernel
+# 105.4 + 143.1 MB, ReconLargeListKernel 0.07 MB), ncu --set full of this HEAD's kernel: profiles/r2_ncu_recon.txt
+TRAFFIC_BYTES_PER_IMAGE = 248_600_000
 
 
 def load_inputs(batch=BATCH, distinct=DISTINCT, size=SIZE):
@@ -285,7 +285,7 @@ def run_ours(args):
                    "value_is": "kernels only, codestreams + host-parsed tables resident in HBM; %d prepared batches (decode contexts) run alternately with jxlb_batch_run_async, one batch run per step; device time = CUDA events first-run start -> last-run end" % contexts,
                    "contexts": contexts,
                    "stages_note": "stages_ms_per_step are per-run CUDA-event intervals on the run's own stream; with 2 contexts they include time shared with the other context's kernels",
-                   "roofline_kernel": "ReconRegionKernel + ReconLargeKernel (dequant + CfL + LLF + inverse VarDCT -> XYB f32 planes)",
+                   "roofline_kernel": "ReconRegionTmaKernel + ReconLargeListKernel (dequant + CfL + LLF + inverse VarDCT -> XYB f32 planes)",
                    "wall_ms_per_step": round(1e3 * wall / steps, 2)},
         "e2e": {"value": round(e2e_value, 1), "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": round(1e3 * float(t_e2e.item()) / e2e_steps, 2),
@@ -297,7 +297,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": TRAFFIC_BYTES_PER_IMAGE * BATCH if TRAFFIC_BYTES_PER_IMAGE else None,
                      "kernel_ms": round(idct_ms, 3), "launches": 2 * BATCH,
-                     "how": "64 ReconRegionKernel + 64 ReconLargeKernel launches of one 64-image batch run alone (no other context in flight) after the timed region; every 4th image's launch pair is bracketed by CUDA events on its stream, mean x 64; peak = burst HBM copy bandwidth",
+                     "how": "64 ReconRegionTmaKernel + 64 ReconLargeListKernel launches of one 64-image batch run alone (no other context in flight) after the timed region; every 4th image's launch pair is bracketed by CUDA events on its stream, mean x 64; peak = burst HBM copy bandwidth",
                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "algorithmic_bytes_per_pixel": IDCT_BYTES_PER_PIXEL},
         "clocks": sampler.summary(),

@@ -2,24 +2,29 @@
 // blocks contained in 64x64-pixel regions, quantised int16 coefficient planes -> XYB f32 planes.  This is the HBM
 // roofline kernel of the path (18.25 B/pixel: 6 B coefficients + 0.25 B metadata read, 12 B written).
 //
-// Persistent CTAs (2 per SM, 192 threads each) walk the image's region list.  Per region:
+// Persistent CTAs (2 per SM, 256 threads each) walk the image's region list.  Per region:
 //   * the 64 x 64 x 3 int16 coefficient tile (24 KB) arrives by ONE TMA tensor load (cp.async.bulk.tensor.3d,
 //     out-of-bounds rows / columns zero-filled by the hardware) signalled on an mbarrier; the load of region n + 1 is
 //     issued as soon as the dequantisation phase of region n has consumed the buffer, so it lands under the two IDCT
 //     passes; the per-cell metadata and LF samples of region n + 1 travel in registers over the same interval;
 //   * dequantisation reads its weights from shared memory (the matrices of every transform up to 32x32 -- 30 KB -- are
-//     staged once per CTA) and the quant-bias adjustment from a 256-entry table per channel; all-zero 8-coefficient
-//     units (the bulk of a q90 picture) cost three 128-bit loads and six 128-bit stores;
-//   * column pass and row pass keep a whole 1-D transform (8 .. 64 points) in the registers of one thread -- at 2 CTAs
-//     per SM a thread may use 168 registers, so even 64-point transforms do not spill; the tile's row stride of 68
+//     staged once per CTA) and the quant-bias adjustment from a 256-entry table per channel, branch-free; all-zero
+//     8-coefficient units cost three 128-bit loads and six 128-bit stores;
+//   * column pass and row pass keep a whole 1-D transform (8 .. 64 points) in the registers of one thread; each pass is
+//     cut into 12 warp-sized items (channel, 32 columns, half of the rows) with the four luma items on warps of their
+//     own; every warp votes on how many leading inputs are non-zero and runs a pruned transform when the high
+//     frequencies are empty (always the case for the chroma channels of most pictures); the tile's row stride of 68
 //     floats makes the column pass (scalar) and the row pass (128-bit) free of bank conflicts;
 //   * finished rows leave with one 256-byte bulk async store each (cp.async.bulk shared -> global), so the 12 B/pixel
 //     output is written in full lines by the copy engine while the CTA moves on.
+// A warp-autonomous variant (one 32x32 area per warp, no CTA barriers) was measured and dropped: 9 warps per SM do not
+// hide the dependent-issue latency of the transforms (184 us per 4096x4096 image against 135 us for this kernel).
 // Blocks that are not contained in one region (larger than 64 pixels or straddling a region border) are left to
 // ReconLargeKernel (kernels.cu), which runs after this kernel and overwrites their rectangles.
 // Arithmetic: identical, operation by operation, to ReconRegion (recon.h), which tests/hostemu runs on the CPU.
 #include <cuda.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -35,7 +40,7 @@ extern std::atomic<uint64_t> g_launches_ac;
 
 namespace {
 
-constexpr int kRT = 192;                       // threads per CTA: 3 channels x 64 columns / rows
+constexpr int kRT = 256;                       // threads per CTA: 2 dequantisation units each; 12 (channel, 32 columns / rows, half) items in the passes
 constexpr int kTS = 68;                        // tile row stride (floats)
 constexpr int kTP = kRegionDim * kTS;          // one channel of the tile
 constexpr uint32_t kSmemTableFloats = 7680;    // quant tables 0 .. 10 (every transform up to 32x32): contiguous at pool offset 0
@@ -47,7 +52,7 @@ struct ReconSmem {
   float tables[kSmemTableFloats];
   float adj[3][2 * kAdjHalf];
   float lf[3][kRegionCells * kRegionCells];
-  float llf_r[3][kRegionCells * kRegionCells];  // horizontal half of the LLF synthesis, one value per (channel, cell)
+  float llf_v[3][kRegionCells * kRegionCells];  // lowest-frequency coefficients from the LF image: [c][cell (oy + ky, ox + kx)] = coefficient (ky, kx)
   float llf[1 + 4 + 16 + 64];
   uint32_t cinfo[kRegionCells * kRegionCells];
   uint32_t dqoff[3][kRegionCells * kRegionCells];
@@ -164,22 +169,17 @@ __device__ __forceinline__ void IdctAdaptive(float (&v)[N]) {
 }
 
 // Column pass of one block column.  p: top of the column in the tile.  llf_col: when non-null, this column carries the
-// block's lowest frequencies in its first N / 8 rows: they come from the LF image, v[ky] = sum_ny A_by[ky][ny] * R[ny]
-// with R (the horizontal half of the synthesis, one value per cell) at llf_col[ny * 8]; ay = A_by.
+// block's lowest frequencies in its first N / 8 rows (one per cell row, llf_col[ky * 8]), which replace what the
+// dequantisation left there.
 template <int N>
-__device__ __forceinline__ void ColumnIdct(float* p, const float* llf_col, const float* ay) {
+__device__ __forceinline__ void ColumnIdct(float* p, const float* llf_col) {
   constexpr int BY = N / 8;
   float v[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) v[i] = p[i * kTS];
   if (llf_col) {
 #pragma unroll
-    for (int ky = 0; ky < BY; ++ky) {
-      float acc = 0.0f;
-#pragma unroll
-      for (int ny = 0; ny < BY; ++ny) acc += ay[ky * BY + ny] * llf_col[ny * kRegionCells];
-      v[ky] = acc;
-    }
+    for (int ky = 0; ky < BY; ++ky) v[ky] = llf_col[ky * kRegionCells];
   }
   IdctAdaptive<N>(v);
 #pragma unroll
@@ -219,7 +219,7 @@ __device__ __forceinline__ void LoadRegionMeta(const FrameDev& f, uint32_t rx, u
     m->hfmul = f.cell_hfmul[o];
   }
   const int c = tid >> 6;
-  m->lf = inside ? f.lf[(size_t) c * f.h8 * f.lf_stride + (size_t) gy * f.lf_stride + gx] : 0.0f;
+  m->lf = (inside && c < 3) ? f.lf[(size_t) c * f.h8 * f.lf_stride + (size_t) gy * f.lf_stride + gx] : 0.0f;
   if (tid == 64) {
     // CfL factors of the region's 64x64 tile (a contained block's top-left corner lies in it)
     const size_t t = (size_t) ry * f.w64 + rx;
@@ -229,7 +229,7 @@ __device__ __forceinline__ void LoadRegionMeta(const FrameDev& f, uint32_t rx, u
 }
 
 __device__ __forceinline__ void StoreRegionMeta(const FrameDev& f, const NumericTables& nt, ReconSmem& sh, int tid, const RegionPrefetch& m, uint32_t rx,
-                                                uint32_t ry) {
+                                                uint32_t ry, bool list_large) {
   if (tid < 64) {
     const int ix = tid & 7, iy = tid >> 3;
     uint32_t info = 0, d0 = 0, d1 = 0, d2 = 0;
@@ -240,7 +240,7 @@ __device__ __forceinline__ void StoreRegionMeta(const FrameDev& f, const Numeric
       const int ox = ix - dx, oy = iy - dy;
       const int bx = (int) StrategyCellsX(t), by = (int) StrategyCellsY(t);
       const bool contained = ox >= 0 && oy >= 0 && ox + bx <= kRegionCells && oy + by <= kRegionCells;
-      if (!contained && (m.strategy & 0x80u)) {  // top-left cell of a block no region contains: left to ReconLargeListKernel
+      if (!contained && (m.strategy & 0x80u) && list_large) {  // top-left cell of a block no region contains: left to ReconLargeListKernel
         const uint32_t slot = atomicAdd(f.large_list, 1u);
         f.large_list[1 + slot] = (rx * kRegionCells + (uint32_t) ix) | ((ry * kRegionCells + (uint32_t) iy) << 16);
       }
@@ -261,7 +261,7 @@ __device__ __forceinline__ void StoreRegionMeta(const FrameDev& f, const Numeric
     sh.dqoff[2][tid] = d2;
     sh.cscale[tid] = scale;
   }
-  sh.lf[tid >> 6][tid & 63] = m.lf;
+  if (tid < 192) sh.lf[tid >> 6][tid & 63] = m.lf;
   if (tid == 64) {
     sh.cfl[0] = m.kx;
     sh.cfl[1] = m.kb;
@@ -278,7 +278,17 @@ __device__ __forceinline__ void DequantUnit(const uint4 raw, const float* adj, c
 #pragma unroll
   for (int k = 0; k < 4; ++k) big |= (((w[k] & 0xFFFFu) + 0x80u) & 0xFFFFu) | (((w[k] >> 16) + 0x80u) & 0xFFFFu);
   float wt[8];
-  if (tab_shared) {
+  if (kstep == 1) {  // consecutive weights, 32-byte aligned (off is a multiple of 8)
+    float4 a, b;
+    if (tab_shared) {
+      a = *reinterpret_cast<const float4*>(tab + off);
+      b = *reinterpret_cast<const float4*>(tab + off + 4);
+    } else {
+      a = __ldg(reinterpret_cast<const float4*>(tab + off));
+      b = __ldg(reinterpret_cast<const float4*>(tab + off + 4));
+    }
+    wt[0] = a.x; wt[1] = a.y; wt[2] = a.z; wt[3] = a.w; wt[4] = b.x; wt[5] = b.y; wt[6] = b.z; wt[7] = b.w;
+  } else if (tab_shared) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) wt[j] = tab[off + (uint32_t) j * kstep];
   } else {
@@ -288,9 +298,8 @@ __device__ __forceinline__ void DequantUnit(const uint4 raw, const float* adj, c
   if (!(big & 0xFF00u)) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint32_t h = (w[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-      const float a = adj[(h + 0x80u) & 0xFFu];   // q + 128
-      out[j] = __fmul_rn(a, __fmul_rn(wt[j], s));
+      const uint32_t idx = ((w[j >> 1] ^ 0x00800080u) >> ((j & 1) * 16)) & 0xFFu;   // (q + 128) for q in [-128, 127]
+      out[j] = __fmul_rn(adj[idx], __fmul_rn(wt[j], s));
     }
   } else {
 #pragma unroll
@@ -339,24 +348,40 @@ __global__ void __launch_bounds__(kRT, 2) ReconRegionTmaKernel(const FrameDev f,
     const uint32_t rn = r + gridDim.x;
     // ---- P0: this region's metadata from registers to shared memory; start fetching the next region's
     // (the previous region's rows must have left the tile before P1 overwrites it)
-    StoreRegionMeta(f, nt, sh, tid, meta, rx, ry);
+    StoreRegionMeta(f, nt, sh, tid, meta, rx, ry, true);
     if (rn < nregions) LoadRegionMeta(f, rn % nrx, rn / nrx, tid, &meta);
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();
-    // lowest frequencies, horizontal half: R[c][cell (oy + ny, ox + kx)] = sum_nx A_bx[kx][nx] * LF[oy + ny][ox + nx]
-    // (one value per thread, computed while the coefficient tile is still in flight; consumed by the column pass)
-    {
+    // lowest frequencies of every block from the LF image (one coefficient per thread, computed while the coefficient
+    // tile is still in flight; the column pass puts them in place):
+    //   coefficient (ky, kx) = sum_ny A_by[ky][ny] * (sum_nx A_bx[kx][nx] * LF[oy + ny][ox + nx])
+    if (tid < 192) {
       const int c = tid >> 6, ci = tid & 63;
       const uint32_t info = sh.cinfo[ci];
-      float rv = 0.0f;
+      float v = 0.0f;
       if (info & kCiValid) {
-        const int ox = (int) ((info >> 8) & 7u), oy = (int) ((info >> 11) & 7u), bx = (int) ((info >> 16) & 15u);
-        const int kxi = (ci & 7) - ox;
-        const float* ax = sh.llf + LlfSharedOffset(FloorLog2((uint32_t) bx)) + kxi * bx;
-        const float* lf = sh.lf[c] + (ci >> 3) * kRegionCells + ox;
-        for (int nx = 0; nx < bx; ++nx) rv += ax[nx] * lf[nx];
+        const int ox = (int) ((info >> 8) & 7u), oy = (int) ((info >> 11) & 7u), bx = (int) ((info >> 16) & 15u), by = (int) ((info >> 20) & 15u);
+        const float* lf = sh.lf[c] + oy * kRegionCells + ox;
+        if (bx == 1 && by == 1) {
+          v = lf[0];
+        } else {
+          const float* ay = sh.llf + LlfSharedOffset(FloorLog2((uint32_t) by)) + ((ci >> 3) - oy) * by;
+          const float* ax = sh.llf + LlfSharedOffset(FloorLog2((uint32_t) bx)) + ((ci & 7) - ox) * bx;
+          for (int ny = 0; ny < by; ++ny) {
+            const float* l = lf + ny * kRegionCells;
+            float rowacc = 0.0f;
+            if (bx == 4) {
+              rowacc += ax[0] * l[0]; rowacc += ax[1] * l[1]; rowacc += ax[2] * l[2]; rowacc += ax[3] * l[3];
+            } else if (bx == 2) {
+              rowacc += ax[0] * l[0]; rowacc += ax[1] * l[1];
+            } else {
+              for (int nx = 0; nx < bx; ++nx) rowacc += ax[nx] * l[nx];
+            }
+            v += ay[ny] * rowacc;
+          }
+        }
       }
-      sh.llf_r[c][ci] = rv;
+      sh.llf_v[c][ci] = v;
     }
     MbarWait(&sh.mbar, parity);
     parity ^= 1;
@@ -411,19 +436,32 @@ __global__ void __launch_bounds__(kRT, 2) ReconRegionTmaKernel(const FrameDev f,
       MbarExpectTx(&sh.mbar, (uint32_t) sizeof(sh.coef));
       TmaLoad3d(&sh.coef[0][0][0], &coef_map, &sh.mbar, (int) ((rn % nrx) * kRegionDim), (int) ((rn / nrx) * kRegionDim), 0);
     }
-    // ---- P3: special 8x8 transforms (disjoint from the DCT blocks) and the column pass
-    {
+    // ---- P3: special 8x8 transforms (disjoint from the DCT blocks) and the column pass.
+    // The passes are split into 12 items (channel, 32 columns, upper / lower half of the rows) of one warp each; the four Y
+    // items go to warps of their own: in most pictures the chroma channels have nothing but their lowest frequencies, so
+    // their (pruned) transforms cost a third of Y's, and a static "channel per warp pair" split would leave four of six
+    // warps waiting at the barrier.
+    const int warp = tid >> 5, lane = tid & 31;
+    // items of this warp: c | g << 2 | h << 3, 0xFF = none
+    const uint32_t items = warp < 4 ? (0xFF00u | (1u | ((uint32_t) (warp >> 1) << 2) | ((uint32_t) (warp & 1) << 3)))
+                                    : ((((uint32_t) (warp & 2)) | ((uint32_t) (warp & 1) << 2) | 8u) << 8) | (((uint32_t) (warp & 2)) | ((uint32_t) (warp & 1) << 2));
+    if (tid < 192) {
       const int c = tid >> 6, ci = tid & 63;
       const uint32_t info = sh.cinfo[ci];
       if ((info & (kCiValid | kCiSpecial)) == (kCiValid | kCiSpecial)) {
         float* rect = sh.tile + c * kTP + (ci >> 3) * 8 * kTS + (ci & 7) * 8;
-        rect[0] = sh.lf[c][ci];
+        rect[0] = sh.llf_v[c][ci];
         SpecialTransform8x8(info & 31u, rect, kTS, nt.afv_basis);
       }
-      const int x = tid & 63;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t it = (items >> (8 * k)) & 0xFFu;
+      if (it == 0xFFu) break;
+      const int c = (int) (it & 3u), x = (int) ((it >> 2) & 1u) * 32 + lane, h = (int) (it >> 3);
       float* col = sh.tile + c * kTP + x;
-      __syncwarp();
-      for (int iy = 0; iy < kRegionCells;) {
+      for (int iy = 4 * h; iy < 4 * h + 4;) {
         const uint32_t inf = sh.cinfo[iy * kRegionCells + (x >> 3)];
         const int by = (int) ((inf >> 20) & 15u);
         if ((inf & (kCiValid | kCiSpecial)) != kCiValid || (int) ((inf >> 11) & 7u) != iy) {
@@ -433,24 +471,25 @@ __global__ void __launch_bounds__(kRT, 2) ReconRegionTmaKernel(const FrameDev f,
         float* p = col + iy * 8 * kTS;
         const int ox = (int) ((inf >> 8) & 7u), bx = (int) ((inf >> 16) & 15u);
         const int kxi = x - ox * 8;
-        const float* llf_col = kxi < bx ? sh.llf_r[c] + iy * kRegionCells + ox + kxi : nullptr;
-        const float* ay = sh.llf + LlfSharedOffset(FloorLog2((uint32_t) by));
+        const float* llf_col = kxi < bx ? sh.llf_v[c] + iy * kRegionCells + ox + kxi : nullptr;
         switch (by) {
-          case 1: ColumnIdct<8>(p, llf_col, ay); break;
-          case 2: ColumnIdct<16>(p, llf_col, ay); break;
-          case 4: ColumnIdct<32>(p, llf_col, ay); break;
-          default: ColumnIdct<64>(p, llf_col, ay); break;
+          case 1: ColumnIdct<8>(p, llf_col); break;
+          case 2: ColumnIdct<16>(p, llf_col); break;
+          case 4: ColumnIdct<32>(p, llf_col); break;
+          default: ColumnIdct<64>(p, llf_col); break;
         }
         iy += by;
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // tile writes of this pass -> visible to the copy engine
     }
     __syncthreads();
-    // ---- P4: row pass; every finished row leaves with one 256-byte bulk store
-    {
-      const int c = tid >> 6, y = tid & 63;
+    // ---- P4: row pass, same items with rows and columns exchanged
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t it = (items >> (8 * k)) & 0xFFu;
+      if (it == 0xFFu) break;
+      const int c = (int) (it & 3u), y = (int) ((it >> 2) & 1u) * 32 + lane, h = (int) (it >> 3);
       float* rowp = sh.tile + c * kTP + y * kTS;
-      for (int ix = 0; ix < kRegionCells;) {
+      for (int ix = 4 * h; ix < 4 * h + 4;) {
         const uint32_t inf = sh.cinfo[(y >> 3) * kRegionCells + ix];
         const int bx = (int) ((inf >> 16) & 15u);
         if ((inf & (kCiValid | kCiSpecial)) != kCiValid || (int) ((inf >> 8) & 7u) != ix) {
@@ -466,10 +505,15 @@ __global__ void __launch_bounds__(kRT, 2) ReconRegionTmaKernel(const FrameDev f,
         }
         ix += bx;
       }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this thread's tile writes -> visible to the copy engine
+    __syncthreads();
+    // every row leaves with one 256-byte bulk store
+    if (tid < 192) {
+      const int c = tid >> 6, y = tid & 63;
       const uint32_t gy = ry * kRegionDim + (uint32_t) y;
       if (gy < f.plane_h) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this thread's tile writes -> visible to the copy engine
-        BulkStoreRow(f.xyb0 + (size_t) c * pplane + (size_t) gy * f.plane_stride + rx * kRegionDim, rowp, kRegionDim * 4);
+        BulkStoreRow(f.xyb0 + (size_t) c * pplane + (size_t) gy * f.plane_stride + rx * kRegionDim, sh.tile + c * kTP + y * kTS, kRegionDim * 4);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
@@ -500,21 +544,21 @@ bool LaunchReconTma(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t
   if (disabled) return false;
   EncodeTiledFn enc = GetEncodeTiled();
   if (!enc) return false;
-  // the kernel stages pool[0, kSmemTableFloats) = quant tables 0 .. 10 (X, Y, B each) in shared memory
+  // the kernels stage pool[0, kSmemTableFloats) = quant tables 0 .. 10 (X, Y, B each) in shared memory
   static const bool layout_ok = GetHostNumericTables().tables.dequant_off[0][0] == 0 && GetHostNumericTables().tables.dequant_off[11][0] == kSmemTableFloats;
   if (!layout_ok) return false;
   if ((reinterpret_cast<uintptr_t>(f.coef) & 15) || (f.coef_stride & 7) || (f.plane_stride & 63) || (f.plane_h & 63) ||
       (reinterpret_cast<uintptr_t>(f.xyb0) & 15))
     return false;
-  CUtensorMap map;
+  CUtensorMap map64;
   const cuuint64_t dims[3] = {f.coef_stride, f.coef_h, 3};
   const cuuint64_t strides[2] = {(cuuint64_t) f.coef_stride * 2, (cuuint64_t) f.coef_stride * 2 * f.coef_h};
-  const cuuint32_t box[3] = {kRegionDim, kRegionDim, 3};
+  const cuuint32_t box64[3] = {kRegionDim, kRegionDim, 3};
   const cuuint32_t estr[3] = {1, 1, 1};
-  if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, f.coef, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+  if (enc(&map64, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, f.coef, dims, strides, box64, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return false;
-  static int ctas_per_launch = 0;
+  static int region_ctas = 0;
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(ReconRegionTmaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ReconSmem));
@@ -525,13 +569,12 @@ bool LaunchReconTma(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ReconRegionTmaKernel, kRT, sizeof(ReconSmem));
     if (per_sm < 1) per_sm = 1;
-    if (const char* e = getenv("JXLB_RECON_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
-    ctas_per_launch = sms * per_sm;
+    region_ctas = sms * per_sm;
   });
   const uint32_t nrx = (f.w8 + kRegionCells - 1) / kRegionCells, nry = (f.h8 + kRegionCells - 1) / kRegionCells;
   const uint32_t nregions = nrx * nry;
-  const uint32_t grid = nregions < (uint32_t) ctas_per_launch ? nregions : (uint32_t) ctas_per_launch;
-  ReconRegionTmaKernel<<<grid, kRT, sizeof(ReconSmem), stream>>>(f, nt_dev, map, nrx, nregions);
+  const uint32_t grid = nregions < (uint32_t) region_ctas ? nregions : (uint32_t) region_ctas;
+  ReconRegionTmaKernel<<<grid, kRT, sizeof(ReconSmem), stream>>>(f, nt_dev, map64, nrx, nregions);
   ++g_launches_ac;
   return true;
 }
