@@ -217,14 +217,25 @@ def run_ours(args):
     dev_s = float(t_dev.item())
     value = world * BATCH * MPIX_PER_IMAGE * args.steps / dev_s
 
-    # ---- end to end through the public batch call: host buffers in, pinned host pixels out.  The reference's entry
-    # points are re-entrant and are called from several app threads at once, so the e2e arm issues its
-    # steps from `callers` host threads, each step one synchronous jxlb_decode_batch call on the whole 64-image batch.
-    # default: 6 caller threads on 1-2 GPUs; fewer per rank on 4 / 8 GPUs, where the ranks share the host's cores and RAM
-    # (every caller keeps 4 GiB of pinned result buffers in the pool)
-    callers = args.callers if args.callers > 0 else (6 if world <= 2 else 4 if world <= 4 else 2)
+    # ---- end to end through the public batch API: host buffers in, pinned host pixels out, every step includes header
+    # parsing, pinned staging, H2D of the codestreams, all kernels and the D2H of every decoded pixel (4 GiB per step).
+    # ONE caller thread keeps `depth` batches in flight with jxlb_decode_batch_submit / _collect (a synchronous call is a
+    # latency chain -- its LF stage alone is ~86 ms of serial entropy chains -- so a single call at a time leaves the GPU
+    # and the PCIe link idle most of the time; the reference's own callers overlap calls from worker pools).
+    depth = max(1, args.depth)
 
     def e2e_steps_run(nsteps):
+        inflight = []
+        for i in range(nsteps):
+            inflight.append(J.PendingBatch(datas, config=2, device=local, keep_native=True))
+            if len(inflight) >= depth:
+                for b in inflight.pop(0).result():
+                    b.free()
+        for p in inflight:
+            for b in p.result():
+                b.free()
+
+    def e2e_sync_run(nsteps, callers):
         nxt = [0]
         lock = threading.Lock()
         errs = []
@@ -236,8 +247,7 @@ def run_ours(args):
                         return
                     nxt[0] += 1
                 try:
-                    res = J.decode_batch(datas, config=2, device=local, keep_native=True)
-                    for b in res:
+                    for b in J.decode_batch(datas, config=2, device=local, keep_native=True):
                         b.free()
                 except Exception as e:  # noqa
                     errs.append(e)
@@ -250,10 +260,10 @@ def run_ours(args):
         if errs:
             raise errs[0]
 
-    e2e_steps_run(2 * callers if args.warmup else 0)  # every decode slot allocates its buffers + pinned pool once
+    e2e_steps_run(2 * depth if args.warmup else 0)  # every decode slot allocates its buffers + pinned pool once
     barrier()
     t1 = time.perf_counter()
-    e2e_steps = max(1, args.steps, 3 * callers)
+    e2e_steps = max(1, args.steps, 4 * depth)
     e2e_steps_run(e2e_steps)
     barrier()
     e2e_wall = time.perf_counter() - t1
@@ -261,6 +271,18 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * MPIX_PER_IMAGE * e2e_steps / float(t_e2e.item())
+    # secondary: plain synchronous jxlb_decode_batch calls from 2 caller threads
+    sync_callers = 2
+    e2e_sync_run(2, sync_callers)
+    barrier()
+    t2 = time.perf_counter()
+    sync_steps = 8
+    e2e_sync_run(sync_steps, sync_callers)
+    barrier()
+    t_sync = torch.tensor([time.perf_counter() - t2], device="cuda")
+    if world > 1:
+        dist.all_reduce(t_sync, op=dist.ReduceOp.MAX)
+    e2e_sync_value = world * BATCH * MPIX_PER_IMAGE * sync_steps / float(t_sync.item())
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -289,8 +311,11 @@ def run_ours(args):
                    "wall_ms_per_step": round(1e3 * wall / steps, 2)},
         "e2e": {"value": round(e2e_value, 1), "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": round(1e3 * float(t_e2e.item()) / e2e_steps, 2),
-                "callers": callers,
-                "api": "jxlb_decode_batch (synchronous, host buffers -> pinned host RGBA), %d concurrent caller threads" % callers},
+                "callers": 1, "in_flight": depth,
+                "pcie_ceiling": "4 GiB of RGBA8 per step over a PCIe Gen5 x16 link measured at 57 GB/s = 75 ms per step = 14.3 GP/s per GPU",
+                "api": "jxlb_decode_batch_submit / _collect (host buffers -> pinned host RGBA), 1 caller thread, %d batches in flight" % depth,
+                "sync_2_callers": {"value": round(e2e_sync_value, 1), "unit": "MP/s", "steps": sync_steps,
+                                   "api": "synchronous jxlb_decode_batch from 2 caller threads"}},
         "gpu_launches": int(launches_per_step * steps),
         "stages_ms_per_step": stages,
         "stages_ms_alone": {k: round(v, 3) for k, v in alone_ms.items()},
@@ -330,8 +355,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--contexts", type=int, default=int(os.environ.get("JXLB_BENCH_CONTEXTS", "6")),
                     help="prepared batches (decode contexts) alternated by the device-resident measurement")
-    ap.add_argument("--callers", type=int, default=int(os.environ.get("JXLB_BENCH_CALLERS", "0")),
-                    help="host threads issuing jxlb_decode_batch calls in the e2e measurement")
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("JXLB_BENCH_DEPTH", "3")),
+                    help="batches the e2e measurement keeps in flight (jxlb_decode_batch_submit / _collect, one caller thread)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -111,6 +111,17 @@ JXLB_API int jxlb_decode_sampled(const uint8_t* data, size_t len, int32_t width,
    (may be NULL).  Returns JXLB_OK when every image decoded. */
 JXLB_API int jxlb_decode_batch(const jxlb_request* reqs, size_t n, jxlb_image* outs, int32_t* status, const jxlb_batch_opts* opts);
 
+/* The same decode, asynchronously.  jxlb_decode_batch_submit parses the requests on the calling thread (the input buffers
+   are copied, as the JNI entry copies its byte array on entry -- JniDecoding.cpp:342-345 -- and may be released when it
+   returns), starts upload / kernels / downloads on a worker thread and returns a handle (NULL on bad arguments or out of
+   memory).  jxlb_decode_batch_collect waits for the batch, fills outs / status exactly like jxlb_decode_batch and frees the
+   handle.  A single-threaded caller keeps the GPU and the PCIe link busy by holding two or three batches in flight:
+   one synchronous call is a latency chain (its LF stage alone is ~86 ms of serial entropy chains, whatever the batch size).
+   Handles may be collected in any order and from any thread; every handle must be collected exactly once. */
+typedef struct jxlb_pending jxlb_pending;
+JXLB_API jxlb_pending* jxlb_decode_batch_submit(const jxlb_request* reqs, size_t n, const jxlb_batch_opts* opts);
+JXLB_API int jxlb_decode_batch_collect(jxlb_pending* pending, jxlb_image* outs, int32_t* status);
+
 /* JxlCoder.getSize: JXLB_OK and (*width, *height), or JXLB_NOT_JXL / JXLB_INVALID_JXL ("null" in the reference). */
 JXLB_API int jxlb_get_size(const uint8_t* data, size_t len, uint32_t* width, uint32_t* height);
 

@@ -7,8 +7,8 @@ machine without the built library, or decoding without a CUDA device, raises —
 """
 from .api import (Bitmap, InvalidJXLException, InvalidImageSizeException, JxlAnimatedImage, JxlCoder, JxlCoderError,
                   JxlResizeFilter, PreferredColorConfig, ScaleMode, UnsupportedJXLException, decode_batch, kernel_launches,
-                  last_batch_timings, lib_path, load_library, PreparedBatch)
+                  last_batch_timings, lib_path, load_library, PendingBatch, PreparedBatch)
 
 __all__ = ["Bitmap", "InvalidJXLException", "InvalidImageSizeException", "JxlAnimatedImage", "JxlCoder", "JxlCoderError",
            "JxlResizeFilter", "PreferredColorConfig", "ScaleMode", "UnsupportedJXLException", "decode_batch", "kernel_launches",
-           "last_batch_timings", "lib_path", "load_library", "PreparedBatch"]
+           "last_batch_timings", "lib_path", "load_library", "PendingBatch", "PreparedBatch"]

@@ -94,6 +94,9 @@ def load_library():
     L = C.CDLL(p)
     L.jxlb_decode_sampled.argtypes = [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_Image)]
     L.jxlb_decode_batch.argtypes = [C.POINTER(_Request), C.c_size_t, C.POINTER(_Image), C.POINTER(C.c_int32), C.POINTER(_BatchOpts)]
+    L.jxlb_decode_batch_submit.restype = C.c_void_p
+    L.jxlb_decode_batch_submit.argtypes = [C.POINTER(_Request), C.c_size_t, C.POINTER(_BatchOpts)]
+    L.jxlb_decode_batch_collect.argtypes = [C.c_void_p, C.POINTER(_Image), C.POINTER(C.c_int32)]
     L.jxlb_get_size.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.jxlb_image_free.argtypes = [C.POINTER(_Image)]
     L.jxlb_anim_open.restype = C.c_void_p
@@ -204,6 +207,44 @@ def decode_batch(datas, width=-1, height=-1, config=PreferredColorConfig.DEFAULT
         else:
             res.append(Bitmap(outs[i], keep_native=keep_native))
     return res
+
+
+class PendingBatch:
+    """jxlb_decode_batch_submit / _collect: submit() returns at once (the inputs have been copied), result() waits and
+    returns the list of Bitmap.  Keep two or three in flight to overlap the batches on the GPU."""
+
+    def __init__(self, datas, width=-1, height=-1, config=PreferredColorConfig.DEFAULT, scale_mode=ScaleMode.FIT,
+                 filt=JxlResizeFilter.MITCHELL_NETRAVALI, api_level=34, device=-1, output_device=-1, keep_native=False):
+        L = load_library()
+        self.n = len(datas)
+        self.keep_native = keep_native
+        bufs = [_as_buffer(d) for d in datas]
+        reqs = (_Request * self.n)()
+        for i, (b, ln) in enumerate(bufs):
+            reqs[i] = _Request(C.cast(b, C.c_void_p), ln, width, height, int(config), int(scale_mode), int(filt))
+        opts = _BatchOpts(api_level, output_device, device, 0)
+        self.h = L.jxlb_decode_batch_submit(reqs, self.n, C.byref(opts))
+        if not self.h:
+            raise JxlCoderError(5, "jxlb_decode_batch_submit failed")
+
+    def result(self, raise_on_error=True):
+        L = load_library()
+        outs = (_Image * self.n)()
+        st = (C.c_int32 * self.n)()
+        L.jxlb_decode_batch_collect(self.h, outs, st)
+        self.h = None
+        res = []
+        for i in range(self.n):
+            if st[i] != 0:
+                if raise_on_error:
+                    for j in range(self.n):
+                        if st[j] == 0:
+                            L.jxlb_image_free(C.byref(outs[j]))
+                    _raise(st[i], outs[i].message.decode(errors="replace"))
+                res.append(JxlCoderError(st[i], outs[i].message.decode(errors="replace")))
+            else:
+                res.append(Bitmap(outs[i], keep_native=self.keep_native))
+        return res
 
 
 class JxlCoder:

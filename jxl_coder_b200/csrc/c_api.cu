@@ -71,6 +71,47 @@ int jxlb_decode_batch(const jxlb_request* reqs, size_t n, jxlb_image* outs, int3
   }
 }
 
+struct jxlb_pending {
+  jxlb::PendingBatch* p;
+  size_t n;
+};
+
+jxlb_pending* jxlb_decode_batch_submit(const jxlb_request* reqs, size_t n, const jxlb_batch_opts* opts) {
+  if (!reqs || !n) return nullptr;
+  jxlb_batch_opts o{0, -1, -1, 0};
+  if (opts) o = *opts;
+  try {
+    jxlb::PendingBatch* p = SubmitBatch(reqs, n, o.api_level, o.device, o.output_device);
+    return new jxlb_pending{p, n};
+  } catch (...) {
+    return nullptr;
+  }
+}
+
+int jxlb_decode_batch_collect(jxlb_pending* h, jxlb_image* outs, int32_t* status) {
+  if (!h || !outs) return JXLB_BAD_ARG;
+  const size_t n = h->n;
+  try {
+    std::vector<DecodedImage> res;
+    BatchTimings tm;
+    const int rc = CollectBatch(h->p, &res, &tm);
+    delete h;
+    {
+      std::lock_guard<std::mutex> l(g_tm_mu);
+      g_last_timings = tm;
+    }
+    for (size_t i = 0; i < n; ++i) {
+      FillImage(res[i], &outs[i]);
+      if (status) status[i] = res[i].status;
+    }
+    return rc;
+  } catch (const std::bad_alloc&) {
+    return FailAll(outs, status, n, JXLB_OOM, "Not enough memory to decode this image");
+  } catch (...) {
+    return FailAll(outs, status, n, JXLB_ERROR, "Error while decoding");
+  }
+}
+
 int jxlb_decode_sampled(const uint8_t* data, size_t len, int32_t width, int32_t height, int32_t color_config, int32_t scale_mode,
                         int32_t filter, int32_t api_level, jxlb_image* out) {
   if (!out) return JXLB_BAD_ARG;

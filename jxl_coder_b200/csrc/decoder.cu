@@ -49,10 +49,24 @@ size_t Align256(size_t v) { return (v + 255) & ~(size_t) 255; }
 
 // Runs fn(i) for i in [0, n) on up to hardware_concurrency host threads (header parsing and staging of a batch are
 // independent per image).
+// Host threads one call may use: the machine's cores divided among the processes of a multi-GPU job (one process per GPU
+// under torchrun: LOCAL_WORLD_SIZE / WORLD_SIZE), so that 8 ranks do not run 8 x nproc parser threads on the same
+// cores; JXLB_HOST_THREADS overrides.
+size_t HostThreads() {
+  static const size_t v = [] {
+    if (const char* e = getenv("JXLB_HOST_THREADS")) return (size_t) std::max(1, atoi(e));
+    unsigned hw = std::thread::hardware_concurrency();
+    if (!hw) hw = 4;
+    int world = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) world = std::max(1, atoi(e));
+    else if (const char* e2 = getenv("WORLD_SIZE")) world = std::max(1, atoi(e2));
+    return (size_t) std::max(2u, hw / (unsigned) world);
+  }();
+  return v;
+}
 template <class Fn>
 void ParallelFor(size_t n, Fn fn) {
-  unsigned hw = std::thread::hardware_concurrency();
-  size_t nt = std::min<size_t>(n, hw ? hw : 4);
+  size_t nt = std::min<size_t>(n, HostThreads());
   if (nt <= 1) {
     for (size_t i = 0; i < n; ++i) fn(i);
     return;
@@ -111,6 +125,7 @@ struct HostPool {
     if (it != free_list.end() && it->first <= n + n / 4 + 4096) {
       void* p = it->second;
       live[p] = it->first;
+      free_bytes -= it->first;
       free_list.erase(it);
       return p;
     }
@@ -119,12 +134,34 @@ struct HostPool {
     live[p] = n;
     return p;
   }
+  // Freed buffers are kept for reuse up to a cap (JXLB_PINNED_POOL_MB, default 12 GiB: three 64 x 4096^2 RGBA8 batches);
+  // beyond it the largest idle buffers go back to the driver, so a long-running process decoding varied sizes does not
+  // accumulate page-locked memory without bound.
+  size_t free_bytes = 0;
+  static size_t Cap() {
+    static const size_t v = [] {
+      const char* e = getenv("JXLB_PINNED_POOL_MB");
+      return (size_t) (e ? std::max(0, atoi(e)) : 12288) << 20;
+    }();
+    return v;
+  }
   bool Put(void* p) {
-    std::lock_guard<std::mutex> l(mu);
-    auto it = live.find(p);
-    if (it == live.end()) return false;
-    free_list.emplace(it->second, p);
-    live.erase(it);
+    std::vector<void*> drop;
+    {
+      std::lock_guard<std::mutex> l(mu);
+      auto it = live.find(p);
+      if (it == live.end()) return false;
+      free_list.emplace(it->second, p);
+      free_bytes += it->second;
+      live.erase(it);
+      while (free_bytes > Cap() && !free_list.empty()) {
+        auto big = std::prev(free_list.end());
+        free_bytes -= big->first;
+        drop.push_back(big->second);
+        free_list.erase(big);
+      }
+    }
+    for (void* d : drop) cudaFreeHost(d);
     return true;
   }
 };
@@ -144,7 +181,7 @@ struct BatchBuffers {
 // latency-bound LF stage of one call overlaps the throughput kernels and the downloads of another.
 struct Slot {
   std::mutex mu;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, lf_stream = nullptr;
   BatchBuffers spare;
 };
 constexpr int kSlots = 8;
@@ -171,6 +208,7 @@ struct DeviceContext {
   int lf_tokens_e2e = 2;  // jxlb_decode_batch: staggering also spreads the result downloads over the PCIe link
   cudaEvent_t origin = nullptr;  // JXLB_TIMELINE=1: stage boundaries of every run are printed relative to this event
   bool timeline = false;
+  int lf_priority = 0;
   NumericTables* nt_dev = nullptr;
   NaturalOrders nat_dev{};
   bool ready = false;
@@ -178,10 +216,14 @@ struct DeviceContext {
   void Init(int dev) {
     device = dev;
     CUDA_OK(cudaSetDevice(dev));
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (Slot& sl : slots) {
       CUDA_OK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
       CUDA_OK(cudaStreamCreateWithFlags(&sl.copy_stream, cudaStreamNonBlocking));
+      CUDA_OK(cudaStreamCreateWithPriority(&sl.lf_stream, cudaStreamNonBlocking, prio_hi));
     }
+    lf_priority = prio_hi;
     for (auto& e : lf_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (const char* e = getenv("JXLB_LF_TOKENS")) lf_tokens = std::max(0, atoi(e));  // 0 = no staggering
     if (const char* e = getenv("JXLB_LF_TOKENS_E2E")) lf_tokens_e2e = std::max(0, atoi(e));
@@ -544,6 +586,10 @@ struct Batch {
   BatchBuffers* buf = nullptr;
   // streams: a slot's (one-shot decodes) or the batch's own (prepared batches, so that two prepared batches overlap)
   cudaStream_t stream = nullptr, copy_stream = nullptr;
+  // The LF stage runs on a stream of its own at the highest priority: its CTAs (one SM each, see LfGroupKernel) are placed
+  // as soon as an SM drains instead of queueing behind the dense kernels of the batches in flight.
+  cudaStream_t lf_stream = nullptr;
+  cudaEvent_t ev_uploaded = nullptr, ev_lf_done = nullptr;
   bool own_streams = false;
   std::mutex mu;              // serialises Run / Finish / Fetch on this batch
   // Event sets: ev = the set of the current run.  Asynchronous runs (RunBatch(sync = false)) rotate through kEventSets
@@ -587,7 +633,10 @@ struct Batch {
     if (own_streams) {
       if (stream) cudaStreamDestroy(stream);
       if (copy_stream) cudaStreamDestroy(copy_stream);
+      if (lf_stream) cudaStreamDestroy(lf_stream);
     }
+    if (ev_uploaded) cudaEventDestroy(ev_uploaded);
+    if (ev_lf_done) cudaEventDestroy(ev_lf_done);
     for (auto& e : img_ev)
       if (e) cudaEventDestroy(e);
     for (void* h : host_dst)
@@ -759,7 +808,12 @@ struct Batch {
     if (!stream) {
       CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
       CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+      CUDA_OK(cudaStreamCreateWithPriority(&lf_stream, cudaStreamNonBlocking, ctx->lf_priority));
       own_streams = true;
+    }
+    if (!ev_uploaded) {
+      CUDA_OK(cudaEventCreateWithFlags(&ev_uploaded, cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&ev_lf_done, cudaEventDisableTiming));
     }
     cudaStream_t s = stream;
     const size_t lf_scratch = Align256(sl_lf.bytes_per_job * jobs_lf.size());
@@ -859,28 +913,29 @@ struct Batch {
       span_armed = false;
     }
     CUDA_OK(cudaEventRecord(ev[2], s));
+    // everything enqueued on `s` so far (the upload, the previous run) precedes the LF stage
+    CUDA_OK(cudaEventRecord(ev_uploaded, s));
+    CUDA_OK(cudaStreamWaitEvent(lf_stream, ev_uploaded, 0));
     for (size_t i = 0; i < n; ++i) {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
       uint8_t* wb = buf->work_buf.p + p.work_off;
-      CUDA_OK(cudaMemsetAsync(wb + p.plan.off_status, 0xFF, (size_t) p.plan.num_streams * 4, s));
+      CUDA_OK(cudaMemsetAsync(wb + p.plan.off_status, 0xFF, (size_t) p.plan.num_streams * 4, lf_stream));
+    }
+    LaunchLfGroups(frames_d, jobs_lf_d, (uint32_t) jobs_lf.size(), sl_lf, lf_stream);
+    CUDA_OK(cudaEventRecord(ev_lf_done, lf_stream));
+    // meanwhile, on the dense stream: clear the coefficient planes
+    for (size_t i = 0; i < n; ++i) {
+      Parsed& p = ps[i];
+      if (p.status != JXLB_OK) continue;
+      uint8_t* wb = buf->work_buf.p + p.work_off;
       if (p.plan.coef_bytes) {
         if (p.plan.coef_bytes % 16 == 0) LaunchFill(wb + p.plan.off_coef, p.plan.coef_bytes, 0u, s);
         else CUDA_OK(cudaMemsetAsync(wb + p.plan.off_coef, 0, p.plan.coef_bytes, s));
       }
     }
+    CUDA_OK(cudaStreamWaitEvent(s, ev_lf_done, 0));
     LaunchSingleSectionFrames(frames_d, jobs_single_d, (uint32_t) jobs_single.size(), ctx->nat_dev, sl_single, s);
-    const int tokens = host_dst.empty() ? ctx->lf_tokens : ctx->lf_tokens_e2e;
-    if (!jobs_lf.empty() && tokens > 0) {
-      std::lock_guard<std::mutex> l(ctx->mu);
-      const uint64_t k = ctx->lf_count++;
-      if (k >= (uint64_t) tokens)
-        CUDA_OK(cudaStreamWaitEvent(s, ctx->lf_ev[(k - tokens) % DeviceContext::kLfEvents], 0));
-      LaunchLfGroups(frames_d, jobs_lf_d, (uint32_t) jobs_lf.size(), sl_lf, s);
-      CUDA_OK(cudaEventRecord(ctx->lf_ev[k % DeviceContext::kLfEvents], s));
-    } else {
-      LaunchLfGroups(frames_d, jobs_lf_d, (uint32_t) jobs_lf.size(), sl_lf, s);
-    }
     CUDA_OK(cudaEventRecord(ev[3], s));
     LaunchPassGroups(frames_d, jobs_groups_d, (uint32_t) jobs_groups.size(), ctx->nat_dev, sl_grp, s);
     LaunchBuildGroupBlocks(frames_d, jobs_lane_groups_d, (uint32_t) jobs_lane_groups.size(), s);
@@ -1221,15 +1276,11 @@ void CopyStatuses(const Batch& b, std::vector<DecodedImage>* out, int* overall) 
 }
 }  // namespace
 
-int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device, std::vector<DecodedImage>* out,
-                BatchTimings* timings, const int32_t* frame_index) {
+// Device half of a decode call: slot, upload, kernels, downloads, per-image statuses.  `b` has been parsed.
+static int DeviceDecode(Batch& b, int device, int output_device, std::vector<DecodedImage>* out, BatchTimings* timings, double parse_ms) {
   using Clock = std::chrono::steady_clock;
   const auto t0 = Clock::now();
   auto ms_since = [&](Clock::time_point a) { return std::chrono::duration<double, std::milli>(Clock::now() - a).count(); };
-  out->assign(n, DecodedImage());
-  Batch b;
-  b.Parse(reqs, n, api_level, frame_index);
-  const double parse_ms = ms_since(t0);
   int overall = JXLB_OK;
   if (!b.AnyOk()) {
     CopyStatuses(b, out, &overall);
@@ -1249,6 +1300,7 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
   const double slot_ms = ms_since(t1);
   b.stream = slot->stream;
   b.copy_stream = slot->copy_stream;
+  b.lf_stream = slot->lf_stream;
   try {
     const auto t2 = Clock::now();
     b.Upload(&slot->spare);
@@ -1261,8 +1313,8 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
     b.Finish(output_device < 0, output_device, out);
     if (b.ctx->timeline)
       fprintf(stderr, "[host] decode_batch n=%zu: parse %.1f  slot wait %.1f  stage+upload %.1f  launch %.1f  finish(wait) %.1f  total %.1f ms | device: "
-              "upload %.1f lf %.1f groups %.1f recon-phase %.1f download-tail %.1f kernels %.1f\n", n,
-              parse_ms, slot_ms, upload_ms, launch_ms, ms_since(t4), ms_since(t0), b.stage_ms[0], b.stage_ms[1], b.stage_ms[2], b.stage_ms[3],
+              "upload %.1f lf %.1f groups %.1f recon-phase %.1f download-tail %.1f kernels %.1f\n", b.n,
+              parse_ms, slot_ms, upload_ms, launch_ms, ms_since(t4), parse_ms + ms_since(t0), b.stage_ms[0], b.stage_ms[1], b.stage_ms[2], b.stage_ms[3],
               b.stage_ms[6], b.stage_ms[7]);
     if (timings) *timings = b.tm;
   } catch (CudaError& e) {
@@ -1278,6 +1330,53 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
   }
   CopyStatuses(b, out, &overall);
   return overall;
+}
+
+int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device, std::vector<DecodedImage>* out,
+                BatchTimings* timings, const int32_t* frame_index) {
+  using Clock = std::chrono::steady_clock;
+  const auto t0 = Clock::now();
+  out->assign(n, DecodedImage());
+  Batch b;
+  b.Parse(reqs, n, api_level, frame_index);
+  const double parse_ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+  return DeviceDecode(b, device, output_device, out, timings, parse_ms);
+}
+
+// ---- submit / collect: the same decode, with the device half on a worker thread -----------------------------------------
+// One synchronous call is a latency chain (parse -> upload -> LF stage, ~86 ms of serial entropy chains whatever the batch
+// size -> AC -> reconstruction overlapped with the downloads): alone it leaves the GPU and the PCIe link idle most of the
+// time.  The reference's entry points are re-entrant and its callers (Glide / Coil worker pools) overlap calls; a caller
+// with ONE thread gets the same overlap by submitting a few batches and collecting them in order.  The input buffers
+// are only read inside SubmitBatch (parse copies the codestreams, as the JNI entry copies its byte array on entry).
+struct PendingBatch {
+  Batch b;
+  std::vector<DecodedImage> out;
+  BatchTimings tm;
+  int rc = JXLB_OK;
+  std::thread worker;
+};
+
+PendingBatch* SubmitBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device) {
+  using Clock = std::chrono::steady_clock;
+  const auto t0 = Clock::now();
+  std::unique_ptr<PendingBatch> p(new PendingBatch());
+  p->out.assign(n, DecodedImage());
+  p->b.Parse(reqs, n, api_level, nullptr);
+  const double parse_ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+  PendingBatch* raw = p.get();
+  p->worker = std::thread([raw, device, output_device, parse_ms]() { raw->rc = DeviceDecode(raw->b, device, output_device, &raw->out, &raw->tm, parse_ms); });
+  return p.release();
+}
+
+int CollectBatch(PendingBatch* p, std::vector<DecodedImage>* out, BatchTimings* timings) {
+  if (!p) return JXLB_BAD_ARG;
+  if (p->worker.joinable()) p->worker.join();
+  *out = std::move(p->out);
+  if (timings) *timings = p->tm;
+  const int rc = p->rc;
+  delete p;
+  return rc;
 }
 
 // ---- prepared batches (throughput interface: inputs resident in HBM, results left in HBM) --------------------------------

@@ -34,6 +34,13 @@ int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, i
 
 void FreeImageMemory(void* data, int device);
 
+// Asynchronous form of DecodeBatch: SubmitBatch parses the requests (the input buffers may be released when it returns),
+// starts the device half on a worker thread and returns a handle; CollectBatch waits for it, hands over the results and
+// frees the handle.  Several submitted batches overlap on the GPU like concurrent DecodeBatch calls do.
+struct PendingBatch;
+PendingBatch* SubmitBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device);
+int CollectBatch(PendingBatch* p, std::vector<DecodedImage>* out, BatchTimings* timings);
+
 }  // namespace jxlb
 
 // ---- prepared batches: parse + upload once ("inputs resident in HBM"), then run the kernels any number of times with

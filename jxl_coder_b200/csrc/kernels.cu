@@ -152,15 +152,24 @@ __device__ int PlaceBlocksWarp(const FrameDev& f, uint32_t lfg, uint32_t* bitmap
   return kOk;
 }
 
-__global__ void __launch_bounds__(kStreamBlockThreads) LfGroupKernel(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs,
-                                                                     ScratchLayout scratch, int warp_place) {
-  const uint32_t j = blockIdx.x;
+// kLfWarps LF groups per CTA, one warp each.  The CTA is sized to take a whole SM for itself (12 warps x 168 registers fill
+// the register file, 12 x 15.5 KB of row buffers most of the shared memory): the LF stage is a set of serial dependency
+// chains that leave an SM's issue slots almost idle, and when its warps were spread one or two per SM over the whole GPU
+// they competed for issue slots with the dense kernels of the other batches in flight -- the chains ran 45 % slower and
+// the dense kernels lost throughput too.  Packed, a 64-image batch's 256 chains hold 22 SMs at ~3 warps per scheduler
+// (each warp issues once every ~3 cycles: the schedulers are full) and the other 126 SMs run the dense kernels undisturbed.
+constexpr int kLfWarps = 12;
+__global__ void __launch_bounds__(kLfWarps * 32, 1) LfGroupKernel(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs,
+                                                                  ScratchLayout scratch, int warp_place) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t j = blockIdx.x * kLfWarps + warp;
   if (j >= njobs) return;
   const StreamJob job = jobs[j];
   const FrameDev& f = frames[job.frame];
-  extern __shared__ __align__(16) uint8_t lf_smem[];
+  extern __shared__ __align__(16) uint8_t lf_smem_all[];
+  uint8_t* lf_smem = lf_smem_all + (size_t) warp * (kLfFastCodeBytes + kLfFastInts * 4);
   int st = kOk;
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     StreamScratch sc = CarveScratch(scratch, j, nullptr, nullptr);
     sc.fast = lf_smem;
     sc.fast_code_bytes = kLfFastCodeBytes;
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(kStreamBlockThreads) LfGroupKernel(const Frame
   __syncwarp();
   st = __shfl_sync(0xFFFFFFFFu, st, 0);
   if (st == kOk && warp_place) st = PlaceBlocksWarp(f, job.index, reinterpret_cast<uint32_t*>(lf_smem));
-  if (threadIdx.x == 0) f.status[job.status_slot] = st;
+  if (lane == 0) f.status[job.status_slot] = st;
 }
 
 __global__ void __launch_bounds__(kStreamBlockThreads) PassGroupKernel(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs,
@@ -347,7 +356,7 @@ void LaunchSingleSectionFrames(const FrameDev* frames, const StreamJob* jobs, ui
 }
 void LaunchLfGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, ScratchLayout scratch, cudaStream_t stream) {
   if (!njobs) return;
-  const int smem = (int) (kLfFastCodeBytes + kLfFastInts * 4);
+  const int smem = (int) (kLfWarps * (kLfFastCodeBytes + kLfFastInts * 4));
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(LfGroupKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -357,7 +366,7 @@ void LaunchLfGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njob
     configured = true;
   }
   static const int warp_place = getenv("JXLB_SERIAL_PLACEMENT") == nullptr;
-  LfGroupKernel<<<njobs, kStreamBlockThreads, smem, stream>>>(frames, jobs, njobs, scratch, warp_place);
+  LfGroupKernel<<<(njobs + kLfWarps - 1) / kLfWarps, kLfWarps * 32, smem, stream>>>(frames, jobs, njobs, scratch, warp_place);
   ++g_launches;
 }
 void LaunchPassGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat, ScratchLayout scratch,

@@ -553,3 +553,24 @@ def test_epf_active_everywhere(J, ref, epf):
     got = J.JxlCoder.decode(data, 2).as_array()
     d = np.abs(got[..., :3].astype(int) - want[..., :3].astype(int))
     assert d.max() <= 1 and (d == 0).mean() > 0.985, (d.max(), (d == 0).mean())
+
+
+def test_submit_collect_matches_sync_call(J, ref):
+    """jxlb_decode_batch_submit / _collect: three batches in flight from one thread, inputs released right after submit,
+    results identical to the synchronous call and within the lossy bound of the reference."""
+    datas = [cases.get(n) for n in cases.SMALL[:6]]
+    sync = [b.pixels.copy() for b in J.decode_batch(datas, config=2)]
+    pend = []
+    for k in range(3):
+        copies = [bytes(bytearray(d)) for d in datas]
+        pend.append(J.PendingBatch(copies, config=2))
+        del copies
+    for p in pend:
+        res = p.result()
+        assert len(res) == len(datas)
+        for got, want in zip(res, sync):
+            assert (got.pixels == want).all()
+    # errors stay per image
+    p = J.PendingBatch([datas[0], b"not a jxl file", datas[1]], config=2)
+    res = p.result(raise_on_error=False)
+    assert isinstance(res[1], J.JxlCoderError) and not isinstance(res[0], Exception) and not isinstance(res[2], Exception)
