@@ -355,7 +355,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--contexts", type=int, default=int(os.environ.get("JXLB_BENCH_CONTEXTS", "6")),
                     help="prepared batches (decode contexts) alternated by the device-resident measurement")
-    ap.add_argument("--depth", type=int, default=int(os.environ.get("JXLB_BENCH_DEPTH", "3")),
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("JXLB_BENCH_DEPTH", "5")),
                     help="batches the e2e measurement keeps in flight (jxlb_decode_batch_submit / _collect, one caller thread)")
     args = ap.parse_args()
     if args.impl == "reference":

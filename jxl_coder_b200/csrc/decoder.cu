@@ -85,7 +85,7 @@ void ParallelFor(size_t n, Fn fn) {
   for (auto& t : ths) t.join();
 }
 constexpr size_t kMaxImageDeviceBytes = (size_t) 48 << 30;  // device planes of ONE image (a B200 has 180 GB)
-constexpr uint32_t kMaxAcSmemCode = 208u << 10;  // AC code blobs up to this size are staged in shared memory
+constexpr uint32_t kMaxAcSmemCode = 196u << 10;  // AC code blobs up to this size are staged in shared memory (+ 24 KB of context rows per CTA)
 
 struct DevBuffer {
   uint8_t* p = nullptr;
@@ -134,14 +134,14 @@ struct HostPool {
     live[p] = n;
     return p;
   }
-  // Freed buffers are kept for reuse up to a cap (JXLB_PINNED_POOL_MB, default 12 GiB: three 64 x 4096^2 RGBA8 batches);
+  // Freed buffers are kept for reuse up to a cap (JXLB_PINNED_POOL_MB, default 40 GiB: the idle sets of a few 64 x 4096^2 RGBA8 batches in flight);
   // beyond it the largest idle buffers go back to the driver, so a long-running process decoding varied sizes does not
   // accumulate page-locked memory without bound.
   size_t free_bytes = 0;
   static size_t Cap() {
     static const size_t v = [] {
       const char* e = getenv("JXLB_PINNED_POOL_MB");
-      return (size_t) (e ? std::max(0, atoi(e)) : 12288) << 20;
+      return (size_t) (e ? std::max(0, atoi(e)) : 40960) << 20;
     }();
     return v;
   }
@@ -191,21 +191,35 @@ struct DeviceContext {
   std::mutex mu;  // guards lazily created state below
   Slot slots[kSlots];
   std::atomic<uint32_t> next_slot{0};
-  // LF-stage tokens (JXLB_LF_TOKENS=n for prepared batches, default 0 = off; JXLB_LF_TOKENS_E2E=n for jxlb_decode_batch,
-  // default 2).  The LF-group kernel is latency-bound (one lane per 2048x2048
-  // LF group) and leaves the GPU almost idle.  With n > 0 each Run() waits for the LF stage issued n launches earlier
-  // before starting its own, which STAGGERS the batches in flight on different streams (one runs its LF stage while the
-  // others run their throughput kernels).  Measured on B200 (profiles/r1c_overlap_notes.txt): the LF warps then lose
-  // ~45 % of their speed to issue-slot contention with the dense kernels sharing their SM sub-partitions, and the
-  // default -- several batches entering their LF stage together, then sharing the GPU for the dense stages -- wins when
-  // the results stay in HBM.  With host outputs the picture flips: batches in lockstep also finish together and their
-  // 4 GiB downloads pile up on the PCIe link after the kernels, while two tokens keep the link busy throughout
-  // (e2e 143 -> 117 ms per 64-image step with 6 callers).
-  static constexpr int kLfEvents = 32;
-  cudaEvent_t lf_ev[kLfEvents]{};
-  uint64_t lf_count = 0;
-  int lf_tokens = 0;      // prepared batches (results stay in HBM)
-  int lf_tokens_e2e = 2;  // jxlb_decode_batch: staggering also spreads the result downloads over the PCIe link
+  // Stage gates.  The batches in flight on one GPU (concurrent jxlb_decode_batch calls, submitted batches, prepared
+  // batches run asynchronously) would otherwise move in lockstep -- all in their LF stage together, then all in their
+  // downloads together, with the PCIe link idle in between.  Each of the three stages of a run (LF sections / AC sections /
+  // per-image reconstruction + downloads) admits a fixed number of batches at a time: a run enqueues, in front of the
+  // stage, a wait for the end-of-stage event of the run that entered it `tokens` runs earlier.  The batches then spread
+  // out into a software pipeline: while one reconstructs and downloads, the next decodes its AC sections and two more
+  // run their LF chains (those hold 32 SMs each, see LfGroupKernel).  JXLB_STAGE_TOKENS="lf,ac,recon" (0 = no gate).
+  struct StageGate {
+    static constexpr int kRing = 64;
+    cudaEvent_t ev[kRing]{};
+    uint64_t count = 0;
+    int tokens = 0;
+    void Init(int t) {
+      tokens = t;
+      for (auto& e : ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // Both are called with DeviceContext::mu held for the whole enqueue of a run, so the record of run k is always
+    // enqueued before the wait of run k + tokens.
+    uint64_t Enter(cudaStream_t s) {
+      const uint64_t k = count++;
+      if (tokens > 0 && k >= (uint64_t) tokens) CUDA_OK(cudaStreamWaitEvent(s, ev[(k - tokens) % kRing], 0));
+      return k;
+    }
+    void Leave(uint64_t k, cudaStream_t s) { CUDA_OK(cudaEventRecord(ev[k % kRing], s)); }
+  };
+  StageGate gate_lf, gate_ac, gate_recon;
+  // One stream carries every device-to-host copy of result pixels on this GPU: measured on B200 / PCIe Gen5 (tests/gpu_pcie2.py),
+  // 64 MiB copies into pinned buffers reach 48.5 GB/s from one or two streams and only 39 GB/s when four streams interleave.
+  cudaStream_t d2h_stream = nullptr;
   cudaEvent_t origin = nullptr;  // JXLB_TIMELINE=1: stage boundaries of every run are printed relative to this event
   bool timeline = false;
   int lf_priority = 0;
@@ -224,9 +238,14 @@ struct DeviceContext {
       CUDA_OK(cudaStreamCreateWithPriority(&sl.lf_stream, cudaStreamNonBlocking, prio_hi));
     }
     lf_priority = prio_hi;
-    for (auto& e : lf_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    if (const char* e = getenv("JXLB_LF_TOKENS")) lf_tokens = std::max(0, atoi(e));  // 0 = no staggering
-    if (const char* e = getenv("JXLB_LF_TOKENS_E2E")) lf_tokens_e2e = std::max(0, atoi(e));
+    CUDA_OK(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
+    {
+      int t[3] = {2, 1, 1};
+      if (const char* e = getenv("JXLB_STAGE_TOKENS")) sscanf(e, "%d,%d,%d", &t[0], &t[1], &t[2]);
+      gate_lf.Init(t[0]);
+      gate_ac.Init(t[1]);
+      gate_recon.Init(t[2]);
+    }
     timeline = getenv("JXLB_TIMELINE") != nullptr;
     CUDA_OK(cudaEventCreate(&origin));
     CUDA_OK(cudaEventRecord(origin, slots[0].stream));
@@ -746,8 +765,8 @@ struct Batch {
         }
         if (lane) {
           for (uint32_t g = 0; g < f.num_groups; ++g) jobs_lane_groups.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, 0});
-          for (uint32_t g0 = 0; g0 < f.num_groups; g0 += 128)
-            jobs_ac_cta.push_back(AcCtaJob{frame_of[i], g0, std::min(128u, f.num_groups - g0), 0});
+          for (uint32_t g0 = 0; g0 < f.num_groups; g0 += AcGroupsPerCta())
+            jobs_ac_cta.push_back(AcCtaJob{frame_of[i], g0, std::min(AcGroupsPerCta(), f.num_groups - g0), 0});
           if (f.num_mod_channels > f.global_mod_decoded)
             for (uint32_t g = 0; g < f.num_groups; ++g) jobs_lane_mod.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, 0});
         } else {
@@ -902,6 +921,7 @@ struct Batch {
   void Run() {
     CUDA_OK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream;
+    std::lock_guard<std::mutex> enqueue_lock(ctx->mu);  // runs are enqueued one at a time (stage gates, DeviceContext)
     if (pending_runs >= kEventSets) CollectRuns();  // the ring is full: drain (synchronises)
     if (pending_runs > 0) {                          // keep the upload events of set 0 readable from every set
       run_index = (run_index + 1) % kEventSets;
@@ -922,7 +942,11 @@ struct Batch {
       uint8_t* wb = buf->work_buf.p + p.work_off;
       CUDA_OK(cudaMemsetAsync(wb + p.plan.off_status, 0xFF, (size_t) p.plan.num_streams * 4, lf_stream));
     }
-    LaunchLfGroups(frames_d, jobs_lf_d, (uint32_t) jobs_lf.size(), sl_lf, lf_stream);
+    {
+      const uint64_t k = ctx->gate_lf.Enter(lf_stream);
+      LaunchLfGroups(frames_d, jobs_lf_d, (uint32_t) jobs_lf.size(), sl_lf, lf_stream);
+      ctx->gate_lf.Leave(k, lf_stream);
+    }
     CUDA_OK(cudaEventRecord(ev_lf_done, lf_stream));
     // meanwhile, on the dense stream: clear the coefficient planes
     for (size_t i = 0; i < n; ++i) {
@@ -937,12 +961,15 @@ struct Batch {
     CUDA_OK(cudaStreamWaitEvent(s, ev_lf_done, 0));
     LaunchSingleSectionFrames(frames_d, jobs_single_d, (uint32_t) jobs_single.size(), ctx->nat_dev, sl_single, s);
     CUDA_OK(cudaEventRecord(ev[3], s));
+    const uint64_t k_ac = ctx->gate_ac.Enter(s);
     LaunchPassGroups(frames_d, jobs_groups_d, (uint32_t) jobs_groups.size(), ctx->nat_dev, sl_grp, s);
     LaunchBuildGroupBlocks(frames_d, jobs_lane_groups_d, (uint32_t) jobs_lane_groups.size(), s);
     LaunchAcLanes(frames_d, jobs_ac_cta_d, (uint32_t) jobs_ac_cta.size(), ctx->nat_dev, ac_smem_code_bytes, ac_fast, s);
     LaunchGroupModular(frames_d, jobs_lane_mod_d, (uint32_t) jobs_lane_mod.size(), sl_grp, s);
     LaunchFrameStatus(frames_d, nframes, s);
+    ctx->gate_ac.Leave(k_ac, s);
     CUDA_OK(cudaEventRecord(ev[4], s));
+    const uint64_t k_recon = ctx->gate_recon.Enter(s);
     EnsureSampleEvents();
     cudaEvent_t* sev = sample_ev[run_index].data();
     size_t sampled = 0, vd = 0;
@@ -1078,6 +1105,7 @@ struct Batch {
       if (i < host_dst.size() && host_dst[i]) CUDA_OK(cudaEventRecord(img_ev[i], s));
     }
     sampled_in_run[run_index] = sampled;
+    ctx->gate_recon.Leave(k_recon, s);
     CUDA_OK(cudaEventRecord(ev[7], s));
     CUDA_OK(cudaEventRecord(span_end, s));
     ran = true;
@@ -1127,6 +1155,10 @@ struct Batch {
     pending_runs = 0;
   }
 
+  cudaStream_t D2hStream() const {
+    static const bool shared = getenv("JXLB_D2H_SHARED") != nullptr;
+    return shared ? ctx->d2h_stream : copy_stream;
+  }
   // Downloads the per-stream statuses (and, if host_out, the pixels), synchronises and resolves per-image status.
   void Finish(bool to_host, int output_device, std::vector<DecodedImage>* out) {
     cudaStream_t s = stream;
@@ -1139,7 +1171,7 @@ struct Batch {
       for (size_t i = 0; i < n && i < host_dst.size(); ++i) {
         if (!host_dst[i] || ps[i].status != JXLB_OK) continue;
         CUDA_OK(cudaEventSynchronize(img_ev[i]));
-        CUDA_OK(cudaMemcpyAsync(host_dst[i], buf->final_out.p + final_off[i], final_bytes[i], cudaMemcpyDeviceToHost, copy_stream));
+        CUDA_OK(cudaMemcpyAsync(host_dst[i], buf->final_out.p + final_off[i], final_bytes[i], cudaMemcpyDeviceToHost, D2hStream()));
       }
     if (ran) CUDA_OK(cudaEventSynchronize(ev[7]));  // every kernel of the run is done: the status words are final
     uint32_t* sh = reinterpret_cast<uint32_t*>(buf->status_host.p);
@@ -1174,7 +1206,7 @@ struct Batch {
       }
     }
     if (to_host) {  // the decode stream's timeline ends when the copy stream has drained
-      CUDA_OK(cudaEventRecord(ev[9], copy_stream));
+      CUDA_OK(cudaEventRecord(ev[9], D2hStream()));
       CUDA_OK(cudaStreamWaitEvent(s, ev[9], 0));
     }
     CUDA_OK(cudaEventRecord(ev[8], s));

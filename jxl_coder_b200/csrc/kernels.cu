@@ -152,17 +152,16 @@ __device__ int PlaceBlocksWarp(const FrameDev& f, uint32_t lfg, uint32_t* bitmap
   return kOk;
 }
 
-// kLfWarps LF groups per CTA, one warp each.  The CTA is sized to take a whole SM for itself (12 warps x 168 registers fill
-// the register file, 12 x 15.5 KB of row buffers most of the shared memory): the LF stage is a set of serial dependency
+// Several LF groups per CTA, one warp each.  The CTA is sized to take a whole SM for itself (200 KB of shared memory): the LF stage is a set of serial dependency
 // chains that leave an SM's issue slots almost idle, and when its warps were spread one or two per SM over the whole GPU
 // they competed for issue slots with the dense kernels of the other batches in flight -- the chains ran 45 % slower and
 // the dense kernels lost throughput too.  Packed, a 64-image batch's 256 chains hold 22 SMs at ~3 warps per scheduler
 // (each warp issues once every ~3 cycles: the schedulers are full) and the other 126 SMs run the dense kernels undisturbed.
-constexpr int kLfWarps = 12;
-__global__ void __launch_bounds__(kLfWarps * 32, 1) LfGroupKernel(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs,
-                                                                  ScratchLayout scratch, int warp_place) {
+constexpr int kLfMaxWarps = 12;
+__global__ void __launch_bounds__(kLfMaxWarps * 32, 1) LfGroupKernel(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs,
+                                                                     ScratchLayout scratch, int warp_place) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  const uint32_t j = blockIdx.x * kLfWarps + warp;
+  const uint32_t j = blockIdx.x * (blockDim.x >> 5) + warp;
   if (j >= njobs) return;
   const StreamJob job = jobs[j];
   const FrameDev& f = frames[job.frame];
@@ -356,7 +355,16 @@ void LaunchSingleSectionFrames(const FrameDev* frames, const StreamJob* jobs, ui
 }
 void LaunchLfGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, ScratchLayout scratch, cudaStream_t stream) {
   if (!njobs) return;
-  const int smem = (int) (kLfWarps * (kLfFastCodeBytes + kLfFastInts * 4));
+  // chains per CTA (JXLB_LF_WARPS, default 8 = two per scheduler); the CTA always asks for 200 KB of shared memory so that
+  // no CTA of a dense kernel fits beside it
+  static const int lf_warps = [] {
+    const char* e = getenv("JXLB_LF_WARPS");
+    const int v = e ? atoi(e) : 8;
+    return v >= 1 && v <= kLfMaxWarps ? v : 8;
+  }();
+  static const bool exclusive = getenv("JXLB_LF_SHARED_SM") == nullptr;
+  const int need = (int) (lf_warps * (kLfFastCodeBytes + kLfFastInts * 4));
+  const int smem = exclusive ? std::max(need, 200 << 10) : need;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(LfGroupKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -366,7 +374,7 @@ void LaunchLfGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njob
     configured = true;
   }
   static const int warp_place = getenv("JXLB_SERIAL_PLACEMENT") == nullptr;
-  LfGroupKernel<<<(njobs + kLfWarps - 1) / kLfWarps, kLfWarps * 32, smem, stream>>>(frames, jobs, njobs, scratch, warp_place);
+  LfGroupKernel<<<(njobs + lf_warps - 1) / lf_warps, lf_warps * 32, smem, stream>>>(frames, jobs, njobs, scratch, warp_place);
   ++g_launches;
 }
 void LaunchPassGroups(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat, ScratchLayout scratch,

@@ -84,6 +84,7 @@ void LaunchColorMatrix(uint8_t* img, uint32_t stride, uint32_t width, uint32_t h
 void LaunchFill(void* p, size_t bytes, uint32_t value32, cudaStream_t stream);
 void LaunchBuildGroupBlocks(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, cudaStream_t stream);
 uint32_t AcLaneSmemBytes(uint32_t code_bytes);
+uint32_t AcGroupsPerCta();  // groups one CTA of the lane-parallel AC kernel decodes (128 or 256)
 void LaunchAcLanes(const FrameDev* frames, const AcCtaJob* jobs, uint32_t njobs, NaturalOrders nat, uint32_t smem_code_bytes,
                    bool fast, cudaStream_t stream);
 void LaunchGroupModular(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, ScratchLayout scratch, cudaStream_t stream);

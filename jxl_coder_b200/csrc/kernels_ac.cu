@@ -21,7 +21,7 @@ std::atomic<uint64_t> g_launches_ac{0};
 
 namespace {
 
-constexpr int kAcCtaGroups = 128;  // groups per CTA (all of the same image)
+constexpr int kAcMaxCtaGroups = 256;  // groups per CTA (all of the same image): 128, or 256 (JXLB_AC_GROUPS; see AcGroupsPerCta)
 constexpr uint32_t kTopBytesPerLane = 96;  // 3 channels x 32 columns of the non-zero context row
 
 __global__ void __launch_bounds__(128) BuildGroupBlocksKernel(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs) {
@@ -131,7 +131,7 @@ __device__ __forceinline__ uint32_t LaneReadUint(LaneBits& lb, uint32_t& state, 
 // kLanes = groups per warp (the other lanes idle): fewer groups per warp means more warps per SM to hide the latency
 // of each lane's dependency chain, and fewer divergent paths to serialise inside a warp.
 // kFast: alias-table code staged in shared memory (the common case); otherwise the general symbol reader is used.
-template <int kLanes, bool kFast>
+template <int kLanes, bool kFast, int kAcCtaGroups>
 __global__ void __launch_bounds__(kAcCtaGroups * 32 / kLanes) AcLaneKernel(const FrameDev* frames, const AcCtaJob* jobs, NaturalOrders nat,
                                                                            uint32_t smem_code_bytes) {
   constexpr int kThreads = kAcCtaGroups * 32 / kLanes;
@@ -351,25 +351,37 @@ void LaunchBuildGroupBlocks(const FrameDev* frames, const StreamJob* jobs, uint3
 }
 
 uint32_t AcLaneSmemBytes(uint32_t code_bytes) {
-  return ((code_bytes + 15u) & ~15u) + (uint32_t) sizeof(AcTables) + kAcCtaGroups * kTopBytesPerLane;
+  return ((code_bytes + 15u) & ~15u) + (uint32_t) sizeof(AcTables) + kAcMaxCtaGroups * kTopBytesPerLane;
+}
+
+uint32_t AcGroupsPerCta() {
+  // 256 groups per CTA (a whole 4096x4096 image) = 32 warps of 8 lanes on one SM: twice the warps to hide the lanes'
+  // dependency chains, and a 64-image batch then holds 64 SMs instead of 128, leaving room for the LF stage and the
+  // dense kernels of the other batches in flight.  The kernel needs 64 registers x 1024 threads = the whole register file.
+  static const uint32_t v = [] {
+    const char* e = getenv("JXLB_AC_GROUPS");
+    const int n = e ? atoi(e) : 256;
+    return (uint32_t) (n == 128 ? 128 : 256);
+  }();
+  return v;
 }
 
 namespace {
-template <int kLanes, bool kFast>
+template <int kLanes, bool kFast, int kGroups>
 void LaunchAcLanesT(const FrameDev* frames, const AcCtaJob* jobs, uint32_t njobs, NaturalOrders nat, uint32_t smem_code_bytes,
                     uint32_t smem, cudaStream_t stream) {
   static uint32_t configured = 0;
   if (smem > configured) {
-    cudaFuncSetAttribute(AcLaneKernel<kLanes, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(AcLaneKernel<kLanes, kFast, kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     configured = smem;
   }
-  AcLaneKernel<kLanes, kFast><<<njobs, kAcCtaGroups * 32 / kLanes, smem, stream>>>(frames, jobs, nat, smem_code_bytes);
+  AcLaneKernel<kLanes, kFast, kGroups><<<njobs, kGroups * 32 / kLanes, smem, stream>>>(frames, jobs, nat, smem_code_bytes);
 }
 int AcLanesPerWarp() {
   static int v = [] {
     const char* e = getenv("JXLB_AC_LANES");
     const int n = e ? atoi(e) : 8;
-    return (n == 32 || n == 16 || n == 8 || n == 4) ? n : 8;
+    return (n == 32 || n == 16 || n == 8) ? n : 8;
   }();
   return v;
 }
@@ -381,14 +393,21 @@ void LaunchAcLanes(const FrameDev* frames, const AcCtaJob* jobs, uint32_t njobs,
   if (!njobs) return;
   smem_code_bytes = (smem_code_bytes + 15u) & ~15u;
   const uint32_t smem = AcLaneSmemBytes(smem_code_bytes);
+  const bool big = AcGroupsPerCta() == 256;
   if (!fast) {
-    LaunchAcLanesT<32, false>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream);
+    if (big) LaunchAcLanesT<32, false, 256>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream);
+    else LaunchAcLanesT<32, false, 128>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream);
+  } else if (big) {
+    switch (AcLanesPerWarp()) {
+      case 32: LaunchAcLanesT<32, true, 256>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
+      case 16: LaunchAcLanesT<16, true, 256>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
+      default: LaunchAcLanesT<8, true, 256>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
+    }
   } else {
     switch (AcLanesPerWarp()) {
-      case 32: LaunchAcLanesT<32, true>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
-      case 16: LaunchAcLanesT<16, true>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
-      case 4: LaunchAcLanesT<4, true>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
-      default: LaunchAcLanesT<8, true>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
+      case 32: LaunchAcLanesT<32, true, 128>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
+      case 16: LaunchAcLanesT<16, true, 128>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
+      default: LaunchAcLanesT<8, true, 128>(frames, jobs, njobs, nat, smem_code_bytes, smem, stream); break;
     }
   }
   ++g_launches_ac;
