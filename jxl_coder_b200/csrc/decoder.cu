@@ -209,9 +209,11 @@ struct DeviceContext {
     }
     // Both are called with DeviceContext::mu held for the whole enqueue of a run, so the record of run k is always
     // enqueued before the wait of run k + tokens.
-    uint64_t Enter(cudaStream_t s) {
+    // gated = false (prepared batches: everything resident in HBM, nothing to download) only takes a ticket, so that the
+    // gated runs behind it still find its end-of-stage event
+    uint64_t Enter(cudaStream_t s, bool gated) {
       const uint64_t k = count++;
-      if (tokens > 0 && k >= (uint64_t) tokens) CUDA_OK(cudaStreamWaitEvent(s, ev[(k - tokens) % kRing], 0));
+      if (gated && tokens > 0 && k >= (uint64_t) tokens) CUDA_OK(cudaStreamWaitEvent(s, ev[(k - tokens) % kRing], 0));
       return k;
     }
     void Leave(uint64_t k, cudaStream_t s) { CUDA_OK(cudaEventRecord(ev[k % kRing], s)); }
@@ -922,6 +924,7 @@ struct Batch {
     CUDA_OK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream;
     std::lock_guard<std::mutex> enqueue_lock(ctx->mu);  // runs are enqueued one at a time (stage gates, DeviceContext)
+    const bool gated = !host_dst.empty() || getenv("JXLB_GATE_PREPARED") != nullptr;
     if (pending_runs >= kEventSets) CollectRuns();  // the ring is full: drain (synchronises)
     if (pending_runs > 0) {                          // keep the upload events of set 0 readable from every set
       run_index = (run_index + 1) % kEventSets;
@@ -943,7 +946,7 @@ struct Batch {
       CUDA_OK(cudaMemsetAsync(wb + p.plan.off_status, 0xFF, (size_t) p.plan.num_streams * 4, lf_stream));
     }
     {
-      const uint64_t k = ctx->gate_lf.Enter(lf_stream);
+      const uint64_t k = ctx->gate_lf.Enter(lf_stream, gated);
       LaunchLfGroups(frames_d, jobs_lf_d, (uint32_t) jobs_lf.size(), sl_lf, lf_stream);
       ctx->gate_lf.Leave(k, lf_stream);
     }
@@ -961,7 +964,7 @@ struct Batch {
     CUDA_OK(cudaStreamWaitEvent(s, ev_lf_done, 0));
     LaunchSingleSectionFrames(frames_d, jobs_single_d, (uint32_t) jobs_single.size(), ctx->nat_dev, sl_single, s);
     CUDA_OK(cudaEventRecord(ev[3], s));
-    const uint64_t k_ac = ctx->gate_ac.Enter(s);
+    const uint64_t k_ac = ctx->gate_ac.Enter(s, gated);
     LaunchPassGroups(frames_d, jobs_groups_d, (uint32_t) jobs_groups.size(), ctx->nat_dev, sl_grp, s);
     LaunchBuildGroupBlocks(frames_d, jobs_lane_groups_d, (uint32_t) jobs_lane_groups.size(), s);
     LaunchAcLanes(frames_d, jobs_ac_cta_d, (uint32_t) jobs_ac_cta.size(), ctx->nat_dev, ac_smem_code_bytes, ac_fast, s);
@@ -969,7 +972,7 @@ struct Batch {
     LaunchFrameStatus(frames_d, nframes, s);
     ctx->gate_ac.Leave(k_ac, s);
     CUDA_OK(cudaEventRecord(ev[4], s));
-    const uint64_t k_recon = ctx->gate_recon.Enter(s);
+    const uint64_t k_recon = ctx->gate_recon.Enter(s, gated);
     EnsureSampleEvents();
     cudaEvent_t* sev = sample_ev[run_index].data();
     size_t sampled = 0, vd = 0;
