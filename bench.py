@@ -143,6 +143,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # the library's pinned-buffer pool and host thread count are per process: share the host among the ranks
+    os.environ.setdefault("JXLB_PINNED_POOL_MB", str(max(8192, 40960 // world)))
+    os.environ.setdefault("JXLB_HOST_THREADS", str(max(2, (os.cpu_count() or 8) // world)))
     import jxl_coder_b200 as J
     J.load_library()
     datas = load_inputs()
@@ -222,7 +225,8 @@ def run_ours(args):
     # ONE caller thread keeps `depth` batches in flight with jxlb_decode_batch_submit / _collect (a synchronous call is a
     # latency chain -- its LF stage alone is ~86 ms of serial entropy chains -- so a single call at a time leaves the GPU
     # and the PCIe link idle most of the time; the reference's own callers overlap calls from worker pools).
-    depth = max(1, args.depth)
+    # every batch in flight keeps 4 GiB of pinned result buffers: on 4 / 8 GPUs (ranks share the host's RAM and cores) fewer
+    depth = max(1, args.depth if world <= 2 else min(args.depth, 3))
 
     def e2e_steps_run(nsteps):
         inflight = []
