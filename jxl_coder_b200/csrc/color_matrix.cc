@@ -1,7 +1,9 @@
 #include "color_matrix.h"
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
+#include <vector>
 
 namespace jxlb {
 
@@ -76,6 +78,22 @@ float ToLinear(float g, int tf) {
       return 1.0f;
     case 17:  // DCI -> SMPTE 428 (Trc.cpp:223-225)
       return powf(std::max(g, 0.0f), 2.6f) / 0.91655527974030934f;
+    case 16:  // PQ -> extended SDR, 203 nits = 1.0 (Trc.cpp:197-208)
+      if (g > 0.0f) {
+        const float pg = powf(g, 1.0f / 78.84375f);
+        const float num = std::max(pg - 0.8359375f, 0.0f);
+        const float den = std::max(18.8515625f - 18.6875f * pg, FLT_MIN);
+        const float linear = powf(num / den, 1.0f / 0.1593017578125f);
+        return linear * 10000.0f / 203.0f;
+      }
+      return 0.0f;
+    case 18: {  // HLG inverse OETF + OOTF, peak 1000 nits (Trc.cpp:229-246)
+      if (g < 0.0f) return 0.0f;
+      float linear;
+      if (g <= 0.5f) linear = powf((g * g) * (1.0f / 3.0f), 1.2f);
+      else linear = powf((expf((g - 0.55991073f) / 0.17883277f) + 0.28466892f) / 12.0f, 1.2f);
+      return linear * 1000.0f / 203.0f;
+    }
     default:  // gamma -> "Gamma2p2" whatever the coded gamma (JniDecoding.cpp:157-160; Trc.cpp:57-59)
       return powf(std::min(std::max(g, 0.0f), 1.0f), 2.2f);
   }
@@ -90,14 +108,22 @@ float ToGammaSrgb(float l) {  // Trc.cpp:181-191
 
 }  // namespace
 
-bool MakeColorMatrixPlan(const ImageMetadata& md, bool* needed, ColorMatrixPlan* plan) {
+bool MakeColorMatrixPlan(const ImageMetadata& md, bool* needed, ColorMatrixPlan* plan, ColorMatrixTables16* tables16) {
   const ColorEncoding& c = md.color;
   *needed = false;
   if (c.want_icc || c.color_space != 0) return true;  // ICC (preferEncoding false) or not RGB: the pass is skipped
   const int tf = c.have_gamma ? 0xFFFF : (int) c.transfer;
   if (!(tf == 16 || tf == 18 || tf == 17 || tf == 1 || tf == 0xFFFF || tf == 13)) return true;  // e.g. linear: skipped
   *needed = true;
-  if (tf == 16 || tf == 18) return false;  // PQ / HLG: Rec.2408 tone mapping not restated
+  // Rec2408ToneMapper(contentBrightness = intensity target, displayMaxBrightness 250, whitePoint 203) for PQ and HLG
+  plan->tonemap = (tf == 16 || tf == 18) ? 1u : 0u;
+  {
+    const float content = md.intensity_target, display = 250.0f, white = 203.0f;
+    const float ld = content / white;
+    plan->weight_a = (display / white) / (ld * ld);
+    plan->weight_b = 1.0f / (display / white);
+    plan->pad = 0;
+  }
   float prim[3][2], white[2] = {0.3127f, 0.3290f};
   const float srgb[3][2] = {{0.640f, 0.330f}, {0.300f, 0.600f}, {0.150f, 0.060f}};
   const float bt2020[3][2] = {{0.708f, 0.292f}, {0.170f, 0.797f}, {0.131f, 0.046f}};
@@ -136,21 +162,14 @@ bool MakeColorMatrixPlan(const ImageMetadata& md, bool* needed, ColorMatrixPlan*
   for (int j = 0; j < 256; ++j) plan->linearize[j] = ToLinear((float) j * (1.f / 255.f), tf);
   for (int j = 0; j < 2049; ++j)
     plan->gamma[j] = (uint8_t) std::min(std::max(roundf(ToGammaSrgb((float) j * (1.f / 2048.f)) * 255.f), 0.f), 255.f);
-  return true;
-}
-
-void ApplyColorMatrixHost(const ColorMatrixPlan& p, uint8_t* rgba, uint32_t stride, uint32_t width, uint32_t height) {
-  for (uint32_t y = 0; y < height; ++y) {
-    uint8_t* row = rgba + (size_t) y * stride;
-    for (uint32_t x = 0; x < width; ++x, row += 4) {
-      const float r = p.linearize[row[0]], g = p.linearize[row[1]], b = p.linearize[row[2]];
-      const float v[3] = {r * p.m[0] + g * p.m[1] + b * p.m[2], r * p.m[3] + g * p.m[4] + b * p.m[5], r * p.m[6] + g * p.m[7] + b * p.m[8]};
-      for (int c = 0; c < 3; ++c) {
-        const uint32_t idx = std::min<uint32_t>((uint16_t) (std::min(std::max(v[c], 0.f), 1.0f) * 2048.f), 2048u);
-        row[c] = p.gamma[idx];
-      }
+  if (tables16) {  // applyColorMatrix16Bit, bitDepth 16 (ColorMatrix.cpp:143-158)
+    const float cut = 65535.0f, scale = 1.f / cut;
+    for (uint32_t j = 0; j < 65536; ++j) {
+      tables16->linearize[j] = ToLinear((float) j * scale, tf);
+      tables16->gamma[j] = (uint16_t) std::min(std::max(roundf(ToGammaSrgb((float) j * scale) * cut), 0.f), cut);
     }
   }
+  return true;
 }
 
 }  // namespace jxlb

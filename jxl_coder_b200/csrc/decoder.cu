@@ -333,7 +333,8 @@ struct Parsed {
   size_t or_off = 0;
   bool color_matrix = false;
   ColorMatrixPlan cmp;
-  size_t cm_off = 0;
+  std::shared_ptr<ColorMatrixTables16> cmt16;  // sources deeper than 8 bits
+  size_t cm_off = 0, cm_rows_off = 0;
   bool matrix_before_resize = false;  // getFrameImpl applies it before RescaleImage, decodeSampledImageImpl after
 };
 
@@ -540,14 +541,12 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
   }
   if (api < 34) {  // JniDecoding.cpp:138-228
     bool needed = false;
-    if (!MakeColorMatrixPlan(md, &needed, &p->cmp)) {
-      Fail(p, JXLB_UNSUPPORTED, "api_level < 34 colour pass with PQ / HLG tone mapping");
+    if (p->out16) p->cmt16.reset(new ColorMatrixTables16());
+    if (!MakeColorMatrixPlan(md, &needed, &p->cmp, p->cmt16.get())) {
+      Fail(p, JXLB_UNSUPPORTED, "api_level < 34 colour pass for this colour encoding");
       return;
     }
-    if (needed && p->out16) {
-      Fail(p, JXLB_UNSUPPORTED, "api_level < 34 colour pass on 16-bit samples");
-      return;
-    }
+    if (!needed) p->cmt16.reset();
     p->color_matrix = needed;
     p->matrix_before_resize = target_frame >= 0;
   }
@@ -730,6 +729,11 @@ struct Batch {
       if (p.color_matrix) {
         p.cm_off = const_total;
         const_total += Align256(sizeof(ColorMatrixPlan));
+        if (p.cmt16) const_total += Align256(sizeof(ColorMatrixTables16));
+        if (p.cmp.tonemap) {  // per-row scratch of the tone mapper (FirstBlackKernel)
+          p.cm_rows_off = work_total;
+          work_total += Align256((size_t) std::max(p.oh, p.out_h) * 4);
+        }
       }
       if (p.resize) {
         auto axis_bytes = [](const ResizeAxis& a) { return Align256(a.start.size() * 4) + Align256(a.count.size() * 4) + Align256(a.weights.size() * 2); };
@@ -859,7 +863,10 @@ struct Batch {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) return;
       FillConstRegion(p.plan, p.cs.data(), p.fh, p.g, stg + p.const_off);
-      if (p.color_matrix) memcpy(stg + p.cm_off, &p.cmp, sizeof(ColorMatrixPlan));
+      if (p.color_matrix) {
+        memcpy(stg + p.cm_off, &p.cmp, sizeof(ColorMatrixPlan));
+        if (p.cmt16) memcpy(stg + p.cm_off + Align256(sizeof(ColorMatrixPlan)), p.cmt16.get(), sizeof(ColorMatrixTables16));
+      }
       if (p.resize) {
         uint8_t* t = stg + p.rs_table_off;
         for (const ResizeAxis* a : {&p.rp.v, &p.rp.h}) {
@@ -1052,7 +1059,9 @@ struct Batch {
         res = dst;
         res_stride = p.ow * bpp;
       }
-      if (p.color_matrix && p.matrix_before_resize) LaunchColorMatrix(const_cast<uint8_t*>(res), res_stride, p.ow, p.oh, cm_dev, s);
+      uint32_t* cm_rows = reinterpret_cast<uint32_t*>(buf->work_buf.p + p.cm_rows_off);
+      if (p.color_matrix && p.matrix_before_resize)
+        LaunchColorMatrix(const_cast<uint8_t*>(res), res_stride, p.ow, p.oh, cm_dev, p.cmp.tonemap != 0, p.out16, cm_rows, s);
       if (p.resize) {
         ResizeDev rd{};
         rd.src = res;
@@ -1101,7 +1110,7 @@ struct Batch {
         // colour pass after the rescale, before the reformat (JniDecoding.cpp:120-228); the zero rows of the quirks above
         // pass through it unchanged only when the tables map 0 to 0, which they do (toLinear(0) = 0, gamma[0] = 0)
         if (p.color_matrix && !p.matrix_before_resize && pr.height)
-          LaunchColorMatrix(const_cast<uint8_t*>(res), res_stride, pr.width, pr.height, cm_dev, s);
+          LaunchColorMatrix(const_cast<uint8_t*>(res), res_stride, pr.width, pr.height, cm_dev, p.cmp.tonemap != 0, p.out16, cm_rows, s);
         if (pr.height) LaunchPack(pr, s);
       }
       // download: only the "image done" event is recorded here; Finish() enqueues each copy once its image is complete

@@ -76,9 +76,12 @@ void LaunchPlace(const uint8_t* src, uint32_t src_stride, uint32_t fw, uint32_t 
 void LaunchOrient(const uint8_t* src, uint32_t src_stride, uint32_t w, uint32_t h, uint32_t bpp, uint32_t orientation, uint8_t* dst,
                   uint32_t dst_stride, cudaStream_t stream);
 
-// api_level < 34 colour pass (kernels_post.cu), in place on straight RGBA8; plan_dev: a ColorMatrixPlan in device memory.
+// api_level < 34 colour pass (kernels_post.cu), in place on straight RGBA8 (or RGBA16: bits16); plan_dev: a ColorMatrixPlan
+// in device memory, followed at the next 256-byte boundary by a ColorMatrixTables16 when bits16.  tonemap: PQ / HLG source
+// (Rec.2408 tone mapping); row_first: `height` words of device scratch for it.
 struct ColorMatrixPlan;
-void LaunchColorMatrix(uint8_t* img, uint32_t stride, uint32_t width, uint32_t height, const ColorMatrixPlan* plan_dev, cudaStream_t stream);
+void LaunchColorMatrix(uint8_t* img, uint32_t stride, uint32_t width, uint32_t height, const ColorMatrixPlan* plan_dev, bool tonemap, bool bits16,
+                       uint32_t* row_first, cudaStream_t stream);
 
 // Sets `bytes` (a multiple of 16, 16-byte aligned) to the repeated 32-bit value with a kernel.
 void LaunchFill(void* p, size_t bytes, uint32_t value32, cudaStream_t stream);

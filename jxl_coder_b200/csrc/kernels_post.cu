@@ -16,8 +16,50 @@ extern std::atomic<uint64_t> g_launches_ac;
 
 namespace {
 
+// Rec2408ToneMapper::transferTone stops tone-mapping a row at its first pixel of zero luminance (color_matrix.h): this
+// kernel finds that pixel for every row (width when there is none).  kBits16: RGBA16 source with the 2^16-entry table.
+template <bool kBits16>
+__global__ void __launch_bounds__(256) FirstBlackKernel(const uint8_t* __restrict__ img, uint32_t stride, uint32_t width, const float* __restrict__ lin,
+                                                        uint32_t* __restrict__ row_first) {
+  const uint32_t y = blockIdx.x;
+  __shared__ uint32_t first;
+  if (threadIdx.x == 0) first = width;
+  __syncthreads();
+  uint32_t mine = width;
+  for (uint32_t x = threadIdx.x; x < width && x < mine; x += blockDim.x) {
+    float r, g, b;
+    if (kBits16) {
+      const uint2 v = *reinterpret_cast<const uint2*>(img + (size_t) y * stride + (size_t) x * 8);
+      r = lin[v.x & 0xFFFF]; g = lin[v.x >> 16]; b = lin[v.y & 0xFFFF];
+    } else {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(img + (size_t) y * stride + (size_t) x * 4);
+      r = lin[v & 0xFF]; g = lin[(v >> 8) & 0xFF]; b = lin[(v >> 16) & 0xFF];
+    }
+    const float light = __fadd_rn(__fadd_rn(__fmul_rn(0.2627f, r), __fmul_rn(0.6780f, g)), __fmul_rn(0.0593f, b));
+    if (light == 0.0f) mine = x;
+  }
+  if (mine < width) atomicMin(&first, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) row_first[y] = first;
+}
+
+// One pixel of the pass after the linearisation: [tone map] -> matrix; separate multiplies and adds, as the reference's
+// scalar loops (no FMA contraction).
+__device__ __forceinline__ void ToneMapAndMatrix(float r, float g, float b, bool tone, float wa, float wb, const float* m, float out[3]) {
+  if (tone) {
+    const float light = __fadd_rn(__fadd_rn(__fmul_rn(0.2627f, r), __fmul_rn(0.6780f, g)), __fmul_rn(0.0593f, b));
+    const float scale = __fdiv_rn(__fadd_rn(1.f, __fmul_rn(wa, light)), __fadd_rn(1.f, __fmul_rn(wb, light)));
+    r = fminf(__fmul_rn(r, scale), 1.f);
+    g = fminf(__fmul_rn(g, scale), 1.f);
+    b = fminf(__fmul_rn(b, scale), 1.f);
+  }
+  out[0] = __fadd_rn(__fadd_rn(__fmul_rn(r, m[0]), __fmul_rn(g, m[1])), __fmul_rn(b, m[2]));
+  out[1] = __fadd_rn(__fadd_rn(__fmul_rn(r, m[3]), __fmul_rn(g, m[4])), __fmul_rn(b, m[5]));
+  out[2] = __fadd_rn(__fadd_rn(__fmul_rn(r, m[6]), __fmul_rn(g, m[7])), __fmul_rn(b, m[8]));
+}
+
 __global__ void __launch_bounds__(256) ColorMatrixKernel(uint8_t* __restrict__ img, uint32_t stride, uint32_t width, uint32_t height,
-                                                         const ColorMatrixPlan* __restrict__ plan) {
+                                                         const ColorMatrixPlan* __restrict__ plan, const uint32_t* __restrict__ row_first) {
   __shared__ float lin[256];
   __shared__ uint8_t gam[2052];
   __shared__ float m[9];
@@ -27,18 +69,44 @@ __global__ void __launch_bounds__(256) ColorMatrixKernel(uint8_t* __restrict__ i
   __syncthreads();
   const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= width) return;
+  const bool tonemap = plan->tonemap != 0;
+  const float wa = plan->weight_a, wb = plan->weight_b;
   for (uint32_t y = blockIdx.y; y < height; y += gridDim.y) {
     uint32_t* px = reinterpret_cast<uint32_t*>(img + (size_t) y * stride) + x;
     const uint32_t v = *px;
-    const float r = lin[v & 0xFF], g = lin[(v >> 8) & 0xFF], b = lin[(v >> 16) & 0xFF];
-    // separate multiplies and adds, as the reference's scalar loop: no FMA contraction
-    const float nr = __fadd_rn(__fadd_rn(__fmul_rn(r, m[0]), __fmul_rn(g, m[1])), __fmul_rn(b, m[2]));
-    const float ng = __fadd_rn(__fadd_rn(__fmul_rn(r, m[3]), __fmul_rn(g, m[4])), __fmul_rn(b, m[5]));
-    const float nb = __fadd_rn(__fadd_rn(__fmul_rn(r, m[6]), __fmul_rn(g, m[7])), __fmul_rn(b, m[8]));
-    const uint32_t ir = min((uint32_t) (fminf(fmaxf(nr, 0.f), 1.f) * 2048.f), 2048u);
-    const uint32_t ig = min((uint32_t) (fminf(fmaxf(ng, 0.f), 1.f) * 2048.f), 2048u);
-    const uint32_t ib = min((uint32_t) (fminf(fmaxf(nb, 0.f), 1.f) * 2048.f), 2048u);
+    float o[3];
+    ToneMapAndMatrix(lin[v & 0xFF], lin[(v >> 8) & 0xFF], lin[(v >> 16) & 0xFF], tonemap && x < row_first[y], wa, wb, m, o);
+    const uint32_t ir = min((uint32_t) (fminf(fmaxf(o[0], 0.f), 1.f) * 2048.f), 2048u);
+    const uint32_t ig = min((uint32_t) (fminf(fmaxf(o[1], 0.f), 1.f) * 2048.f), 2048u);
+    const uint32_t ib = min((uint32_t) (fminf(fmaxf(o[2], 0.f), 1.f) * 2048.f), 2048u);
     *px = (uint32_t) gam[ir] | ((uint32_t) gam[ig] << 8) | ((uint32_t) gam[ib] << 16) | (v & 0xFF000000u);
+  }
+}
+
+// applyColorMatrix16Bit: RGBA16 in place, 2^16-entry tables read through L1 / L2 (384 KB per image).
+__global__ void __launch_bounds__(256) ColorMatrix16Kernel(uint8_t* __restrict__ img, uint32_t stride, uint32_t width, uint32_t height,
+                                                           const ColorMatrixPlan* __restrict__ plan, const ColorMatrixTables16* __restrict__ t,
+                                                           const uint32_t* __restrict__ row_first) {
+  __shared__ float m[9];
+  if (threadIdx.x < 9) m[threadIdx.x] = plan->m[threadIdx.x];
+  __syncthreads();
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= width) return;
+  const bool tonemap = plan->tonemap != 0;
+  const float wa = plan->weight_a, wb = plan->weight_b;
+  for (uint32_t y = blockIdx.y; y < height; y += gridDim.y) {
+    uint2* px = reinterpret_cast<uint2*>(img + (size_t) y * stride) + x;
+    const uint2 v = *px;
+    float o[3];
+    ToneMapAndMatrix(__ldg(t->linearize + (v.x & 0xFFFF)), __ldg(t->linearize + (v.x >> 16)), __ldg(t->linearize + (v.y & 0xFFFF)),
+                     tonemap && x < row_first[y], wa, wb, m, o);
+    const uint32_t ir = min((uint32_t) (fminf(fmaxf(o[0], 0.f), 1.f) * 65535.f), 65535u);
+    const uint32_t ig = min((uint32_t) (fminf(fmaxf(o[1], 0.f), 1.f) * 65535.f), 65535u);
+    const uint32_t ib = min((uint32_t) (fminf(fmaxf(o[2], 0.f), 1.f) * 65535.f), 65535u);
+    uint2 w;
+    w.x = (uint32_t) __ldg(t->gamma + ir) | ((uint32_t) __ldg(t->gamma + ig) << 16);
+    w.y = (uint32_t) __ldg(t->gamma + ib) | (v.y & 0xFFFF0000u);
+    *px = w;
   }
 }
 
@@ -145,10 +213,18 @@ void LaunchOrient(const uint8_t* src, uint32_t src_stride, uint32_t w, uint32_t 
   ++g_launches_ac;
 }
 
-void LaunchColorMatrix(uint8_t* img, uint32_t stride, uint32_t width, uint32_t height, const ColorMatrixPlan* plan_dev, cudaStream_t stream) {
+void LaunchColorMatrix(uint8_t* img, uint32_t stride, uint32_t width, uint32_t height, const ColorMatrixPlan* plan_dev, bool tonemap, bool bits16,
+                       uint32_t* row_first, cudaStream_t stream) {
   if (!width || !height) return;
+  const ColorMatrixTables16* t16 = reinterpret_cast<const ColorMatrixTables16*>(reinterpret_cast<const uint8_t*>(plan_dev) + ((sizeof(ColorMatrixPlan) + 255) & ~(size_t) 255));
+  if (tonemap) {
+    if (bits16) FirstBlackKernel<true><<<height, 256, 0, stream>>>(img, stride, width, t16->linearize, row_first);
+    else FirstBlackKernel<false><<<height, 256, 0, stream>>>(img, stride, width, plan_dev->linearize, row_first);
+    ++g_launches_ac;
+  }
   dim3 grid((width + 255) / 256, std::min<uint32_t>(height, 1184), 1);
-  ColorMatrixKernel<<<grid, 256, 0, stream>>>(img, stride, width, height, plan_dev);
+  if (bits16) ColorMatrix16Kernel<<<grid, 256, 0, stream>>>(img, stride, width, height, plan_dev, t16, row_first);
+  else ColorMatrixKernel<<<grid, 256, 0, stream>>>(img, stride, width, height, plan_dev, row_first);
   ++g_launches_ac;
 }
 

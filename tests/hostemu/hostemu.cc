@@ -271,6 +271,23 @@ int emu_color_matrix(const uint8_t* jxl, size_t len, uint8_t* rgba, uint32_t w, 
   ApplyColorMatrixHost(plan, rgba, w * 4, w, h);
   return 0;
 }
+// The 16-bit variant (applyColorMatrix16Bit) on RGBA16 rows.
+int emu_color_matrix16(const uint8_t* jxl, size_t len, uint16_t* rgba, uint32_t w, uint32_t h) {
+  std::vector<uint8_t> cs;
+  size_t cs_len = 0;
+  if (ExtractCodestream(jxl, len, &cs, &cs_len)) return -1;
+  ImageMetadata md;
+  uint64_t fb = 0;
+  std::string err;
+  if (ParseImageHeader(cs.data(), cs.size(), cs_len, &md, &fb, &err)) return -1;
+  bool needed = false;
+  static ColorMatrixPlan plan;
+  static ColorMatrixTables16 t16;
+  if (!MakeColorMatrixPlan(md, &needed, &plan, &t16)) return 2;
+  if (!needed) return 1;
+  ApplyColorMatrixHost16(plan, t16, rgba, w * 8, w, h);
+  return 0;
+}
 
 
 // ApproxRcp (numeric.h) against the host's RCPPS on n pseudo-random positive normal floats in [2^-20, 2^20): returns the

@@ -8,7 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = ["tests/hostemu/hostemu.cc", "jxl_coder_b200/csrc/frame_parser.cc", "jxl_coder_b200/csrc/plan.cc",
        "jxl_coder_b200/csrc/natural_orders.cc", "jxl_coder_b200/csrc/numeric_tables.cc", "jxl_coder_b200/csrc/color_params.cc",
-       "jxl_coder_b200/csrc/resize.cc", "jxl_coder_b200/csrc/color_matrix.cc"]
+       "jxl_coder_b200/csrc/resize.cc", "jxl_coder_b200/csrc/color_matrix.cc", "jxl_coder_b200/csrc/resize_host.cc",
+       "jxl_coder_b200/csrc/color_matrix_host.cc"]
 OUT = os.path.join(HERE, "hostemu", "_build", "libhostemu.so")
 _lib = None
 
@@ -44,6 +45,7 @@ def lib():
         L.emu_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
                                  C.POINTER(C.c_uint32)]
         L.emu_color_matrix.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.emu_color_matrix16.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32]
         L.emu_expand_lehmer.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.emu_rcp_check.argtypes = [C.c_long]
         L.emu_rcp_check.restype = C.c_long
@@ -137,4 +139,11 @@ def color_matrix(jxl, rgba):
     """api_level < 34 colour pass (csrc/color_matrix.cc) on a copy of rgba [h,w,4] u8.  Returns (status, array)."""
     a = np.ascontiguousarray(rgba, dtype=np.uint8).copy()
     st = lib().emu_color_matrix(bytes(jxl), len(jxl), a.ctypes.data, a.shape[1], a.shape[0])
+    return st, a
+
+
+def color_matrix16(jxl, rgba16):
+    """The same on RGBA16 samples [h,w,4] u16 (applyColorMatrix16Bit).  Returns (status, array)."""
+    a = np.ascontiguousarray(rgba16, dtype=np.uint16).copy()
+    st = lib().emu_color_matrix16(bytes(jxl), len(jxl), a.ctypes.data, a.shape[1], a.shape[0])
     return st, a
