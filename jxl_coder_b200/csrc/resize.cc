@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace jxlb {
@@ -34,8 +35,23 @@ float BcSpline(float d, float b, float c, bool horner) {
   return 0.0f;
 }
 
+// pic-scale's Lanczos3: sinc(x) * sinc(x / 3) for |x| < 3, sinc(x) = sin(pi x) / (pi x).  Its sine goes through the pxfm
+// crate's f_sinpif (a correctly rounded f32 sinpi); here sin(pi x) is evaluated in double and rounded to f32 once, which
+// gives the same f32 wherever the double result is not within 2^-29 of a rounding boundary (bit-exact against the
+// reference binary on every size tried, tests/test_resize_host.py).
+float Sinc(float x) {
+  if (x == 0.0f) return 1.0f;
+  const float s = (float) std::sin(M_PI * (double) x);
+  return s / (3.14159265358979323846f * x);
+}
+float Lanczos3(float x) {
+  const float a = std::fabs(x);
+  if (a >= 3.0f) return 0.0f;
+  return Sinc(a) * Sinc(a / 3.0f);
+}
+
 struct Kernel {
-  int kind;              // 0 bilinear, 1 bc-spline (expanded), 2 bc-spline (Horner)
+  int kind;              // 0 bilinear, 1 bc-spline (expanded), 2 bc-spline (Horner), 3 Lanczos3
   float b, c;
   float min_kernel_size;
   float operator()(float x) const {
@@ -43,6 +59,7 @@ struct Kernel {
       const float a = std::fabs(x);
       return a < 1.0f ? 1.0f - a : 0.0f;
     }
+    if (kind == 3) return Lanczos3(x);
     return BcSpline(x, b, c, kind == 2);
   }
 };
@@ -56,7 +73,11 @@ bool KernelFor(int32_t filter, Kernel* k) {
     case 4: *k = Kernel{1, third, third, 4.0f}; return true;        // MitchellNetravalli
     case 6: *k = Kernel{1, 0.0f, 0.5f, 4.0f}; return true;          // CatmullRom
     case 7: *k = Kernel{1, 0.0f, 0.0f, 4.0f}; return true;          // Hermite
-    default: return false;  // 5 / 9 Lanczos3 (sinc through pxfm's sinpi) and 10 Bicubic: weights not reproduced -> refused
+    case 10: *k = Kernel{1, 0.0f, 0.5f, 4.0f}; return true;         // Bicubic: pic-scale 0.7.6 gives CatmullRom's output bit for bit
+    case 5: case 9:                                                 // Lanczos3; HANN is mapped to Lanczos (SizeScaler.cpp:86-89)
+      *k = Kernel{3, 0.f, 0.f, 6.0f};
+      return true;
+    default: return false;
   }
 }
 
@@ -117,6 +138,7 @@ void MakeNearestAxis(uint32_t in_size, uint32_t out_size, ResizeAxis* a) {
 int MakeResizePlan(uint32_t src_w, uint32_t src_h, int32_t req_w, int32_t req_h, int32_t scale_mode, int32_t filter, bool has_alpha,
                    ResizePlan* p) {
   if (!src_w || !src_h || req_w == 0 || req_h == 0) return kResizeBadArg;
+  if (has_alpha && (filter == 5 || filter == 9)) return kResizeUnsupported;  // see resize.h
   // resolve_dimensions (weaver/src/scale.rs:100-135)
   size_t nw, nh;
   if (req_w > 0 && req_h == -1) {

@@ -23,8 +23,11 @@
 // Parity reached: Bilinear and Nearest bit-exact on every size tried; the spline family bit-exact on exact ratios (all of
 // BASELINE configs[3]: 7680x4320 -> 1920x1080) and otherwise within one Q15 unit on ~1 tap weight in 10^3 (the f32
 // evaluation order of pic-scale's spline polynomial is unknown), i.e. |diff| = 1 on < 0.1 % of the output samples.
-// Refused with kResizeUnsupported, never approximated: Lanczos3 / HANN (pic-scale's sinc goes through the pxfm crate's
-// sinpi), Bicubic, and 16-bit sources (weave_scale_u16 works in f32).
+//   * Lanczos3 (HANN is mapped to it, SizeScaler.cpp:86-89): sinc(x) sinc(x / 3), 6 taps -- bit-exact against the binary;
+//     Bicubic: pic-scale 0.7.6 gives CatmullRom's output bit for bit.
+// Refused with kResizeUnsupported, never approximated: Lanczos3 / HANN on sources WITH ALPHA (the filter's strong negative
+// lobes push resampled colours above their alpha, and what pic-scale's divide-back does then -- some samples saturate,
+// some wrap -- is not pinned), and 16-bit sources (weave_scale_u16 works in f32).
 #pragma once
 #include <cstdint>
 #include <vector>

@@ -283,11 +283,17 @@ def test_decode_sampled_rescale_on_lossy_multi_group(J, ref):
     assert ((a >> 30) == (b >> 30)).all()
 
 
-def test_decode_sampled_unpinned_rescales_are_refused(J, ref):
+def test_decode_sampled_lanczos_hann_bicubic(J, ref):
+    """Lanczos3, HANN (mapped to Lanczos3 by SizeScaler.cpp:86-89) and Bicubic on a lossless source: bit-exact.  Lanczos3 on a
+    source with alpha is refused (resize.h)."""
     _, data = _resize_src(ref, 96, 64)
-    for (rw, rh, mode, filt) in [(24, 16, 3, 5), (24, 16, 3, 9), (40, 40, 2, 10)]:  # Lanczos3, HANN, Bicubic
-        with pytest.raises(J.UnsupportedJXLException):
-            J.JxlCoder.decode_sampled(data, rw, rh, 2, mode, filt)
+    for (rw, rh, mode, filt) in [(24, 16, 3, 5), (24, 16, 3, 9), (40, 40, 2, 10), (150, 100, 1, 5), (35, 23, 3, 10)]:
+        r = ref.decode_sampled(data, w=rw, h=rh, cfg=2, scale_mode=mode, filt=filt)
+        got = J.JxlCoder.decode_sampled(data, rw, rh, 2, mode, filt)
+        assert (got.width, got.height) == (r["width"], r["height"])
+        assert (got.pixels[:, : got.width * 4] == r["pixels"][:, : got.width * 4]).all(), (rw, rh, mode, filt)
+    with pytest.raises(J.UnsupportedJXLException):
+        J.JxlCoder.decode_sampled(cases.get("rgba_lossless_128"), 40, 40, 2, 1, 5)
     # w = h = -1: no rescale (JxlCoder.kt:55-62); 0 on an axis: no rescale either (JniDecoding.cpp:116-117)
     assert J.JxlCoder.decode_sampled(data, -1, -1, 2, 1, 4).width == 96
     assert J.JxlCoder.decode_sampled(data, 0, 10, 2, 1, 4).width == 96
