@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -336,6 +337,24 @@ struct Parsed {
   std::shared_ptr<ColorMatrixTables16> cmt16;  // sources deeper than 8 bits
   size_t cm_off = 0, cm_rows_off = 0;
   bool matrix_before_resize = false;  // getFrameImpl applies it before RescaleImage, decodeSampledImageImpl after
+  // ---- frame composition (blending over earlier frames / reference slots) ----
+  // One entry per frame of the codestream up to the target, as the frame headers describe them.
+  struct SeenFrame {
+    size_t begin_byte = 0, end_byte = 0;
+    uint32_t frame_type = 0, fw = 0, fh = 0;
+    int32_t x0 = 0, y0 = 0;
+    bool covers_canvas = false, saves = false, save_before_ct = false, upsampled = false;
+    uint32_t slot = 0;
+    BlendingInfo blend, alpha_blend;
+  };
+  std::vector<SeenFrame> seen;   // filled for multi-frame codestreams
+  size_t header_bytes = 0;       // image header (frames start byte-aligned after it)
+  bool layer_only = false;       // hidden entry of a batch: this frame alone, decoded to straight RGBA at frame size
+  bool composed = false;         // the picture is the target frame blended over `layers` (indices into Batch::ps, in frame order)
+  std::vector<size_t> layers;
+  std::vector<SeenFrame> layer_info;  // blend description of every layer, then of the target frame itself (layers.size() + 1 entries)
+  size_t canvas_off = 0, canvas_bytes = 0;  // 5 canvases in the work region: reference slots 0 .. 3 and the current picture
+  std::vector<int> chain;        // frames (indices into `seen`) the target needs, in order, set by ParseRequest
 };
 
 int Fail(Parsed* p, int status, const std::string& msg) {
@@ -374,7 +393,10 @@ int ColorSpaceTag(const ImageMetadata& md, int api) {
   return JXLB_CS_SRGB;
 }
 
-void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = -1) {
+// layer_only: decode displayed-or-not frame number `target_frame` (counting EVERY frame of the codestream) alone, as a
+// layer of a composition: no independence check, no placement / orientation / rescale / colour pass / reformat.
+void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = -1, bool layer_only = false) {
+  p->layer_only = layer_only;
   if (CheckPreconditions(r, api, p)) return;
   if (!r.data || r.len == 0) {
     Fail(p, JXLB_INVALID_JXL, "empty input");
@@ -423,6 +445,7 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
   }
   // frames: decode the last one (or displayed frame `target_frame`); earlier frames must not be needed
   int nframes = 0, displayed = 0;
+  p->header_bytes = (size_t) (frame_bit / 8);
   bool saved[4] = {false, false, false, false};  // reference slots written by the frames before the target
   for (;;) {
     p->fh = FrameHeader();
@@ -434,7 +457,26 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
     ++nframes;
     const bool shown = p->fh.frame_type == 0 || p->fh.frame_type == 3;
     if (shown) ++displayed;
-    if (target_frame >= 0 ? (shown && displayed - 1 == target_frame) : p->fh.is_last) break;
+    {
+      Parsed::SeenFrame sf;
+      sf.begin_byte = (size_t) (frame_bit / 8);
+      sf.end_byte = (size_t) p->fh.end_byte;
+      sf.frame_type = p->fh.frame_type;
+      sf.fw = p->fh.coded_w;
+      sf.fh = p->fh.coded_h;
+      sf.x0 = p->fh.have_crop ? p->fh.x0 : 0;
+      sf.y0 = p->fh.have_crop ? p->fh.y0 : 0;
+      sf.covers_canvas = !p->fh.have_crop && p->fh.coded_w == md.xsize && p->fh.coded_h == md.ysize;
+      sf.saves = !p->fh.is_last && (p->fh.frame_type == 2 || (p->fh.frame_type != 1 && (p->fh.duration == 0 || p->fh.save_as_reference != 0)));
+      sf.slot = p->fh.save_as_reference & 3;
+      sf.save_before_ct = p->fh.save_before_ct;
+      sf.upsampled = p->fh.upsampling != 1;
+      sf.blend = p->fh.blend;
+      const int ai = md.alpha_channel();
+      sf.alpha_blend = (ai >= 0 && (size_t) ai < p->fh.ec_blend.size()) ? p->fh.ec_blend[ai] : p->fh.blend;
+      p->seen.push_back(sf);
+    }
+    if (layer_only ? nframes - 1 == target_frame : (target_frame >= 0 ? (shown && displayed - 1 == target_frame) : p->fh.is_last)) break;
     if (p->fh.is_last) {
       Fail(p, JXLB_BAD_ARG, "frame index out of range");
       return;
@@ -447,7 +489,7 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
   p->fw = fh.coded_w;
   p->fh_ = fh.coded_h;
   const bool covers_canvas = !fh.have_crop && fh.coded_w == md.xsize && fh.coded_h == md.ysize;
-  if (nframes > 1 || !covers_canvas) {
+  if (!layer_only && (nframes > 1 || !covers_canvas)) {
     // Frames are decoded as independent pictures.  That is what a kReplace frame is when it covers the canvas, or when
     // the canvas it is laid over is empty (its source slots were never written): then the picture is the frame at its
     // crop position over cleared pixels.  Anything else needs the earlier frames (composition): refused.
@@ -458,11 +500,45 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
       for (const BlendingInfo& b : fh.ec_blend) independent = independent && !saved[b.source & 3];
     }
     if (!independent) {
-      Fail(p, JXLB_UNSUPPORTED, "multi-frame image needing composition");
-      return;
+      // Composition: the picture is this frame blended over what earlier frames left in the reference slots.  Walk back
+      // from the target to find the frames it really depends on (a frame matters when it is stored in a slot that a later
+      // needed frame reads as its background).
+      const std::vector<Parsed::SeenFrame>& F = p->seen;
+      const int T = (int) F.size() - 1;
+      auto needs_bg = [&](const Parsed::SeenFrame& f) {
+        return !(f.covers_canvas && f.blend.mode == 0 && (!p->has_alpha || f.alpha_blend.mode == 0));
+      };
+      bool ok = true;
+      std::string why;
+      uint32_t need = 0;  // bit s: the content of reference slot s (as of the frame being looked at) is needed
+      std::vector<int> chain;
+      auto check = [&](const Parsed::SeenFrame& f) {
+        if (f.frame_type == 1) ok = false, why = "LF frame";
+        else if (f.frame_type == 2 && !f.covers_canvas) ok = false, why = "reference-only frame that is not canvas-sized (patch source)";
+        else if (f.save_before_ct && f.saves) ok = false, why = "reference frame saved before the colour transform";
+        else if (f.upsampled) ok = false, why = "upsampled frame in a composition";
+        else if (p->has_alpha && f.alpha_blend.source != f.blend.source && needs_bg(f)) ok = false, why = "alpha blended from a different reference slot than colour";
+        else if (f.blend.mode > 4 || f.alpha_blend.mode > 4) ok = false, why = "blend mode";
+      };
+      check(F[T]);
+      if (needs_bg(F[T])) need |= 1u << (F[T].blend.source & 3);
+      for (int k = T - 1; k >= 0 && ok && need; --k) {
+        if (!F[k].saves || !(need & (1u << F[k].slot))) continue;
+        check(F[k]);
+        chain.push_back(k);
+        need &= ~(1u << F[k].slot);
+        if (needs_bg(F[k])) need |= 1u << (F[k].blend.source & 3);
+      }
+      if (!ok) {
+        Fail(p, JXLB_UNSUPPORTED, "multi-frame image needing composition: " + why);
+        return;
+      }
+      std::reverse(chain.begin(), chain.end());
+      p->composed = true;
+      p->chain = chain;  // what is still in `need` was never written: an empty canvas
     }
   }
-  if (!covers_canvas) {
+  if (!covers_canvas && !p->composed && !layer_only) {
     if (md.orientation != 1 || fh.upsampling != 1) {
       Fail(p, JXLB_UNSUPPORTED, "cropped frame with orientation or upsampling");
       return;
@@ -515,6 +591,15 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
       Fail(p, JXLB_UNSUPPORTED, "colour encoding that the reference converts through its ICC path (lcms2)");
       return;
     }
+  }
+  if (layer_only) {  // a layer of a composition: the frame's own samples, nothing else
+    p->orient = 1;
+    p->out_w = p->fw;
+    p->out_h = p->fh_;
+    p->format = JXLB_FORMAT_RGBA_8888;
+    p->color_space = JXLB_CS_NONE;
+    MakeFramePlan(md, fh, p->g, p->cs.size(), &p->plan);
+    return;
   }
   // rescale (JniDecoding.cpp:116-136)
   const bool use_sampler = (r.width > 0 || r.height > 0) && (r.width != 0 && r.height != 0);
@@ -680,6 +765,65 @@ struct Batch {
     freeh(own.status_host);
   }
 
+  // Requests whose picture is a composition (ParseRequest set `composed` and the chain of frames the target depends on):
+  // every frame of the chain becomes a hidden entry of the batch -- a mini codestream (image header + that frame's bytes)
+  // decoded alone to straight RGBA at frame size -- and the owner composites them in order in Run().
+  std::vector<std::vector<uint8_t>> layer_streams;  // owns the mini codestreams until they have been parsed
+  void ExpandCompositions(const jxlb_request* reqs, const int32_t* frame_index) {
+    (void) frame_index;
+    const size_t nreq = ps.size();
+    struct Todo {
+      size_t owner;
+      int frame;
+    };
+    std::vector<Todo> todo;
+    for (size_t i = 0; i < nreq; ++i) {
+      Parsed& p = ps[i];
+      if (p.status != JXLB_OK || !p.composed) continue;
+      for (int k : p.chain) todo.push_back(Todo{i, k});
+    }
+    if (todo.empty()) return;
+    const size_t first_hidden = ps.size();
+    ps.resize(first_hidden + todo.size());
+    layer_streams.resize(todo.size());
+    ParallelFor(todo.size(), [&](size_t t) {
+      const Parsed& owner = ps[todo[t].owner];
+      const Parsed::SeenFrame& sf = owner.seen[todo[t].frame];
+      std::vector<uint8_t>& mini = layer_streams[t];
+      mini.assign(owner.cs.begin(), owner.cs.begin() + owner.header_bytes);
+      mini.insert(mini.end(), owner.cs.begin() + sf.begin_byte, owner.cs.begin() + sf.end_byte);
+      jxlb_request r = reqs[todo[t].owner];
+      r.data = mini.data();
+      r.len = mini.size();
+      r.width = r.height = -1;
+      r.color_config = JXLB_CONFIG_RGBA_8888;
+      Parsed& hp = ps[first_hidden + t];
+      try {
+        ParseRequest(r, api_level, &hp, 0, /*layer_only=*/true);
+      } catch (const std::exception&) {
+        hp = Parsed();
+        Fail(&hp, JXLB_OOM, "Not enough memory to decode this image");
+      }
+      hp.layer_only = true;
+    });
+    layer_streams.clear();
+    for (size_t t = 0; t < todo.size(); ++t) {
+      Parsed& owner = ps[todo[t].owner];
+      const Parsed& hp = ps[first_hidden + t];
+      if (hp.status != JXLB_OK && owner.status == JXLB_OK) {
+        Fail(&owner, hp.status, hp.message);
+        continue;
+      }
+      owner.layers.push_back(first_hidden + t);
+      owner.layer_info.push_back(owner.seen[todo[t].frame]);
+    }
+    for (size_t i = 0; i < nreq; ++i)
+      if (ps[i].status == JXLB_OK && ps[i].composed) ps[i].layer_info.push_back(ps[i].seen.back());
+    // a failed owner drops its layers
+    for (size_t t = 0; t < todo.size(); ++t)
+      if (ps[todo[t].owner].status != JXLB_OK && ps[first_hidden + t].status == JXLB_OK) Fail(&ps[first_hidden + t], JXLB_ERROR, "owner failed");
+  }
+
   // Host side: parse every request, lay out the batch.  No CUDA calls.
   void Parse(const jxlb_request* reqs, size_t count, int api, const int32_t* frame_index = nullptr) {
     n = count;
@@ -699,10 +843,12 @@ struct Batch {
         Fail(&ps[i], JXLB_ERROR, std::string("Error while decoding: ") + e.what());
       }
     });
-    frame_of.assign(n, 0);
-    final_off.assign(n, 0);
-    final_bytes.assign(n, 0);
-    for (size_t i = 0; i < n; ++i) {
+    ExpandCompositions(reqs, frame_index);
+    const size_t np = ps.size();  // requests + hidden layer entries
+    frame_of.assign(np, 0);
+    final_off.assign(np, 0);
+    final_bytes.assign(np, 0);
+    for (size_t i = 0; i < np; ++i) {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
       // an image whose planes alone could not be allocated fails by itself instead of failing the batch's allocation
@@ -717,7 +863,13 @@ struct Batch {
       p.stage_stride = Align256((size_t) p.fw * 4 * (p.out16 ? 2 : 1));
       p.stage_off = stage_total;
       // the fused VarDCT kernel packs straight into final_out; only modular frames (and the unfused debug path) stage RGBA
-      if (p.plan.proto.encoding != 0 || UseUnfusedFilters() || p.resize || p.color_matrix || p.orient != 1 || p.placed) stage_total += Align256(p.stage_stride * p.fh_);
+      if (p.plan.proto.encoding != 0 || UseUnfusedFilters() || p.resize || p.color_matrix || p.orient != 1 || p.placed || p.layer_only || p.composed)
+        stage_total += Align256(p.stage_stride * p.fh_);
+      if (p.composed) {
+        p.canvas_bytes = Align256((size_t) p.md.xsize * p.md.ysize * 16);  // float RGBA reference slots; the picture fits in one too
+        p.canvas_off = work_total;
+        work_total += 5 * p.canvas_bytes;
+      }
       if (p.placed) {
         p.place_off = work_total;
         work_total += Align256((size_t) p.md.xsize * p.md.ysize * 4 * (p.out16 ? 2 : 1));
@@ -747,7 +899,7 @@ struct Batch {
       }
       xyb_slot_bytes = std::max(xyb_slot_bytes, Align256(p.plan.xyb_bytes * (UseUnfusedFilters() ? 2 : 1)));
       if (p.plan.proto.encoding == 0) ++n_vardct;
-      final_bytes[i] = (size_t) p.out_w * FormatBytesPerPixel((uint32_t) p.format) * p.out_h;
+      final_bytes[i] = p.layer_only ? 0 : (size_t) p.out_w * FormatBytesPerPixel((uint32_t) p.format) * p.out_h;
       final_off[i] = final_total;
       final_total += Align256(final_bytes[i]);
       frame_of[i] = nframes++;
@@ -795,7 +947,7 @@ struct Batch {
     sl_lf.bytes_per_job = Align256(job_bytes(sl_lf));
     bool grp_modular = false, grp_local_tree = false;
     uint32_t grp_dim = 256;
-    for (size_t i = 0; i < n; ++i) {
+    for (size_t i = 0; i < ps.size(); ++i) {
       if (ps[i].status != JXLB_OK || ps[i].plan.proto.single_section) continue;
       const FrameDev& f = ps[i].plan.proto;
       if (f.num_mod_channels > f.global_mod_decoded) {
@@ -859,7 +1011,7 @@ struct Batch {
     CUDA_OK(cudaEventRecord(ev_ring[0][0], s));
     uint8_t* stg = buf->staging.p;
     frames.assign(nframes, FrameDev());
-    ParallelFor(n, [&](size_t i) {
+    ParallelFor(ps.size(), [&](size_t i) {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) return;
       FillConstRegion(p.plan, p.cs.data(), p.fh, p.g, stg + p.const_off);
@@ -946,7 +1098,7 @@ struct Batch {
     // everything enqueued on `s` so far (the upload, the previous run) precedes the LF stage
     CUDA_OK(cudaEventRecord(ev_uploaded, s));
     CUDA_OK(cudaStreamWaitEvent(lf_stream, ev_uploaded, 0));
-    for (size_t i = 0; i < n; ++i) {
+    for (size_t i = 0; i < ps.size(); ++i) {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
       uint8_t* wb = buf->work_buf.p + p.work_off;
@@ -959,7 +1111,7 @@ struct Batch {
     }
     CUDA_OK(cudaEventRecord(ev_lf_done, lf_stream));
     // meanwhile, on the dense stream: clear the coefficient planes
-    for (size_t i = 0; i < n; ++i) {
+    for (size_t i = 0; i < ps.size(); ++i) {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
       uint8_t* wb = buf->work_buf.p + p.work_off;
@@ -983,7 +1135,9 @@ struct Batch {
     EnsureSampleEvents();
     cudaEvent_t* sev = sample_ev[run_index].data();
     size_t sampled = 0, vd = 0;
-    for (size_t i = 0; i < n; ++i) {
+    // hidden layer entries first: their pictures must exist when the owners composite them (one stream: enqueue order)
+    for (size_t oi = 0; oi < ps.size(); ++oi) {
+      const size_t i = oi < ps.size() - n ? n + oi : oi - (ps.size() - n);
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
       const FrameDev& f = frames[frame_of[i]];
@@ -1012,7 +1166,7 @@ struct Batch {
       pk.dst_stride = pk.width * FormatBytesPerPixel(pk.format);
       pk.dst = buf->final_out.p + final_off[i];
       const PackParams pk_final = pk;
-      const bool post = p.resize || p.color_matrix || p.orient != 1 || p.placed;
+      const bool post = p.resize || p.color_matrix || p.orient != 1 || p.placed || p.layer_only || p.composed;
       if (post) {  // the decode stage hands straight RGBA8 to the rescaler / colour pass; ReformatColorConfig runs on their result
         pk.format = 4;  // staging: samples as decoded (RGBA8, or RGBA16 for sources deeper than 8 bits)
         pk.associate = 0;
@@ -1041,8 +1195,47 @@ struct Batch {
         LaunchModularToRgba(f, od, s);
         if (!post) LaunchPack(pk, s);
       }
+      if (p.layer_only) continue;  // a layer: its straight RGBA picture stays in the staging buffer for its owner
       const uint8_t* res = od.data;
       uint32_t res_stride = od.stride_bytes;
+      if (p.composed) {
+        // reference slots 0 .. 3 and the current picture; every layer is blended over the slot it names and stored in
+        // the slot it is saved to (blending reads and writes a pixel in the same thread, so source == destination is fine)
+        const uint32_t bpp = p.out16 ? 8 : 4;
+        uint8_t* canvas = buf->work_buf.p + p.canvas_off;
+        float4* slot[4] = {nullptr, nullptr, nullptr, nullptr};
+        uint8_t* cur = canvas + 4 * p.canvas_bytes;
+        for (size_t l = 0; l < p.layer_info.size(); ++l) {
+          const Parsed::SeenFrame& sf = p.layer_info[l];
+          const bool own = l + 1 == p.layer_info.size();
+          const Parsed& lp = own ? p : ps[p.layers[l]];
+          CompositeParams cpz{};
+          cpz.bg = slot[sf.blend.source & 3];
+          cpz.fg = buf->stage_out.p + lp.stage_off;
+          cpz.fg_stride = (uint32_t) lp.stage_stride;
+          cpz.fw = lp.fw;
+          cpz.fh = lp.fh_;
+          cpz.x0 = sf.x0;
+          cpz.y0 = sf.y0;
+          cpz.out = own ? cur : nullptr;
+          cpz.save = (!own && sf.saves) ? reinterpret_cast<float4*>(canvas + sf.slot * p.canvas_bytes) : nullptr;
+          cpz.cw = p.md.xsize;
+          cpz.ch = p.md.ysize;
+          cpz.canvas_stride = p.md.xsize * bpp;
+          cpz.bits16 = p.out16;
+          cpz.has_alpha = p.has_alpha;
+          cpz.alpha_premultiplied = p.alpha_premultiplied;
+          cpz.mode_color = sf.blend.mode;
+          cpz.mode_alpha = sf.alpha_blend.mode;
+          cpz.clamp = sf.blend.clamp || sf.alpha_blend.clamp;
+          cpz.dither = (own && !p.out16) ? reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(ctx->nt_dev) + offsetof(NumericTables, dither)) : nullptr;
+          cpz.orientation = p.md.orientation;
+          LaunchComposite(cpz, s);
+          if (cpz.save) slot[sf.slot] = cpz.save;
+        }
+        res = cur;
+        res_stride = p.md.xsize * bpp;
+      }
       const ColorMatrixPlan* cm_dev = reinterpret_cast<const ColorMatrixPlan*>(buf->const_buf.p + p.cm_off);
       if (p.placed) {
         uint8_t* dst = buf->work_buf.p + p.place_off;
@@ -1187,7 +1380,7 @@ struct Batch {
       }
     if (ran) CUDA_OK(cudaEventSynchronize(ev[7]));  // every kernel of the run is done: the status words are final
     uint32_t* sh = reinterpret_cast<uint32_t*>(buf->status_host.p);
-    for (size_t i = 0; i < n; ++i) {
+    for (size_t i = 0; i < ps.size(); ++i) {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
       CUDA_OK(cudaMemcpyAsync(sh + p.status_base, buf->work_buf.p + p.work_off + p.plan.off_status, (size_t) p.plan.num_streams * 4,
@@ -1231,14 +1424,22 @@ struct Batch {
     tm.ms[4] = stage_ms[6];
     tm.ms[5] = stage_ms[7] + stage_ms[6];
     const int32_t* shs = reinterpret_cast<const int32_t*>(buf->status_host.p);
-    for (size_t i = 0; i < n; ++i) {
+    // hidden layer entries first (indices n ..), so that an owner sees its layers' failures
+    for (size_t oi = 0; oi < ps.size(); ++oi) {
+      const size_t i = oi < ps.size() - n ? n + oi : oi - (ps.size() - n);
       Parsed& p = ps[i];
       auto drop = [&]() {
-        if (!result[i]) return;
+        if (i >= n || !result[i]) return;
         if (to_host) Pool().Put(result[i]);
         else cudaFree(result[i]);
         result[i] = nullptr;
       };
+      if (p.status == JXLB_OK)
+        for (size_t l : p.layers)
+          if (ps[l].status != JXLB_OK) {
+            Fail(&p, ps[l].status, ps[l].message);
+            break;
+          }
       if (p.status != JXLB_OK) {
         drop();
         continue;
@@ -1265,7 +1466,7 @@ struct Batch {
         drop();
         continue;
       }
-      if (!out) continue;
+      if (!out || i >= n) continue;
       DecodedImage& d = (*out)[i];
       d.width = p.out_w;
       d.height = p.out_h;

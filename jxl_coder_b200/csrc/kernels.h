@@ -67,6 +67,23 @@ const uint8_t* LaunchResize(const ResizeDev& r, cudaStream_t stream);
 // steps_host: the host copy of f.sq_steps (launch geometry).
 void LaunchUnsqueeze(const FrameDev& f, const SqStep* steps_host, cudaStream_t stream);
 
+// One step of frame composition (kernels_post.cu): the frame `fg` (fw x fh straight RGBA8 / RGBA16 at (x0, y0), may stick out
+// of the canvas) blended over the canvas `bg` (null = empty canvas) into `out` (and `save`: the reference slot the frame
+// is stored in, may be null).  Blend modes as coded: 0 kReplace, 1 kAdd, 2 kBlend, 3 kAlphaWeightedAdd, 4 kMul.
+struct CompositeParams {
+  const float4* bg;      // reference slot the frame is blended over: cw x ch float RGBA in [0, 1], null = empty canvas
+  const uint8_t* fg;     // the frame: straight RGBA8 / RGBA16
+  uint8_t* out;          // the picture as integers (last step only; null for intermediate frames)
+  float4* save;          // reference slot the result is stored in (null = not stored)
+  uint32_t fg_stride, fw, fh;
+  int32_t x0, y0;
+  uint32_t cw, ch, canvas_stride;
+  uint32_t bits16, has_alpha, alpha_premultiplied, mode_color, mode_alpha, clamp;
+  const float* dither;   // the 32x32 dither table for the LAST step of an 8-bit picture, else null
+  uint32_t orientation;  // codestream orientation (the dither pattern is indexed by the flipped position, pixel_stages.h)
+};
+void LaunchComposite(const CompositeParams& p, cudaStream_t stream);
+
 // Lays an fw x fh frame at (x0, y0) over a cleared cw x ch canvas (colour 0, alpha fill_alpha in the sample depth).
 void LaunchPlace(const uint8_t* src, uint32_t src_stride, uint32_t fw, uint32_t fh, uint32_t bpp, int32_t x0, int32_t y0, uint32_t fill_alpha,
                  uint8_t* dst, uint32_t dst_stride, uint32_t cw, uint32_t ch, cudaStream_t stream);

@@ -181,6 +181,109 @@ __global__ void __launch_bounds__(256) PlaceKernel(const uint8_t* __restrict__ s
 
 }  // namespace
 
+namespace {
+// Frame composition (JPEG XL blending, ISO/IEC 18181-1 F.? / libjxl blending.cc): one thread per canvas pixel.  Samples are
+// straight RGBA8 / RGBA16; the arithmetic is float on v * (1 / max) like libjxl's, rounded back with lrintf.
+template <typename Pixel, int kMax>
+__global__ void __launch_bounds__(256) CompositeKernel(const CompositeParams p) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= p.cw || y >= p.ch) return;
+  // reference slots hold unrounded float samples in [0, 1] like libjxl's (an animation blends many frames in a row)
+  float4 bgf = make_float4(0.f, 0.f, 0.f, p.has_alpha ? 0.f : 1.f);
+  if (p.bg) bgf = p.bg[(size_t) y * p.cw + x];
+  float of[4] = {bgf.x, bgf.y, bgf.z, bgf.w};
+  bool blended = false;
+  const int32_t fx = (int32_t) x - p.x0, fy = (int32_t) y - p.y0;
+  if (fx >= 0 && fy >= 0 && fx < (int32_t) p.fw && fy < (int32_t) p.fh) {
+    uint32_t fg[4];
+    const Pixel v = *reinterpret_cast<const Pixel*>(p.fg + (size_t) fy * p.fg_stride + (size_t) fx * sizeof(Pixel));
+    if (sizeof(Pixel) == 4) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(&v);
+      fg[0] = w & 0xFF; fg[1] = (w >> 8) & 0xFF; fg[2] = (w >> 16) & 0xFF; fg[3] = w >> 24;
+    } else {
+      const uint2 w = *reinterpret_cast<const uint2*>(&v);
+      fg[0] = w.x & 0xFFFF; fg[1] = w.x >> 16; fg[2] = w.y & 0xFFFF; fg[3] = w.y >> 16;
+    }
+    blended = true;
+    {
+      // separately rounded operations in libjxl's order (its blending loops are scalar code without FMA)
+      const float inv = 1.0f / (float) kMax;
+      float fa = p.has_alpha ? __fmul_rn((float) fg[3], inv) : 1.0f;
+      const float ba = bgf.w;
+      if (p.clamp) fa = fminf(fmaxf(fa, 0.0f), 1.0f);
+      const float one_m_fa = __fsub_rn(1.0f, fa);
+      const float na = __fsub_rn(1.0f, __fmul_rn(one_m_fa, __fsub_rn(1.0f, ba)));
+      const float rna = na > 0.0f ? __fdiv_rn(1.0f, na) : 0.0f;
+      const float bgc[3] = {bgf.x, bgf.y, bgf.z};
+      float oc[3];
+      for (int c = 0; c < 3; ++c) {
+        const float f = __fmul_rn((float) fg[c], inv), b = bgc[c];
+        float o;
+        switch (p.mode_color) {
+          case 0: o = f; break;
+          case 1: o = __fadd_rn(b, f); break;
+          case 2:
+            if (!p.has_alpha) o = f;
+            else if (p.alpha_premultiplied) o = __fadd_rn(f, __fmul_rn(b, one_m_fa));
+            else o = __fmul_rn(__fadd_rn(__fmul_rn(f, fa), __fmul_rn(__fmul_rn(b, ba), one_m_fa)), rna);
+            break;
+          case 3: o = __fadd_rn(b, __fmul_rn(f, fa)); break;
+          default: o = __fmul_rn(b, p.clamp ? fminf(fmaxf(f, 0.0f), 1.0f) : f); break;
+        }
+        oc[c] = o;
+      }
+      float oa = 1.0f;
+      if (p.has_alpha) {
+        const float f = __fmul_rn((float) fg[3], inv);
+        switch (p.mode_alpha) {
+          case 0: oa = f; break;
+          case 1: oa = __fadd_rn(ba, f); break;
+          case 2: oa = na; break;
+          case 3: oa = ba; break;   // the alpha channel itself is carried over by kAlphaWeightedAdd
+          default: oa = __fmul_rn(ba, p.clamp ? fa : f); break;
+        }
+      }
+      of[0] = oc[0]; of[1] = oc[1]; of[2] = oc[2]; of[3] = p.has_alpha ? oa : 1.0f;
+    }
+  }
+  (void) blended;
+  if (p.save) p.save[(size_t) y * p.cw + x] = make_float4(of[0], of[1], of[2], of[3]);
+  if (!p.out) return;
+  // The picture handed out goes through libjxl's float pipeline when frames are blended, whose 8-bit conversion adds the
+  // 32x32 blue-noise dither to EVERY channel, alpha included.  The stage runs over the frame's rectangle in 4-lane vectors
+  // starting at its left edge and loads the pattern with one unaligned vector load at (y % 32) * 32 + (x % 32): lanes
+  // that cross column 32 read on into the NEXT row of the table instead of wrapping.  Reproduced (bit-exact against the
+  // reference on every blend mode, tests/test_gpu_composition.py).
+  float dth = 0.0f;
+  if (p.dither && kMax == 255) {
+    const uint32_t o = p.orientation;
+    if (o == 1) {
+      const uint32_t left = p.x0 > 0 ? (uint32_t) p.x0 : 0u;
+      const uint32_t start = x >= left ? left + ((x - left) & ~3u) : (x & ~3u);
+      dth = p.dither[((y & 31) * 32 + (start & 31) + (x - start)) & 1023];
+    } else {
+      const bool flip_x = o == 2 || o == 3 || o == 7 || o == 8, flip_y = o == 3 || o == 4 || o == 6 || o == 7;
+      const uint32_t ox = flip_x ? p.cw - 1 - x : x, oy = flip_y ? p.ch - 1 - y : y;
+      dth = p.dither[(oy & 31) * 32 + (ox & 31)];
+    }
+  }
+  uint32_t out[4];
+  for (int c = 0; c < 4; ++c) out[c] = (uint32_t) lrintf(fminf(fmaxf(of[c] * (float) kMax + dth, 0.0f), (float) kMax));
+  if (!p.has_alpha) out[3] = (uint32_t) kMax;
+  uint8_t* dst = p.out + (size_t) y * p.canvas_stride + (size_t) x * sizeof(Pixel);
+  if (sizeof(Pixel) == 4) *reinterpret_cast<uint32_t*>(dst) = out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24);
+  else *reinterpret_cast<uint2*>(dst) = make_uint2(out[0] | (out[1] << 16), out[2] | (out[3] << 16));
+}
+}  // namespace
+
+void LaunchComposite(const CompositeParams& p, cudaStream_t stream) {
+  if (!p.cw || !p.ch) return;
+  dim3 grid((p.cw + 255) / 256, p.ch, 1);
+  if (p.bits16) CompositeKernel<uint2, 65535><<<grid, 256, 0, stream>>>(p);
+  else CompositeKernel<uint32_t, 255><<<grid, 256, 0, stream>>>(p);
+  ++g_launches_ac;
+}
+
 void LaunchPlace(const uint8_t* src, uint32_t src_stride, uint32_t fw, uint32_t fh, uint32_t bpp, int32_t x0, int32_t y0, uint32_t fill_alpha,
                  uint8_t* dst, uint32_t dst_stride, uint32_t cw, uint32_t ch, cudaStream_t stream) {
   if (!cw || !ch) return;

@@ -307,6 +307,99 @@ int ref_encode_ex(const uint8_t *pixels, size_t npix_bytes, uint32_t w, uint32_t
   return 0;
 }
 
+// Layered / composed images, libjxl encoder API directly: nlayers frames, frame i = a crop of size dims[i] = {x0, y0, w, h}
+// of RGBA (or RGB) u8 pixels with blend[i] = {mode, source, save_as_reference, duration}; canvas w x h.  Used ONLY to
+// stage inputs for the composition tests (cropped frames, kBlend / kAdd / kMul over reference slots).
+int ref_encode_layers(const uint8_t *pixels, uint32_t w, uint32_t h, int channels, int lossless, float distance, int nlayers,
+                      const int32_t *dims, const int32_t *blend, int animation, int effort, uint8_t **out, size_t *out_len) {
+  auto enc = JxlEncoderMake(nullptr);
+  auto runner = JxlThreadParallelRunnerMake(nullptr, JxlThreadParallelRunnerDefaultNumWorkerThreads());
+  if (JXL_ENC_SUCCESS != JxlEncoderSetParallelRunner(enc.get(), JxlThreadParallelRunner, runner.get())) return 1;
+  JxlBasicInfo bi;
+  JxlEncoderInitBasicInfo(&bi);
+  bi.xsize = w;
+  bi.ysize = h;
+  bi.bits_per_sample = 8;
+  bi.uses_original_profile = lossless ? JXL_TRUE : JXL_FALSE;
+  bi.num_color_channels = 3;
+  const bool alpha = channels == 4;
+  if (alpha) {
+    bi.num_extra_channels = 1;
+    bi.alpha_bits = 8;
+  }
+  if (animation) {
+    bi.have_animation = JXL_TRUE;
+    bi.animation.tps_numerator = 1000;
+    bi.animation.tps_denominator = 1;
+    bi.animation.num_loops = 0;
+    bi.animation.have_timecodes = JXL_FALSE;
+  }
+  if (JXL_ENC_SUCCESS != JxlEncoderSetBasicInfo(enc.get(), &bi)) return 2;
+  if (alpha) {
+    JxlExtraChannelInfo ci;
+    JxlEncoderInitExtraChannelInfo(JXL_CHANNEL_ALPHA, &ci);
+    ci.bits_per_sample = 8;
+    ci.alpha_premultiplied = 0;
+    if (JXL_ENC_SUCCESS != JxlEncoderSetExtraChannelInfo(enc.get(), 0, &ci)) return 3;
+  }
+  JxlColorEncoding ce;
+  JxlColorEncodingSetToSRGB(&ce, JXL_FALSE);
+  if (JXL_ENC_SUCCESS != JxlEncoderSetColorEncoding(enc.get(), &ce)) return 4;
+  const uint8_t *px = pixels;
+  for (int i = 0; i < nlayers; ++i) {
+    JxlEncoderFrameSettings *fs = JxlEncoderFrameSettingsCreate(enc.get(), nullptr);
+    if (lossless) {
+      if (JXL_ENC_SUCCESS != JxlEncoderSetFrameLossless(fs, JXL_TRUE)) return 5;
+    } else if (JXL_ENC_SUCCESS != JxlEncoderSetFrameDistance(fs, distance)) {
+      return 5;
+    }
+    JxlEncoderFrameSettingsSetOption(fs, JXL_ENC_FRAME_SETTING_EFFORT, effort);
+    JxlFrameHeader fh;
+    JxlEncoderInitFrameHeader(&fh);
+    const int32_t *d = dims + 4 * i, *b = blend + 4 * i;
+    fh.duration = (uint32_t) b[3];
+    fh.layer_info.have_crop = JXL_TRUE;
+    fh.layer_info.crop_x0 = d[0];
+    fh.layer_info.crop_y0 = d[1];
+    fh.layer_info.xsize = (uint32_t) d[2];
+    fh.layer_info.ysize = (uint32_t) d[3];
+    fh.layer_info.blend_info.blendmode = (JxlBlendMode) b[0];
+    fh.layer_info.blend_info.source = (uint32_t) b[1];
+    fh.layer_info.blend_info.alpha = 0;
+    fh.layer_info.blend_info.clamp = JXL_FALSE;
+    fh.layer_info.save_as_reference = (uint32_t) b[2];
+    if (JXL_ENC_SUCCESS != JxlEncoderSetFrameHeader(fs, &fh)) return 6;
+    if (alpha) {
+      JxlBlendInfo abi = fh.layer_info.blend_info;
+      if (JXL_ENC_SUCCESS != JxlEncoderSetExtraChannelBlendInfo(fs, 0, &abi)) return 7;
+    }
+    JxlPixelFormat pf = {(uint32_t) channels, JXL_TYPE_UINT8, JXL_NATIVE_ENDIAN, 0};
+    const size_t bytes = (size_t) d[2] * d[3] * channels;
+    if (JXL_ENC_SUCCESS != JxlEncoderAddImageFrame(fs, &pf, px, bytes)) return 8;
+    px += bytes;
+  }
+  JxlEncoderCloseInput(enc.get());
+  std::vector<uint8_t> comp(1 << 16);
+  uint8_t *next = comp.data();
+  size_t avail = comp.size();
+  JxlEncoderStatus r = JXL_ENC_NEED_MORE_OUTPUT;
+  while (r == JXL_ENC_NEED_MORE_OUTPUT) {
+    r = JxlEncoderProcessOutput(enc.get(), &next, &avail);
+    if (r == JXL_ENC_NEED_MORE_OUTPUT) {
+      size_t off = next - comp.data();
+      comp.resize(comp.size() * 2);
+      next = comp.data() + off;
+      avail = comp.size() - off;
+    }
+  }
+  if (r != JXL_ENC_SUCCESS) return 9;
+  size_t n = next - comp.data();
+  *out = (uint8_t *) malloc(n);
+  memcpy(*out, comp.data(), n);
+  *out_len = n;
+  return 0;
+}
+
 // Animated: nframes frames of w*h*channels u8, each with `duration` ticks (tps 1000/1), via the reference's
 // JxlAnimatedEncoder (interop/JxlAnimatedEncoder.hpp:55-190).
 int ref_anim_encode(const uint8_t *frames, uint32_t w, uint32_t h, int colorspace, int compression, int nframes,

@@ -188,6 +188,23 @@ def encode_ex(pixels, w, h, channels, bits=8, lossless=False, distance=1.0, alph
     return _take_bytes(out, n)
 
 
+def encode_layers(layers, w, h, channels=4, lossless=True, distance=1.0, animation=False, effort=5):
+    """layers: list of dict(pixels=[h_i, w_i, channels] u8, x0, y0, mode, source, save, duration).  Blend modes as in
+    jxl/codestream_header.h: 0 replace, 1 add, 2 blend, 3 muladd, 4 mul.  TEST INPUT GENERATION ONLY."""
+    L = lib()
+    L.ref_encode_layers.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
+    px = np.concatenate([np.ascontiguousarray(l["pixels"], dtype=np.uint8).reshape(-1) for l in layers])
+    dims = np.array([[l.get("x0", 0), l.get("y0", 0), l["pixels"].shape[1], l["pixels"].shape[0]] for l in layers], np.int32)
+    blend = np.array([[l.get("mode", 0), l.get("source", 0), l.get("save", 0), l.get("duration", 0)] for l in layers], np.int32)
+    out, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+    rc = L.ref_encode_layers(px.ctypes.data, w, h, channels, int(lossless), distance, len(layers), dims.ctypes.data, blend.ctypes.data,
+                             int(animation), effort, C.byref(out), C.byref(n))
+    if rc:
+        raise RefError("encode_layers", f"rc={rc}")
+    return _take_bytes(out, n)
+
+
 def anim_encode(frames, w, h, colorspace=2, compression=2, duration=40, num_loops=0, quality=90, effort=7,
                 decoding_speed=0):
     fr = np.ascontiguousarray(frames)
