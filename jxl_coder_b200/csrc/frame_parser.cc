@@ -311,7 +311,7 @@ int ParseFrameHeader(const uint8_t* cs, size_t cs_padded, size_t cs_len, const I
       auto read_blend = [&](BlendingInfo* bi) {
         bi->mode = br.U32(0, 0, 1, 0, 2, 0, 3, 2);
         if (nextra > 0 && (bi->mode == 2 || bi->mode == 3)) bi->alpha_channel = br.U32(0, 0, 1, 0, 2, 0, 3, 3);
-        if (nextra > 0 && (bi->mode == 2 || bi->mode == 3 || bi->mode == 4)) bi->clamp = br.Read(1);
+        if ((nextra > 0 && (bi->mode == 2 || bi->mode == 3)) || bi->mode == 4) bi->clamp = br.Read(1);  // kMul carries it even without extra channels
         if (bi->mode != 0 || !full) bi->source = br.Read(2);
       };
       read_blend(&fh->blend);
