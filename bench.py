@@ -350,6 +350,119 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the decode path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    os.environ.setdefault("JXLB_PINNED_POOL_MB", str(max(8192, 40960 // world)))
+    os.environ.setdefault("JXLB_HOST_THREADS", str(max(2, (os.cpu_count() or 8) // world)))
+    return torch, dist, world, rank, local
+
+
+def _timed_steps(torch, dist, world, step, steps, warmup):
+    """W warm-up steps, then K timed steps between barrier + synchronize; returns seconds (max over ranks)."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warmup):
+        step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_c3(args):
+    """configs[2]: 256 x 1080p lossy -> RGBA_F16, the batch sharded over the ranks by compressed size (strong scaling: the
+    256 images are the whole job at every N).  Host codestreams in, pinned host RGBA_F16 out (e2e through jxlb_decode_batch)."""
+    torch, dist, world, rank, local = _dist_setup()
+    import jxl_coder_b200 as J
+    from jxl_coder_b200 import shard
+    from oracle import gen_inputs
+    J.load_library()
+    distinct = [gen_inputs.c3_image(i) for i in range(4)]
+    datas = [distinct[i % 4] for i in range(256)]
+    idx, mine = shard.shard_for_rank(datas, world, rank)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = J.kernel_launches()
+
+    def step():
+        for b in J.decode_batch(mine, config=3, device=local, keep_native=True):
+            b.free()
+    secs = _timed_steps(torch, dist, world, step, args.steps, max(3, args.warmup))
+    launches = J.kernel_launches() - launches0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if rank != 0:
+        return
+    mp = 256 * 1920 * 1080 / 1e6
+    value = mp * args.steps / secs
+    out = {"metric": "Mpixels/s decoded (JXL->RGBA_F16)", "value": round(value, 1), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(3, args.warmup), "ms_per_step": round(1e3 * secs / args.steps, 2), "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "batch of 256 synthetic 1920x1080 lossy VarDCT (q=90) JXL -> RGBA_F16, sharded over the GPUs by compressed size (configs[2]); 4 distinct images cycled",
+                      "images_per_gpu": len(mine), "l2": "inputs_larger_than_L2 (each step touches > 9 GB of planes)"},
+           "e2e": {"value": round(value, 1), "unit": "MP/s", "h2d_bytes_per_step": sum(len(d) for d in datas), "d2h_bytes_per_step": 256 * 1920 * 1080 * 8,
+                   "api": "jxlb_decode_batch (host buffers -> pinned host RGBA_F16), one synchronous call per rank per step"},
+           "gpu_launches": int(launches), "clocks": sampler.summary()}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_c5(args):
+    """configs[4]: the 120-frame 1024x1024 RGBA lossy animation, every frame through JxlAnimatedImage.getFrame; the frames
+    are alternated over the ranks (frame i on rank i % N): each rank opens the file and asks for its frames in order."""
+    torch, dist, world, rank, local = _dist_setup()
+    import jxl_coder_b200 as J
+    from oracle import gen_inputs
+    J.load_library()
+    data = gen_inputs.c5_animation()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = J.kernel_launches()
+
+    def step():
+        a = J.JxlAnimatedImage(data, J.PreferredColorConfig.RGBA_8888)
+        n = a.number_of_frames
+        for i in range(rank, n, world):
+            a.get_frame(i)
+        a.close()
+    secs = _timed_steps(torch, dist, world, step, args.steps, max(3, args.warmup))
+    launches = J.kernel_launches() - launches0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if rank != 0:
+        return
+    mp = 120 * 1024 * 1024 / 1e6
+    value = mp * args.steps / secs
+    out = {"metric": "Mpixels/s decoded (JXL->RGBA8)", "value": round(value, 1), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(3, args.warmup), "ms_per_step": round(1e3 * secs / args.steps, 2), "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "JxlAnimatedImage: 120-frame 1024x1024 RGBA lossy animation, getFrame(i) for every frame, frames alternated over the GPUs (configs[4])",
+                      "ms_per_frame": round(1e3 * secs / args.steps / 120, 3)},
+           "e2e": {"value": round(value, 1), "unit": "MP/s", "h2d_bytes_per_step": len(data), "d2h_bytes_per_step": 120 * 1024 * 1024 * 4,
+                   "api": "jxlb_anim_open + jxlb_anim_get_frame per frame (host file -> pinned host RGBA8)"},
+           "gpu_launches": int(launches), "clocks": sampler.summary()}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -361,9 +474,15 @@ def main():
                     help="prepared batches (decode contexts) alternated by the device-resident measurement")
     ap.add_argument("--depth", type=int, default=int(os.environ.get("JXLB_BENCH_DEPTH", "5")),
                     help="batches the e2e measurement keeps in flight (jxlb_decode_batch_submit / _collect, one caller thread)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2 = BASELINE configs[1] (the headline, default); c3 = configs[2] (256 x 1080p -> RGBA_F16 sharded); c5 = configs[4] (animation)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c3":
+        run_c3(args)
+    elif args.config == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 

@@ -1,10 +1,10 @@
 """Multi-GPU batches: one process per GPU, images sharded across ranks, no data-path collective.
 
 JPEG XL images of a batch are independent, so a batch partitions over the ranks of a torch.distributed
-job and every rank decodes its shard on its own GPU through the C ABI.  The only communication is control-plane: the
-(index -> rank) assignment is computed identically on every rank from the compressed sizes, and -- only when the caller
-asks for the pixels in one place -- decoded images are gathered to a destination rank (NCCL for device tensors over
-NVLink, gloo for host tensors in the CPU tests).
+job and every rank decodes its shard on its own GPU through the C ABI.  The only communication is control-plane (the (index -> rank) assignment is computed identically on every rank from the
+compressed sizes) plus, only when the caller asks for the pixels in one place, a gather of the decoded images:
+decode_batch_sharded_device leaves every image in HBM and moves it to the destination rank's GPU with NCCL point-to-point
+transfers (device buffers over NVLink / NVSwitch); decode_batch_sharded is the host-array variant (gloo in the CPU tests).
 """
 import numpy as np
 
@@ -73,3 +73,69 @@ def decode_batch_sharded(datas, decode_fn, world_size=None, rank=None, gather_to
         for w in ws:
             w.wait()
     return result
+
+
+class _DevView:
+    """__cuda_array_interface__ over a decoded image left in HBM by the C ABI (jxlb_image.data on device >= 0)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(bitmap):
+    """uint8 CUDA tensor [height, stride] aliasing a Bitmap decoded with output_device >= 0 (zero-copy; keep the Bitmap alive)."""
+    import torch
+    if bitmap.device is None or bitmap.device < 0 or not bitmap.device_ptr:
+        raise ValueError("the bitmap is not in device memory")
+    n = bitmap.stride * bitmap.height
+    with torch.cuda.device(bitmap.device):
+        t = torch.as_tensor(_DevView(bitmap.device_ptr, n), device="cuda:%d" % bitmap.device)
+    return t.view(bitmap.height, bitmap.stride)
+
+
+def decode_batch_sharded_device(datas, device, gather_to=None, group=None, **decode_kwargs):
+    """GPU data plane of a sharded batch: every rank decodes its shard with the pixels LEFT IN HBM (output_device = its
+    GPU), and -- when gather_to is given -- the decoded images travel to that rank's GPU with NCCL point-to-point
+    transfers (device buffers, NVLink / NVSwitch; images differ in size, so one send / recv per image batched with
+    batch_isend_irecv rather than an equal-sized all_gather).  No image ever touches host memory.
+
+    Returns {index: uint8 CUDA tensor [height, stride_bytes]} (this rank's shard; the whole batch on rank gather_to) and the
+    list of (index, width, height, stride, config) of everything held.  Requires an initialised NCCL process group."""
+    import torch
+    import torch.distributed as dist
+    from . import api
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    parts = partition([len(d) for d in datas], world)
+    mine = parts[rank]
+    bitmaps = api.decode_batch([datas[i] for i in mine], device=device, output_device=device, keep_native=True, **decode_kwargs) if mine else []
+    held = {}
+    meta = []
+    for i, b in zip(mine, bitmaps):
+        # own copy in torch's allocator, then hand the library's buffer back (the result buffers are cudaMalloc'ed per image)
+        t = device_tensor(b).clone()
+        b.free()
+        held[i] = t
+        meta.append((i, b.width, b.height, b.stride, b.config))
+    if gather_to is None or world == 1:
+        return held, meta
+    metas = [None] * world
+    dist.all_gather_object(metas, meta, group=group)
+    ops = []
+    if rank == gather_to:
+        for r, m in enumerate(metas):
+            if r == rank:
+                continue
+            for (i, w, h, stride, cfg) in m:
+                t = torch.empty((h, stride), dtype=torch.uint8, device="cuda:%d" % device)
+                held[i] = t
+                ops.append(dist.P2POp(dist.irecv, t, r, group=group))
+        meta = [x for m in metas for x in m]
+    else:
+        for i in mine:
+            ops.append(dist.P2POp(dist.isend, held[i], gather_to, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    torch.cuda.synchronize(device)
+    return held, meta
