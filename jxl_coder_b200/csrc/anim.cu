@@ -42,7 +42,21 @@ struct jxlb_anim {
   };
   std::map<Key, DecodedImage> cache;
   std::deque<Key> cache_order;
+  // Read-ahead: when a prefetched block is handed out, the NEXT block is submitted at once (SubmitBatch: device half on a
+  // worker thread), so that a player walking through the frames finds it decoded -- a block alone is a latency chain
+  // (its LF stage) during which the GPU is almost idle, and two blocks in flight overlap.
+  PendingBatch* ahead = nullptr;
+  int32_t ahead_first = -1, ahead_n = 0, ahead_w = 0, ahead_h = 0;
+  void DropAhead() {
+    if (!ahead) return;
+    std::vector<DecodedImage> res;
+    CollectBatch(ahead, &res, nullptr);
+    for (auto& d : res) FreeImageMemory(d.data, d.device);
+    ahead = nullptr;
+    ahead_first = -1;
+  }
   ~jxlb_anim() {
+    DropAhead();
     for (auto& kv : cache) FreeImageMemory(kv.second.data, kv.second.device);
   }
 };
@@ -184,20 +198,41 @@ static int AnimGetFrame(jxlb_anim* a, int32_t frame, int32_t width, int32_t heig
       DecodeBatch(&r, 1, a->api_level, -1, -1, &res, &tm, &fi);
       d = res[0];
     } else {
+      // requests of the block of frames [first, first + n): mini codestreams (image header + one frame each)
+      auto submit_block = [&](int32_t first, int32_t n) {
+        std::vector<std::vector<uint8_t>> mini(n);
+        std::vector<jxlb_request> reqs(n);
+        for (int32_t k = 0; k < n; ++k) {
+          const auto& fb = a->frame_bytes[first + k];
+          mini[k].reserve(a->header_bytes + (fb.second - fb.first));
+          mini[k].assign(a->cs.begin(), a->cs.begin() + a->header_bytes);
+          mini[k].insert(mini[k].end(), a->cs.begin() + fb.first, a->cs.begin() + fb.second);
+          reqs[k] = jxlb_request{mini[k].data(), mini[k].size(), rw, rh, a->cfg, a->scale_mode, a->filter};
+        }
+        std::vector<int32_t> fidx(n, 0);  // every mini codestream holds one frame: displayed frame 0
+        return SubmitBatch(reqs.data(), (size_t) n, a->api_level, -1, -1, fidx.data());
+      };
       const int32_t n = std::min<int32_t>(a->prefetch, (int32_t) a->frames.size() - frame);
-      std::vector<std::vector<uint8_t>> mini(n);
-      std::vector<jxlb_request> reqs(n);
-      std::vector<int32_t> fidx(n, 0);
-      for (int32_t k = 0; k < n; ++k) {
-        const auto& fb = a->frame_bytes[frame + k];
-        mini[k].reserve(a->header_bytes + (fb.second - fb.first));
-        mini[k].assign(a->cs.begin(), a->cs.begin() + a->header_bytes);
-        mini[k].insert(mini[k].end(), a->cs.begin() + fb.first, a->cs.begin() + fb.second);
-        reqs[k] = jxlb_request{mini[k].data(), mini[k].size(), rw, rh, a->cfg, a->scale_mode, a->filter};
-      }
       std::vector<DecodedImage> res;
       BatchTimings tm;
-      DecodeBatch(reqs.data(), (size_t) n, a->api_level, -1, -1, &res, &tm, fidx.data());
+      if (a->ahead && a->ahead_first == frame && a->ahead_n == n && a->ahead_w == rw && a->ahead_h == rh) {
+        CollectBatch(a->ahead, &res, &tm);  // the read-ahead block is exactly what is asked for
+        a->ahead = nullptr;
+        a->ahead_first = -1;
+      } else {
+        a->DropAhead();
+        CollectBatch(submit_block(frame, n), &res, &tm);
+      }
+      {  // read ahead: the block after this one
+        const int32_t nf = frame + n, nn = std::min<int32_t>(a->prefetch, (int32_t) a->frames.size() - nf);
+        if (nn > 0 && !a->ahead && !a->cache.count(jxlb_anim::Key{nf, rw, rh})) {
+          a->ahead = submit_block(nf, nn);
+          a->ahead_first = nf;
+          a->ahead_n = nn;
+          a->ahead_w = rw;
+          a->ahead_h = rh;
+        }
+      }
       d = res[0];
       for (int32_t k = 1; k < n; ++k) {
         const jxlb_anim::Key kk{frame + k, rw, rh};

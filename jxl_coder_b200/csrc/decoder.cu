@@ -1602,12 +1602,12 @@ struct PendingBatch {
   std::thread worker;
 };
 
-PendingBatch* SubmitBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device) {
+PendingBatch* SubmitBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device, const int32_t* frame_index) {
   using Clock = std::chrono::steady_clock;
   const auto t0 = Clock::now();
   std::unique_ptr<PendingBatch> p(new PendingBatch());
   p->out.assign(n, DecodedImage());
-  p->b.Parse(reqs, n, api_level, nullptr);
+  p->b.Parse(reqs, n, api_level, frame_index);
   const double parse_ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
   PendingBatch* raw = p.get();
   p->worker = std::thread([raw, device, output_device, parse_ms]() { raw->rc = DeviceDecode(raw->b, device, output_device, &raw->out, &raw->tm, parse_ms); });

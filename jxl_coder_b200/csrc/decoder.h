@@ -38,7 +38,8 @@ void FreeImageMemory(void* data, int device);
 // starts the device half on a worker thread and returns a handle; CollectBatch waits for it, hands over the results and
 // frees the handle.  Several submitted batches overlap on the GPU like concurrent DecodeBatch calls do.
 struct PendingBatch;
-PendingBatch* SubmitBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device);
+PendingBatch* SubmitBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device,
+                          const int32_t* frame_index = nullptr);
 int CollectBatch(PendingBatch* p, std::vector<DecodedImage>* out, BatchTimings* timings);
 
 }  // namespace jxlb
