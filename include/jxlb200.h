@@ -19,6 +19,15 @@
  *
  * Pixels are computed on the GPU only.  If no CUDA device is usable every decode entry point fails with
  * JXLB_ERROR_NO_DEVICE; there is no CPU fallback.
+ *
+ * Host dependence of lossy output.  The reference's libjxl is a JXL_HIGH_PRECISION=0 SSE2 build whose edge-preserving
+ * filter and quant-bias adjustment use the x86 RCPPS instruction, an 11-bit table lookup whose values belong to the CPU
+ * vendor.  To return the pictures the reference returns ON THE SAME MACHINE, this library fills its 2048-entry
+ * reciprocal table by executing RCPPS on the host CPU when the library is loaded (csrc/numeric_tables.cc: FillRcp11); the
+ * GPU then looks reciprocals up in that table.  Consequences: (1) lossy output can differ by 1 LSB on isolated samples
+ * between an Intel and an AMD host, exactly as the reference's own output does; (2) on a non-x86 host, or with the
+ * environment variable JXLB_EXACT_RCP=1 (read once, at first use), the table holds correctly rounded reciprocals instead
+ * -- vendor-independent output that stays within 1 LSB of the reference.  Lossless output never depends on the host.
  */
 #ifndef JXLB200_H_
 #define JXLB200_H_

@@ -3,6 +3,7 @@
 #include "numeric_tables.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -15,16 +16,23 @@ namespace {
 // rcp11[i] = rcpps(1 + i / 2048) as the HOST CPU computes it (numeric.h: NumericTables::rcp11).  Checked: on this
 // machine RCPPS depends on the top 11 mantissa bits only and scales exactly with the exponent
 // (tests/test_numeric_host.py::test_rcp_table_reproduces_rcpps).
+// JXLB_EXACT_RCP=1 (or a non-x86 host) fills the table with correctly rounded reciprocals of the bucket's lower edge
+// instead: vendor-independent output, at most 1 LSB from the reference's on a few more samples (include/jxlb200.h).
 void FillRcp11(uint32_t* out) {
+  const char* e = getenv("JXLB_EXACT_RCP");
+  const bool exact = e && *e && *e != '0';
   for (uint32_t i = 0; i < 2048; ++i) {
     union { float f; uint32_t u; } v, r;
     v.u = 0x3F800000u | (i << 12);
-#if defined(__x86_64__) || defined(__i386__)
-    alignas(16) float in4[4] = {v.f, v.f, v.f, v.f}, out4[4];
-    _mm_store_ps(out4, _mm_rcp_ps(_mm_load_ps(in4)));
-    r.f = out4[0];
-#else
     r.f = 1.0f / v.f;
+#if defined(__x86_64__) || defined(__i386__)
+    if (!exact) {
+      alignas(16) float in4[4] = {v.f, v.f, v.f, v.f}, out4[4];
+      _mm_store_ps(out4, _mm_rcp_ps(_mm_load_ps(in4)));
+      r.f = out4[0];
+    }
+#else
+    (void) exact;
 #endif
     out[i] = r.u;
   }

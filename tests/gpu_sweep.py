@@ -17,7 +17,10 @@ def main():
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 120
     rng = np.random.default_rng(seed)
-    counts = {"MATCH": 0, "REFUSED": 0, "MISMATCH": 0, "REF_ERR": 0}
+    # MATCH_PQ_DARK: Rec.2100-PQ output whose only samples beyond the tolerance sit where the reference is in the darkest
+    # quarter of the range and are rarer than 3 in 10^5 (1 in 10^3 after a rescale has spread them): the bound of
+    # tests/golden_lib.pq_close, the PQ curve being ill-conditioned at black.
+    counts = {"MATCH": 0, "MATCH_PQ_DARK": 0, "REFUSED": 0, "MISMATCH": 0, "REF_ERR": 0}
     refused = {}
     only = os.environ.get("SWEEP_ONLY_LOSSLESS")
     for k in range(n):
@@ -104,6 +107,18 @@ def main():
                 info = (dm,)
         else:
             info = ("shape/config", got.width, got.height, got.config, r["width"], r["height"])
+        if not ok and tf == 16 and (got.width, got.height) == (r["width"], r["height"]) and got.config in ("ARGB_8888", "RGBA_1010102"):
+            if got.config == "ARGB_8888":
+                da, rb, tol, dark = np.abs(a.astype(int) - b.astype(int)), b.astype(int), 2 if sampled or alpha else 1, 64
+            else:
+                ua, ub = a.view(np.uint32), b.view(np.uint32)
+                da = np.stack([np.abs(((ua >> sh) & 0x3FF).astype(int) - ((ub >> sh) & 0x3FF).astype(int)) for sh in (0, 10, 20)])
+                rb, tol, dark = np.stack([((ub >> sh) & 0x3FF).astype(int) for sh in (0, 10, 20)]), 8, 256
+            far = da > tol
+            if float(far.mean()) <= (1e-3 if sampled else 3e-5) and int(rb[far].max()) < dark:
+                counts["MATCH_PQ_DARK"] += 1
+                print("MATCH_PQ_DARK", info, "far share %.2e, brightest reference value there %d" % (float(far.mean()), int(rb[far].max())), flush=True)
+                continue
         if ok:
             counts["MATCH"] += 1
         else:
