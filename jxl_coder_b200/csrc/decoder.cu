@@ -956,7 +956,7 @@ struct Batch {
         if (!ps[i].g.has_global_tree) grp_local_tree = true;
       }
     }
-    sl_grp.arena_bytes = grp_modular ? (grp_local_tree ? (192u << 10) : (16u << 10)) : 0;
+    sl_grp.arena_bytes = grp_modular ? (grp_local_tree ? (192u << 10) : (64u << 10)) : 0;  // local tree + code, group-local palette colours
     sl_grp.wp_ints = grp_modular ? ModFastScratch::Ints(grp_dim + 8) : 0;
     sl_grp.max_local_nodes = 2048;
     sl_grp.bytes_per_job = Align256(job_bytes(sl_grp));
@@ -1174,6 +1174,7 @@ struct Batch {
         pk.dst_stride = od.stride_bytes;
       }
       if (f.sq_nch) LaunchUnsqueeze(f, p.g.sq.steps.data(), s);
+      if (f.encoding == 0 && !f.single_section && !f.sq_nch && f.num_mod_channels && f.global_nb_transforms) LaunchModularGlobalInverse(f, s);
       if (f.encoding == 0) {
         const bool timed = (vd++ % kTimeEvery) == 0;
         LaunchLfFinal(f, s);

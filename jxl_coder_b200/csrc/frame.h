@@ -136,8 +136,12 @@ struct FrameDev {
   uint32_t num_mod_channels;       // channels of the frame's modular image (colour for modular frames + extras)
   uint32_t num_color_mod_channels; // 0 for VarDCT, 1 or 3 for modular
   uint32_t global_mod_decoded;     // channels fully decoded in the global stream (filled by host plan)
-  uint32_t global_nb_transforms;   // frame-level modular transforms (multi-section frames; host-parsed)
+  uint32_t global_nb_transforms;   // frame-level modular transforms (multi-section frames; host-parsed, PlanChannels applied)
   ModTransform global_tr[kMaxTransforms];
+  uint32_t num_coded;              // multi-section frames: coded (non-meta) channels once the frame-level palettes are applied
+  uint8_t coded_plane[kMaxModPlanes];  // ... and the plane of `mod` each of them is decoded into
+  const int32_t* meta;             // palette colours of the frame-level transforms (host-decoded meta channels)
+  uint32_t bit_depth;              // bits per sample of the image (implicit palette colours scale with it)
   // ---- planes (device) ----
   int32_t* lf_quant;               // [3][h8][lf_stride]  (Y, X, B as coded)
   uint32_t lf_stride;

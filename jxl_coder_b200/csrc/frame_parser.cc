@@ -567,8 +567,55 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
     }
     if (parse_here) {
       int st = ReadModularHeader(br, &g->global_mh);
-      if (st == kErrUnsupported) JXLB_FAIL(kParseUnsupported, "palette transform");
+      if (st == kErrUnsupported) JXLB_FAIL(kParseUnsupported, "delta palette or too many modular transforms");
       if (st != kOk || br.Overrun()) JXLB_FAIL(kParseInvalid, "global modular header");
+      if (!g->global_mh.has_squeeze && fh.toc_entries > 1) {
+        // frame-level RCTs / palettes: replay them on the channel list; the palettes' colours (meta channels) are the only
+        // channels of a multi-section frame that live in the global stream, and are decoded here
+        st = PlanChannels(&g->global_mh, nmod, &g->chplan);
+        if (st == kErrUnsupported) JXLB_FAIL(kParseUnsupported, "nested palette transforms");
+        if (st != kOk) JXLB_FAIL(kParseInvalid, "modular transform channel range");
+        if (g->chplan.nb_meta) {
+          ModularContext mc{};
+          Arena a2;
+          std::vector<uint8_t> amem(4u << 20);
+          a2.Init(amem.data(), (uint32_t) amem.size());
+          if (g->global_mh.use_global_tree) {
+            if (!g->has_global_tree) JXLB_FAIL(kParseInvalid, "global tree missing");
+            mc.tree = reinterpret_cast<const TreeNode*>(g->tree_blob.data());
+            mc.num_nodes = g->tree_nodes;
+            mc.uses_wp = g->tree_uses_wp;
+            mc.max_property = g->tree_max_property;
+            mc.code.Bind(g->tree_code.data());
+          } else {
+            uint32_t toff, nn, wp, maxp, coff;
+            st = DecodeTree(br, a2, 1u << 16, &toff, &nn, &wp, &maxp);
+            if (st == kOk) st = ParseCode<false>(br, (nn + 1) / 2, true, a2, &coff);
+            if (st != kOk) JXLB_FAIL(st == kErrBadStream ? kParseInvalid : kParseUnsupported, "global modular stream tree");
+            mc.tree = reinterpret_cast<const TreeNode*>(a2.base + toff);
+            mc.num_nodes = nn;
+            mc.uses_wp = wp;
+            mc.max_property = maxp;
+            mc.code.Bind(a2.base + coff);
+          }
+          g->meta_data.assign((size_t) g->chplan.meta_ints + 1, 0);
+          std::vector<ModChannel> chs(g->chplan.nb_meta);
+          uint32_t maxw = 0;
+          for (uint32_t c = 0; c < g->chplan.nb_meta; ++c) {
+            const ModTransform& tr = g->global_mh.tr[g->chplan.meta_tr[c]];
+            chs[c].data = g->meta_data.data() + tr.meta_off;
+            chs[c].w = tr.nb_colours;
+            chs[c].h = tr.num_c;
+            chs[c].stride = tr.nb_colours;
+            maxw = std::max(maxw, tr.nb_colours);
+          }
+          std::vector<int32_t> scratch(ModFastScratch::Ints(maxw + 8));
+          std::vector<uint32_t> lz(1u << 20);
+          st = DecodeModularChannelsFast(br, mc, g->global_mh.wp, chs.data(), g->chplan.nb_meta, 0, scratch.data(), lz.data(), (1u << 20) - 1);
+          if (st == kErrUnsupported || st == kErrScratch) JXLB_FAIL(kParseUnsupported, "global modular stream");
+          if (st != kOk || br.Overrun()) JXLB_FAIL(kParseInvalid, "global modular stream");
+        }
+      }
       if (g->global_mh.has_squeeze) {
         // lossy extra channels of a VarDCT frame (squeeze.h); anything wider is refused
         if (fh.encoding != 0 || g->global_mh.nb_transforms != 1) JXLB_FAIL(kParseUnsupported, "squeeze transform outside a VarDCT frame's extra channels");

@@ -117,6 +117,8 @@ struct FrameGlobals {
   std::vector<uint8_t> tree_code;     // code blob for the tree's leaf contexts
   uint64_t global_modular_bit = 0;    // where the global modular GroupHeader starts
   ModularHeader global_mh{};          // parsed for multi-section frames with a modular image
+  ChannelPlan chplan{};               // ... its channel list (palette meta channels first)
+  std::vector<int32_t> meta_data;     // ... and the palette colours, decoded on the host (they live in the global stream)
   // squeezed extra channels (squeeze.h): channel pyramid, inverse steps, and the samples of the channels that live in
   // the global stream (decoded on the host: they are at most group_dim x group_dim), concatenated in channel order
   bool squeeze = false;

@@ -37,6 +37,7 @@ __device__ StreamScratch CarveScratch(const ScratchLayout& s, uint32_t job, uint
   sc.arena.Init(p, s.arena_bytes);
   p += (s.arena_bytes + 255u) & ~255u;
   sc.wp = reinterpret_cast<int32_t*>(p);
+  sc.wp_ints = s.wp_ints;
   p += ((uint64_t) s.wp_ints * 4 + 255u) & ~(uint64_t) 255u;
   sc.nzmap = p;
   p += 3 * 1024;
@@ -310,8 +311,16 @@ __global__ void __launch_bounds__(256) ModularToRgbaKernel(const FrameDev f, Out
   if (*f.frame_bad) return;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= (int) f.width || y >= (int) f.height) return;
-  if (!f.single_section) StageGlobalInverseRct(f, x, y);
+  if (!f.single_section) StageGlobalInverse(f, x, y);
   StageModularToRgba(f, out, x, y);
+}
+
+// Frame-level transforms on the extra channels of a multi-section VarDCT frame (e.g. a palette on a lossless alpha).
+__global__ void __launch_bounds__(256) ModularGlobalInverseKernel(const FrameDev f) {
+  if (*f.frame_bad) return;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= (int) f.width || y >= (int) f.height) return;
+  StageGlobalInverse(f, x, y);
 }
 
 __global__ void __launch_bounds__(256) PackKernel(const PackParams p) {
@@ -447,6 +456,11 @@ int LaunchFilters(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t s
 void LaunchColor(const FrameDev& f, const ColorParams& cp, const NumericTables* nt_dev, const float* src, OutputDesc out,
                  cudaStream_t stream) {
   ColorKernel<<<PixelGrid(f.width, f.height, 256), 256, 0, stream>>>(f, cp, nt_dev, src, out);
+  ++g_launches;
+}
+
+void LaunchModularGlobalInverse(const FrameDev& f, cudaStream_t stream) {
+  ModularGlobalInverseKernel<<<PixelGrid(f.width, f.height, 256), 256, 0, stream>>>(f);
   ++g_launches;
 }
 

@@ -119,6 +119,7 @@ int LaunchFilters(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t s
 void LaunchColor(const FrameDev& f, const ColorParams& cp, const NumericTables* nt_dev, const float* src, OutputDesc out,
                  cudaStream_t stream);
 void LaunchModularToRgba(const FrameDev& f, OutputDesc out, cudaStream_t stream);
+void LaunchModularGlobalInverse(const FrameDev& f, cudaStream_t stream);
 // Fused Gaborish + EPF + colour + pack (kernels_filter.cu): XYB planes in f.xyb0 -> packed pixels.
 void LaunchFilterColorPack(const FrameDev& f, const ColorParams& cp, const NumericTables* nt_dev, const OutputDesc& od,
                            const PackParams& pack, cudaStream_t stream);

@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(32) GroupModularKernel(const FrameDev* frames,
   sc.arena.Init(p, scratch.arena_bytes);
   p += (scratch.arena_bytes + 255u) & ~255u;
   sc.wp = reinterpret_cast<int32_t*>(p);
+  sc.wp_ints = scratch.wp_ints;
   sc.nzmap = nullptr;
   sc.lz77 = nullptr;
   sc.lz77_mask = 0;

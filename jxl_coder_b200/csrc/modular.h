@@ -30,12 +30,17 @@ struct WPHeader {
   }
 };
 
+static constexpr int kMaxModPlanes = 8;  // channels of a modular image once every transform is undone
 struct ModTransform {
   uint8_t id;          // 0 RCT, 1 palette, 2 squeeze
   uint8_t rct_type;
   uint16_t pad;
   uint32_t begin_c;
   uint32_t num_c, nb_colours, nb_deltas, d_pred;
+  // filled by PlanChannels: the output planes the transform works on (RCT: 3, palette: num_c; pl[0] also holds the
+  // palette's index channel) and where the palette's colours sit in the stream's meta-channel buffer (int32 units)
+  uint8_t pl[kMaxModPlanes];
+  uint32_t meta_off;
 };
 static constexpr int kMaxTransforms = 8;
 
@@ -76,6 +81,8 @@ JXLB_HD_NOINLINE int ReadModularHeader(BitReader& br, ModularHeader* h) {
     t.rct_type = 0;
     t.pad = 0;
     t.begin_c = t.num_c = t.nb_colours = t.nb_deltas = t.d_pred = 0;
+    t.meta_off = 0;
+    for (int k = 0; k < kMaxModPlanes; ++k) t.pl[k] = 0;
     if (t.id == 0) {
       t.begin_c = br.U32(0, 3, 8, 6, 72, 10, 1096, 13);
       t.rct_type = (uint8_t) br.U32(6, 0, 0, 2, 2, 4, 10, 6);
@@ -86,7 +93,9 @@ JXLB_HD_NOINLINE int ReadModularHeader(BitReader& br, ModularHeader* h) {
       t.nb_colours = br.U32(0, 8, 256, 10, 1280, 12, 5376, 16);
       t.nb_deltas = br.U32(0, 0, 1, 8, 257, 10, 1281, 16);
       t.d_pred = br.Read(4);
-      return kErrUnsupported;  // palette: not on the round-1 path
+      // delta palettes (entries predicted from neighbouring output pixels: the encoder's opt-in lossy-palette mode)
+      if (t.nb_deltas != 0 || t.d_pred != 0) return kErrUnsupported;
+      if (t.num_c > (uint32_t) kMaxModPlanes) return kErrUnsupported;
     } else if (t.id == 2) {
       if (h->has_squeeze) return kErrUnsupported;  // one squeeze transform per header
       h->has_squeeze = 1;
@@ -441,6 +450,140 @@ JXLB_HD void RctPermutation(uint32_t type, uint32_t out[3]) {
   out[0] = perm % 3;
   out[1] = (perm + 1 + perm / 3) % 3;
   out[2] = (perm + 2 - perm / 3) % 3;
+}
+
+// ---- channel list of a stream whose header carries transforms ---------------------------------------------------------
+// A palette transform replaces num_c channels by one index channel and puts a "meta" channel (nb_colours x num_c, the
+// colours) at the front of the stream's channel list; begin_c of every later transform counts those meta channels
+// (ISO/IEC 18181-1 modular transforms; libjxl's meta-apply step).  PlanChannels replays the header's transforms on the
+// list of the nfinal output planes and records, per transform, the planes it works on, so that the inverse can run per
+// pixel on planes in place: the index channel of a palette lives in the first of its output planes.
+struct ChannelPlan {
+  uint32_t nb_meta;                      // meta channels, first in the stream
+  uint32_t ncoded;                       // channels that follow them
+  uint8_t coded_plane[kMaxModPlanes];    // output plane holding coded channel i
+  uint8_t meta_tr[kMaxTransforms];       // transform owning meta channel i
+  uint32_t meta_ints;                    // size of the meta-channel buffer
+};
+
+JXLB_HD int PlanChannels(ModularHeader* mh, uint32_t nfinal, ChannelPlan* cp) {
+  if (nfinal > (uint32_t) kMaxModPlanes) return kErrUnsupported;
+  uint8_t list[kMaxModPlanes + kMaxTransforms];  // plane id, or 0x80 | transform for a meta channel
+  uint32_t len = nfinal, nb_meta = 0;
+  for (uint32_t i = 0; i < nfinal; ++i) list[i] = (uint8_t) i;
+  cp->meta_ints = 0;
+  for (uint32_t t = 0; t < mh->nb_transforms; ++t) {
+    ModTransform& tr = mh->tr[t];
+    if (tr.id == 0) {
+      if (tr.begin_c + 3 > len) return kErrBadStream;
+      if (tr.begin_c < nb_meta) return kErrUnsupported;  // RCT across palette colours
+      for (int k = 0; k < 3; ++k) tr.pl[k] = list[tr.begin_c + k];
+    } else if (tr.id == 1) {
+      if (tr.num_c == 0 || tr.begin_c + tr.num_c > len) return kErrBadStream;
+      if (tr.begin_c < nb_meta) return kErrUnsupported;  // palette of a palette
+      if (tr.nb_colours > (1u << 20)) return kErrUnsupported;
+      for (uint32_t k = 0; k < tr.num_c; ++k) tr.pl[k] = list[tr.begin_c + k];
+      for (uint32_t i = tr.begin_c + tr.num_c; i < len; ++i) list[i - (tr.num_c - 1)] = list[i];
+      len -= tr.num_c - 1;
+      for (uint32_t i = len; i > 0; --i) list[i] = list[i - 1];
+      list[0] = (uint8_t) (0x80u | t);
+      ++len;
+      ++nb_meta;
+      tr.meta_off = cp->meta_ints;
+      cp->meta_ints += tr.nb_colours * tr.num_c;
+    } else {
+      return kErrUnsupported;  // squeeze: handled by its own path (squeeze.h), never together with the others here
+    }
+  }
+  cp->nb_meta = nb_meta;
+  cp->ncoded = len - nb_meta;
+  for (uint32_t i = 0; i < nb_meta; ++i) cp->meta_tr[i] = (uint8_t) (list[i] & 0x7Fu);
+  for (uint32_t i = nb_meta; i < len; ++i) cp->coded_plane[i - nb_meta] = list[i];
+  return kOk;
+}
+
+// Colours outside the coded palette (ISO/IEC 18181-1: negative indices address a fixed table of 72 signed deltas,
+// indices past the palette two implicit colour cubes).  Table as shipped in the reference's libjxl 0.12.0.
+JXLB_HD_NOINLINE int32_t ImplicitPaletteValue(int32_t index, uint32_t c, int32_t palette_size, uint32_t bit_depth) {
+  if (c >= 3) return 0;
+  if (index < 0) {
+    const int16_t kDelta[72 * 3] = {
+        0, 0, 0, 4, 4, 4, 11, 0, 0, 0, 0, -13, 0, -12, 0, -10, -10, -10, -18, -18, -18, -27, -27, -27, -18, -18, 0, 0, 0, -32, -32, 0, 0, -37, -37,
+        -37, 0, -32, -32, 24, 24, 45, 50, 50, 50, -45, -24, -24, -24, -45, -45, 0, -24, -24, -34, -34, 0, -24, 0, -24, -45, -45, -24, 64, 64, 64,
+        -32, 0, -32, 0, -32, 0, -32, 0, 32, -24, -45, -24, 45, 24, 45, 24, -24, -45, -45, -24, 24, 80, 80, 80, 64, 0, 0, 0, 0, -64, 0, -64, -64, -24,
+        -24, 45, 96, 96, 96, 64, 64, 0, 45, -24, -24, 34, -34, 0, 112, 112, 112, 24, -45, -45, 45, 45, -24, 0, -32, 32, 24, -24, 45, 0, 96, 96, 45,
+        -24, 24, 24, -45, -24, -24, -45, 24, 0, -64, 0, 96, 0, 0, 128, 128, 128, 64, 0, 64, 144, 144, 144, 96, 96, 0, -36, -36, 36, 45, -24, -45, 45,
+        -45, -24, 0, 0, -96, 0, 128, 128, 0, 96, 0, 45, 24, -45, -128, 0, 0, 24, -45, 24, -45, 24, -45, 64, 0, -64, 64, -64, -64, 96, 0, 96, 45, -45,
+        24, 24, 45, -45, 64, 64, -64, 128, 128, 0, 0, 0, -128, -24, 45, -45};
+    int32_t i = -(index + 1);
+    i %= 143;  // 1 + 2 * (72 - 1)
+    const int32_t e = (i + 1) >> 1;
+    int32_t v = kDelta[e * 3 + c];
+    v *= (i & 1) ? 1 : -1;
+    if (bit_depth > 8) v *= 1 << (bit_depth - 8);
+    return v;
+  }
+  index -= palette_size;
+  if (index < 64) {  // small cube: 4 x 4 x 4
+    index >>= 2 * c;
+    return (int32_t) (((int64_t) (index % 4) * ((1ll << bit_depth) - 1)) / 4 + (1ll << (bit_depth > 3 ? bit_depth - 3 : 0)));
+  }
+  index -= 64;       // large cube: 5 x 5 x 5
+  if (c == 1) index /= 5;
+  else if (c == 2) index /= 25;
+  return (int32_t) (((int64_t) (index % 5) * ((1ll << bit_depth) - 1)) / 4);
+}
+
+JXLB_HD int32_t PaletteValue(const int32_t* pal, int32_t index, uint32_t c, uint32_t nb_colours, uint32_t bit_depth) {
+  if (index >= 0 && (uint32_t) index < nb_colours) return pal[(size_t) c * nb_colours + (uint32_t) index];
+  return ImplicitPaletteValue(index, c, (int32_t) nb_colours, bit_depth);
+}
+
+// One pixel of the inverse palette: the index sits in the first output plane.
+JXLB_HD void InversePalettePixel(const ModTransform& tr, const int32_t* meta, uint32_t bit_depth, int32_t index, int32_t* out) {
+  const int32_t* pal = meta + tr.meta_off;
+  if (tr.num_c == 1) {  // single-channel palettes clamp the index instead of using implicit colours
+    const int32_t hi = (int32_t) tr.nb_colours - 1;
+    if (index > hi) index = hi;
+    if (index < 0) index = hi < 0 ? -1 : 0;
+  }
+  for (uint32_t c = 0; c < tr.num_c; ++c) out[c] = PaletteValue(pal, index, c, tr.nb_colours, bit_depth);
+}
+
+// Serial inverse of every transform of a stream header over whole planes (`planes`: the stream's output planes, all of one
+// size).  The per-pixel form for frame-level transforms of large images is StageGlobalInverse (pixel_stages.h).
+JXLB_HD void ApplyInverseTransforms(const ModularHeader& mh, const ModChannel* planes, const int32_t* meta, uint32_t bit_depth) {
+  for (int t = (int) mh.nb_transforms - 1; t >= 0; --t) {
+    const ModTransform& tr = mh.tr[t];
+    if (tr.id == 0) {
+      const ModChannel& a = planes[tr.pl[0]];
+      const ModChannel& b = planes[tr.pl[1]];
+      const ModChannel& c = planes[tr.pl[2]];
+      uint32_t perm[3];
+      RctPermutation(tr.rct_type, perm);
+      const ModChannel* dst[3] = {&planes[tr.pl[perm[0]]], &planes[tr.pl[perm[1]]], &planes[tr.pl[perm[2]]]};
+      for (uint32_t y = 0; y < a.h; ++y) {
+        for (uint32_t x = 0; x < a.w; ++x) {
+          int32_t v0 = a.data[(size_t) y * a.stride + x];
+          int32_t v1 = b.data[(size_t) y * b.stride + x];
+          int32_t v2 = c.data[(size_t) y * c.stride + x];
+          InverseRctPixel(tr.rct_type, v0, v1, v2);
+          dst[0]->data[(size_t) y * dst[0]->stride + x] = v0;
+          dst[1]->data[(size_t) y * dst[1]->stride + x] = v1;
+          dst[2]->data[(size_t) y * dst[2]->stride + x] = v2;
+        }
+      }
+    } else if (tr.id == 1) {
+      const ModChannel& ic = planes[tr.pl[0]];
+      for (uint32_t y = 0; y < ic.h; ++y) {
+        for (uint32_t x = 0; x < ic.w; ++x) {
+          int32_t v[kMaxModPlanes];
+          InversePalettePixel(tr, meta, bit_depth, ic.data[(size_t) y * ic.stride + x], v);
+          for (uint32_t c = 0; c < tr.num_c; ++c) planes[tr.pl[c]].data[(size_t) y * planes[tr.pl[c]].stride + x] = v[c];
+        }
+      }
+    }
+  }
 }
 
 }  // namespace jxlb

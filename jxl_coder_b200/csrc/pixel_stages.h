@@ -121,20 +121,25 @@ JXLB_HD void StageModularToRgba(const FrameDev& f, const OutputDesc& out, int x,
   StoreRgba(out, x, y, v[0], v[1], v[2], AlphaAt(f, out, x, y));
 }
 
-// Frame-level inverse RCTs of a multi-section modular frame, one pixel (the per-group ones are undone in the group
-// decoder).  Applied in reverse transform order.
-JXLB_HD void StageGlobalInverseRct(const FrameDev& f, int x, int y) {
+// Frame-level inverse transforms (RCT, palette) of a multi-section frame's modular image, one pixel (the per-group ones
+// are undone in the group decoder).  Applied in reverse transform order on the planes PlanChannels assigned (modular.h).
+JXLB_HD void StageGlobalInverse(const FrameDev& f, int x, int y) {
   const size_t plane = (size_t) f.height * f.mod_stride, o = (size_t) y * f.mod_stride + x;
   for (int t = (int) f.global_nb_transforms - 1; t >= 0; --t) {
     const ModTransform& tr = f.global_tr[t];
-    if (tr.id != 0 || tr.begin_c + 3 > f.num_mod_channels) continue;
-    int32_t a = f.mod[(tr.begin_c) * plane + o], b = f.mod[(tr.begin_c + 1) * plane + o], c = f.mod[(tr.begin_c + 2) * plane + o];
-    InverseRctPixel(tr.rct_type, a, b, c);
-    uint32_t perm[3];
-    RctPermutation(tr.rct_type, perm);
-    f.mod[(tr.begin_c + perm[0]) * plane + o] = a;
-    f.mod[(tr.begin_c + perm[1]) * plane + o] = b;
-    f.mod[(tr.begin_c + perm[2]) * plane + o] = c;
+    if (tr.id == 0) {
+      int32_t a = f.mod[tr.pl[0] * plane + o], b = f.mod[tr.pl[1] * plane + o], c = f.mod[tr.pl[2] * plane + o];
+      InverseRctPixel(tr.rct_type, a, b, c);
+      uint32_t perm[3];
+      RctPermutation(tr.rct_type, perm);
+      f.mod[tr.pl[perm[0]] * plane + o] = a;
+      f.mod[tr.pl[perm[1]] * plane + o] = b;
+      f.mod[tr.pl[perm[2]] * plane + o] = c;
+    } else if (tr.id == 1) {
+      int32_t v[kMaxModPlanes];
+      InversePalettePixel(tr, f.meta, f.bit_depth, f.mod[tr.pl[0] * plane + o], v);
+      for (uint32_t c = 0; c < tr.num_c; ++c) f.mod[tr.pl[c] * plane + o] = v[c];
+    }
   }
 }
 

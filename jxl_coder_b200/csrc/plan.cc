@@ -65,6 +65,13 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
   f.global_mod_decoded = 0;
   f.global_nb_transforms = g.global_mh.nb_transforms;
   for (int i = 0; i < kMaxTransforms; ++i) f.global_tr[i] = g.global_mh.tr[i];
+  f.bit_depth = md.bits_per_sample;
+  f.num_coded = f.num_mod_channels;
+  for (uint32_t i = 0; i < (uint32_t) kMaxModPlanes; ++i) f.coded_plane[i] = (uint8_t) i;
+  if (g.global_mh.nb_transforms && !g.squeeze && fh.toc_entries > 1) {
+    f.num_coded = g.chplan.ncoded;
+    for (uint32_t i = 0; i < g.chplan.ncoded; ++i) f.coded_plane[i] = g.chplan.coded_plane[i];
+  }
   // a channel is decoded in the global stream iff it fits one group in both dimensions (and all earlier ones do)
   if (f.width <= f.group_dim && f.height <= f.group_dim) f.global_mod_decoded = f.num_mod_channels;
 
@@ -93,6 +100,7 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
     p.off_sq_steps = take(g.sq.steps.size() * sizeof(SqStep));
     p.off_sq_global = take(g.sq_global_data.size() * sizeof(int32_t));
   }
+  if (!g.meta_data.empty()) p.off_meta = take(g.meta_data.size() * sizeof(int32_t));
   p.const_bytes = o;
 
   // ---- work region
@@ -156,6 +164,7 @@ void FillConstRegion(const FramePlan& plan, const uint8_t* cs_padded, const Fram
     memcpy(dst + plan.off_sq_steps, g.sq.steps.data(), g.sq.steps.size() * sizeof(SqStep));
     memcpy(dst + plan.off_sq_global, g.sq_global_data.data(), g.sq_global_data.size() * sizeof(int32_t));
   }
+  if (!g.meta_data.empty()) memcpy(dst + plan.off_meta, g.meta_data.data(), g.meta_data.size() * sizeof(int32_t));
   uint32_t* bo = reinterpret_cast<uint32_t*>(dst + plan.off_blockinfo_off);
   size_t acc = 0;
   for (uint32_t l = 0; l < fh.num_lf_groups; ++l) {
@@ -207,6 +216,7 @@ FrameDev BindFrameDev(const FramePlan& p, const uint8_t* cb, uint8_t* wb) {
     f.sq_global_data = reinterpret_cast<const int32_t*>(cb + p.off_sq_global);
     f.sq_buf = reinterpret_cast<int32_t*>(wb + p.off_sq_buf);
   }
+  f.meta = p.off_meta ? reinterpret_cast<const int32_t*>(cb + p.off_meta) : nullptr;
   return f;
 }
 

@@ -90,6 +90,7 @@ JXLB_HD_NOINLINE int ParseHfGlobal(BitReader& br, uint32_t num_groups, uint32_t 
 struct StreamScratch {
   Arena arena;             // local trees / codes
   int32_t* wp;             // ModFastScratch::Ints(max channel width) ints
+  uint32_t wp_ints = 0;    // capacity of wp (0: not recorded; sized by the caller for the widest group channel)
   uint32_t* lz77;          // optional LZ77 window (power-of-two entries) or nullptr
   uint32_t lz77_mask;
   uint8_t* nzmap;          // 3 * 32 * 32 bytes for the AC non-zero context map
@@ -100,10 +101,13 @@ struct StreamScratch {
 
 // Reads a modular sub-stream's GroupHeader and resolves its tree + code (global or local, built in scratch).
 JXLB_HD_NOINLINE int BeginModularStream(BitReader& br, const FrameDev& f, StreamScratch& s, uint32_t max_local_nodes,
-                                        ModularHeader* mh, ModularContext* mc) {
+                                        ModularHeader* mh, ModularContext* mc, bool allow_palette = false) {
   int st = ReadModularHeader(br, mh);
   if (st != kOk) return st;
   if (mh->has_squeeze) return kErrUnsupported;  // squeeze is only handled in a frame's global header (host)
+  if (!allow_palette)
+    for (uint32_t t = 0; t < mh->nb_transforms; ++t)
+      if (mh->tr[t].id == 1) return kErrUnsupported;  // streams decoded straight into fixed planes (LF, HF metadata)
   if (mh->use_global_tree) {
     if (!f.global_tree || !f.global_code) return kErrBadStream;
     mc->tree = f.global_tree;
@@ -161,6 +165,50 @@ JXLB_HD void ApplyInverseRcts(const ModularHeader& mh, ModChannel* ch, uint32_t 
       }
     }
   }
+}
+
+// Decodes a stream whose result is `nplanes` equally sized planes, honouring the transforms of its header: palette
+// colours (meta channels, first in the stream) go to scratch, the remaining coded channels straight into the planes the
+// inverse transforms then expand in place (PlanChannels, modular.h).
+JXLB_HD_NOINLINE int DecodeTransformedStream(BitReader& br, StreamScratch& s, ModularHeader& mh, const ModularContext& mc,
+                                             const ModChannel* planes, uint32_t nplanes, uint32_t stream_id, uint32_t bit_depth) {
+  ChannelPlan cp;
+  int st = PlanChannels(&mh, nplanes, &cp);
+  if (st != kOk) return st;
+  int32_t* meta = nullptr;
+  if (cp.meta_ints) {
+    const uint32_t mo = s.arena.Alloc(cp.meta_ints * 4u, 16);
+    if (mo == 0xFFFFFFFFu) return kErrScratch;
+    meta = reinterpret_cast<int32_t*>(s.arena.base + mo);
+  }
+  ModChannel list[kMaxModPlanes + kMaxTransforms];
+  uint32_t n = 0, maxw = 0;
+  for (uint32_t i = 0; i < cp.nb_meta; ++i) {
+    const ModTransform& tr = mh.tr[cp.meta_tr[i]];
+    list[n].data = meta + tr.meta_off;
+    list[n].w = tr.nb_colours;
+    list[n].h = tr.num_c;
+    list[n].stride = tr.nb_colours;
+    if (tr.nb_colours > maxw) maxw = tr.nb_colours;
+    ++n;
+  }
+  for (uint32_t i = 0; i < cp.ncoded; ++i) {
+    list[n] = planes[cp.coded_plane[i]];
+    if (list[n].w > maxw) maxw = list[n].w;
+    ++n;
+  }
+  // the caller's predictor scratch is sized for the planes; a palette wider than that borrows from the arena
+  int32_t* wp = s.wp;
+  if (cp.nb_meta && (s.wp_ints == 0 || ModFastScratch::Ints(maxw) > s.wp_ints)) {
+    const uint32_t wo = s.arena.Alloc(ModFastScratch::Ints(maxw) * 4u, 16);
+    if (wo == 0xFFFFFFFFu) return kErrScratch;
+    wp = reinterpret_cast<int32_t*>(s.arena.base + wo);
+  }
+  st = DecodeModularChannelsFast(br, mc, mh.wp, list, n, stream_id, wp, s.lz77, s.lz77_mask,
+                                 s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
+  if (st != kOk) return st;
+  ApplyInverseTransforms(mh, planes, meta, bit_depth);
+  return kOk;
 }
 
 JXLB_HD void LfGroupRect(const FrameDev& f, uint32_t lfg, uint32_t* cx0, uint32_t* cy0, uint32_t* w8, uint32_t* h8,
@@ -442,14 +490,14 @@ JXLB_HD_NOINLINE int DecodeModularGroup(BitReader& br, const FrameDev& f, uint32
     if (cst != kOk) return cst;
     if (!nch) return kOk;
   } else {
-    const uint32_t first = f.global_mod_decoded;
-    if (first >= f.num_mod_channels) return kOk;
-    nch = f.num_mod_channels - first;
+    // the coded channels left once the frame-level palettes are applied (all of them, without palettes)
+    if (f.global_mod_decoded >= f.num_mod_channels) return kOk;
+    nch = f.num_coded;
     if (nch > 8) return kErrUnsupported;
     const uint32_t w = f.width - x0 < gd ? f.width - x0 : gd;
     const uint32_t h = f.height - y0 < gd ? f.height - y0 : gd;
     for (uint32_t i = 0; i < nch; ++i) {
-      ch[i].data = f.mod + (size_t) (first + i) * f.height * f.mod_stride + (size_t) y0 * f.mod_stride + x0;
+      ch[i].data = f.mod + (size_t) f.coded_plane[i] * f.height * f.mod_stride + (size_t) y0 * f.mod_stride + x0;
       ch[i].w = w;
       ch[i].h = h;
       ch[i].stride = f.mod_stride;
@@ -458,14 +506,17 @@ JXLB_HD_NOINLINE int DecodeModularGroup(BitReader& br, const FrameDev& f, uint32
   ModularHeader mh;
   ModularContext mc;
   uint32_t arena_mark = s.arena.used;
-  int st = BeginModularStream(br, f, s, max_local_nodes, &mh, &mc);
+  int st = BeginModularStream(br, f, s, max_local_nodes, &mh, &mc, /*allow_palette=*/!f.sq_nch);
   if (st != kOk) return st;
   const uint32_t stream_id = 1 + 3 * f.num_lf_groups + 17 + g;
-  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, nch, stream_id, s.wp, s.lz77, s.lz77_mask,
-                                 s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
+  if (f.sq_nch) {
+    if (mh.nb_transforms) return kErrUnsupported;
+    st = DecodeModularChannelsFast(br, mc, mh.wp, ch, nch, stream_id, s.wp, s.lz77, s.lz77_mask,
+                                   s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
+  } else {
+    st = DecodeTransformedStream(br, s, mh, mc, ch, nch, stream_id, f.bit_depth);  // group-local RCTs / palettes undone here
+  }
   if (st != kOk) return st;
-  if (!f.sq_nch) ApplyInverseRcts(mh, ch, nch);
-  else if (mh.nb_transforms) return kErrUnsupported;
   s.arena.used = arena_mark;
   if (br.Overrun()) return kErrTruncated;
   return kOk;
@@ -511,12 +562,10 @@ JXLB_HD_NOINLINE int DecodeGlobalModular(BitReader& br, const FrameDev& f, Strea
   ModularHeader mh;
   ModularContext mc;
   uint32_t arena_mark = s.arena.used;
-  int st = BeginModularStream(br, f, s, max_local_nodes, &mh, &mc);
+  int st = BeginModularStream(br, f, s, max_local_nodes, &mh, &mc, /*allow_palette=*/true);
   if (st != kOk) return st;
-  st = DecodeModularChannelsFast(br, mc, mh.wp, ch, nch, 0, s.wp, s.lz77, s.lz77_mask,
-                                 s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
+  st = DecodeTransformedStream(br, s, mh, mc, ch, nch, 0, f.bit_depth);
   if (st != kOk) return st;
-  if (nch == f.num_mod_channels) ApplyInverseRcts(mh, ch, nch);
   s.arena.used = arena_mark;
   return kOk;
 }

@@ -97,6 +97,7 @@ void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, si
   StreamScratch s;
   s.arena.Init(arena_mem.data(), (uint32_t) arena_mem.size());
   s.wp = wp.data();
+  s.wp_ints = (uint32_t) wp.size();
   s.lz77 = lz.data();
   s.lz77_mask = (1u << 20) - 1;
   s.nzmap = nz.data();
@@ -126,6 +127,10 @@ void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, si
       if (e->status) e->failed_stream = (int) (f.num_lf_groups + gi);
     }
     if (!e->status && f.sq_nch) UnsqueezeAllSerial(f);
+    // frame-level transforms on the extra channels of a VarDCT frame (the device runs ModularGlobalInverseKernel)
+    if (!e->status && f.encoding == 0 && !f.sq_nch && f.num_mod_channels && f.global_nb_transforms)
+      for (uint32_t y = 0; y < f.height; ++y)
+        for (uint32_t x = 0; x < f.width; ++x) StageGlobalInverse(f, (int) x, (int) y);
   }
   return e;
 }
@@ -215,7 +220,7 @@ int emu_render(void* h, uint8_t* out, uint32_t stride_bytes, int bits16, float* 
     if (e->md.xyb_encoded) return 3;
     for (uint32_t y = 0; y < f.height; ++y)
       for (uint32_t x = 0; x < f.width; ++x) {
-        if (!f.single_section) StageGlobalInverseRct(f, (int) x, (int) y);
+        if (!f.single_section) StageGlobalInverse(f, (int) x, (int) y);
         StageModularToRgba(f, od, (int) x, (int) y);
       }
   }
@@ -227,6 +232,27 @@ uint32_t emu_plane_h(void* h) { return static_cast<Emu*>(h)->f.plane_h; }
 // Unit hooks for table checks.
 uint32_t emu_freq_ctx(uint32_t k) { return ZeroDensityFreqCtx(k); }
 uint32_t emu_nnz_ctx(uint32_t k) { return ZeroDensityNnzCtx(k); }
+// PlanChannels (modular.h) on a hand-made header.  tr: per transform (id, begin_c, num_c, nb_colours).
+// out: [0] nb_meta, [1] ncoded, [2..9] coded_plane, [10..17] meta_tr, [18] meta_ints
+int emu_plan_channels(uint32_t nfinal, uint32_t ntr, const uint32_t* tr, uint32_t* out) {
+  ModularHeader mh{};
+  mh.nb_transforms = (uint8_t) ntr;
+  for (uint32_t t = 0; t < ntr; ++t) {
+    mh.tr[t].id = (uint8_t) tr[4 * t];
+    mh.tr[t].begin_c = tr[4 * t + 1];
+    mh.tr[t].num_c = tr[4 * t + 2];
+    mh.tr[t].nb_colours = tr[4 * t + 3];
+  }
+  ChannelPlan cp{};
+  const int st = PlanChannels(&mh, nfinal, &cp);
+  if (st != kOk) return st;
+  out[0] = cp.nb_meta;
+  out[1] = cp.ncoded;
+  for (int i = 0; i < 8; ++i) out[2 + i] = cp.coded_plane[i];
+  for (int i = 0; i < 8; ++i) out[10 + i] = cp.meta_tr[i];
+  out[18] = cp.meta_ints;
+  return 0;
+}
 // Lehmer digits -> permutation (entropy.h ExpandLehmer); digits is overwritten.
 int emu_expand_lehmer(uint32_t size, uint32_t end, uint32_t* perm, uint32_t* digits) { return ExpandLehmer(size, end, perm, digits); }
 void emu_logcount(uint32_t idx7, uint32_t* nb, uint32_t* sym) { LogCountLookup(idx7, nb, sym); }
