@@ -663,6 +663,7 @@ struct Batch {
   std::vector<FrameDev> frames;
   std::vector<StreamJob> jobs_single, jobs_lf, jobs_groups;   // jobs_groups: groups decoded by the one-warp-per-section kernel
   std::vector<StreamJob> jobs_lane_groups, jobs_lane_mod;     // groups taken by the lane-parallel AC kernel (+ their modular tails)
+  uint32_t lz_slots = 0, lz_entries = 0;                      // LZ77 windows handed to modular streams (StreamJob::lz_slot)
   std::vector<AcCtaJob> jobs_ac_cta;
   uint32_t ac_smem_code_bytes = 0;
   bool ac_fast = true;        // every lane-decoded image has an alias-table (ANS) AC code
@@ -906,8 +907,20 @@ struct Batch {
       p.status_base = status_total;
       status_total += p.plan.num_streams;
       const FrameDev& f = p.plan.proto;
+      // modular streams coded with the frame's global code when that code uses LZ77 (libjxl's effort-1 lossless encoder):
+      // every such stream gets a window as large as the symbols it can hold
+      bool lz = false;
+      if (f.num_mod_channels && p.g.has_global_tree && p.g.tree_code.size() >= sizeof(CodeHeader) &&
+          reinterpret_cast<const CodeHeader*>(p.g.tree_code.data())->lz77) {
+        lz = true;
+        const uint64_t side = std::min<uint64_t>(f.group_dim, std::max(f.width, f.height));
+        const uint64_t symbols = std::min<uint64_t>(side * side, (uint64_t) f.width * f.height) * f.num_mod_channels + 65536;
+        uint32_t e = 1u << 12;
+        while (e < symbols && e < (1u << kLz77WindowLog)) e <<= 1;
+        lz_entries = std::max(lz_entries, e);
+      }
       if (f.single_section) {
-        jobs_single.push_back(StreamJob{frame_of[i], 0, f.num_lf_groups + f.num_groups, 0});
+        jobs_single.push_back(StreamJob{frame_of[i], 0, f.num_lf_groups + f.num_groups, lz ? ++lz_slots : 0});
       } else {
         if (f.encoding == 0)
           for (uint32_t l = 0; l < f.num_lf_groups; ++l) jobs_lf.push_back(StreamJob{frame_of[i], l, l, 0});
@@ -926,9 +939,9 @@ struct Batch {
           for (uint32_t g0 = 0; g0 < f.num_groups; g0 += AcGroupsPerCta())
             jobs_ac_cta.push_back(AcCtaJob{frame_of[i], g0, std::min(AcGroupsPerCta(), f.num_groups - g0), 0});
           if (f.num_mod_channels > f.global_mod_decoded)
-            for (uint32_t g = 0; g < f.num_groups; ++g) jobs_lane_mod.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, 0});
+            for (uint32_t g = 0; g < f.num_groups; ++g) jobs_lane_mod.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, lz ? ++lz_slots : 0});
         } else {
-          for (uint32_t g = 0; g < f.num_groups; ++g) jobs_groups.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, 0});
+          for (uint32_t g = 0; g < f.num_groups; ++g) jobs_groups.push_back(StreamJob{frame_of[i], g, f.num_lf_groups + g, lz ? ++lz_slots : 0});
         }
       }
     }
@@ -998,7 +1011,8 @@ struct Batch {
     const size_t single_scratch = Align256(sl_single.bytes_per_job * jobs_single.size());
     buf->const_buf.Ensure(const_total);
     buf->work_buf.Ensure(work_total);
-    buf->scratch_buf.Ensure(lf_scratch + grp_scratch + single_scratch);
+    const size_t lz_scratch = Align256((size_t) lz_slots * lz_entries * 4);
+    buf->scratch_buf.Ensure(lf_scratch + grp_scratch + single_scratch + lz_scratch);
     buf->meta_buf.Ensure(meta_total);
     buf->stage_out.Ensure(stage_total);
     buf->final_out.Ensure(final_total);
@@ -1008,6 +1022,10 @@ struct Batch {
     sl_lf.base = buf->scratch_buf.p;
     sl_grp.base = buf->scratch_buf.p + lf_scratch;
     sl_single.base = buf->scratch_buf.p + lf_scratch + grp_scratch;
+    for (ScratchLayout* l : {&sl_lf, &sl_grp, &sl_single}) {
+      l->lz_base = lz_slots ? buf->scratch_buf.p + lf_scratch + grp_scratch + single_scratch : nullptr;
+      l->lz_entries = lz_entries;
+    }
     CUDA_OK(cudaEventRecord(ev_ring[0][0], s));
     uint8_t* stg = buf->staging.p;
     frames.assign(nframes, FrameDev());

@@ -49,6 +49,13 @@ __device__ StreamScratch CarveScratch(const ScratchLayout& s, uint32_t job, uint
   return sc;
 }
 
+__device__ void BindLz77Window(const ScratchLayout& s, const StreamJob& job, StreamScratch* sc) {
+  if (job.lz_slot && s.lz_base) {
+    sc->lz77 = reinterpret_cast<uint32_t*>(s.lz_base + (uint64_t) (job.lz_slot - 1) * s.lz_entries * 4u);
+    sc->lz77_mask = s.lz_entries - 1;
+  }
+}
+
 __global__ void __launch_bounds__(kStreamBlockThreads) SingleSectionKernel(const FrameDev* frames, const StreamJob* jobs,
                                                                            uint32_t njobs, NaturalOrders nat, ScratchLayout scratch) {
   const uint32_t j = blockIdx.x;
@@ -58,6 +65,7 @@ __global__ void __launch_bounds__(kStreamBlockThreads) SingleSectionKernel(const
   uint8_t* hf_mem;
   uint32_t* perm;
   StreamScratch sc = CarveScratch(scratch, j, &hf_mem, &perm);
+  BindLz77Window(scratch, job, &sc);
   Arena hf;
   hf.Init(hf_mem, scratch.hf_arena_bytes);
   f.status[job.status_slot] = DecodeSingleSectionFrame(f, nat, sc, hf, perm, scratch.max_local_nodes);
@@ -192,6 +200,7 @@ __global__ void __launch_bounds__(kStreamBlockThreads) PassGroupKernel(const Fra
   const StreamJob job = jobs[j];
   const FrameDev& f = frames[job.frame];
   StreamScratch sc = CarveScratch(scratch, j, nullptr, nullptr);
+  BindLz77Window(scratch, job, &sc);
   BitReader br;
   const uint32_t sec = 1 + f.num_lf_groups + 1 + job.index;
   br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);

@@ -14,7 +14,7 @@ struct StreamJob {
   uint32_t frame;
   uint32_t index;        // LF group / group index
   uint32_t status_slot;  // entry of FrameDev::status to write
-  uint32_t pad;
+  uint32_t lz_slot;      // 1-based LZ77 window of ScratchLayout::lz_base for this stream's modular data, 0 = none
 };
 
 // Per-launch scratch: job j owns [j * bytes_per_job, (j + 1) * bytes_per_job) of `base`, carved into
@@ -26,6 +26,10 @@ struct ScratchLayout {
   uint32_t wp_ints;
   uint32_t hf_arena_bytes;   // single-section frames only
   uint32_t max_local_nodes;
+  // LZ77 windows for the modular streams of frames whose global code uses LZ77 (libjxl's effort-1 lossless encoder):
+  // lz_entries (a power of two >= the symbols of one stream, at most 2^20 as in libjxl) uint32 each
+  uint8_t* lz_base;
+  uint32_t lz_entries;
 };
 
 void LaunchSingleSectionFrames(const FrameDev* frames, const StreamJob* jobs, uint32_t njobs, NaturalOrders nat,

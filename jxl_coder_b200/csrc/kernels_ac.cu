@@ -337,6 +337,10 @@ __global__ void __launch_bounds__(32) GroupModularKernel(const FrameDev* frames,
   sc.nzmap = nullptr;
   sc.lz77 = nullptr;
   sc.lz77_mask = 0;
+  if (job.lz_slot && scratch.lz_base) {
+    sc.lz77 = reinterpret_cast<uint32_t*>(scratch.lz_base + (uint64_t) (job.lz_slot - 1) * scratch.lz_entries * 4u);
+    sc.lz77_mask = scratch.lz_entries - 1;
+  }
   const uint32_t sec = 1 + f.num_lf_groups + 1 + job.index;
   BitReader br;
   br.Init(f.cs, f.cs_bytes, f.group_ac_end_bit[job.index], f.sec_bit_end[sec]);

@@ -71,6 +71,8 @@ def main():
         except J.UnsupportedJXLException as e:
             counts["REFUSED"] += 1
             refused[str(e)] = refused.get(str(e), 0) + 1
+            if os.environ.get("SWEEP_SHOW_REFUSED") and os.environ["SWEEP_SHOW_REFUSED"] in str(e):
+                print("REFUSED", str(e), desc, flush=True)
             continue
         except Exception as e:
             counts["MISMATCH"] += 1

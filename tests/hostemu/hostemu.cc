@@ -4,6 +4,7 @@
 // the resulting planes with the Python oracle, so the bit-level logic of the CUDA kernels is verified on a box without
 // a GPU; the GPU tests then only need to show that the kernels produce the same planes as this run.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -100,6 +101,10 @@ void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, si
   s.wp_ints = (uint32_t) wp.size();
   s.lz77 = lz.data();
   s.lz77_mask = (1u << 20) - 1;
+  if (getenv("EMU_NO_LZ77")) {  // what the device lanes have: no LZ77 window
+    s.lz77 = nullptr;
+    s.lz77_mask = 0;
+  }
   s.nzmap = nz.data();
   const NaturalOrders& nat = NaturalOrderPoolHost();
   const uint32_t kMaxNodes = 1u << 16;

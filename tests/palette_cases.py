@@ -1,6 +1,7 @@
 """Inputs that make the reference's encoder emit palette transforms (csrc/modular.h: PlanChannels / InversePalettePixel):
 frame-level colour palettes, per-channel palettes (16-bit data with few distinct values, two-level alpha), palettes inside
-single-section frames and inside the groups of large frames, and a lossless alpha beside lossy colour."""
+single-section frames and inside the groups of large frames, and a lossless alpha beside lossy colour -- plus effort-1
+lossless files, whose modular streams use LZ77."""
 import numpy as np
 
 import cases
@@ -35,6 +36,10 @@ CASES = {
     "pal_local_rgba_102x307": (lambda: (synth.synth_image(102, 307, 1, alpha=True), 102, 307, 4, 8), dict(lossless=True, options={"EFFORT": 6})),
     "pal_alpha2_rgba_822x769": (lambda: (two_level_alpha(822, 769, 6), 822, 769, 4, 8), dict(lossless=True, options={"EFFORT": 5})),
     "pal_lossy_colour_lossless_alpha2_560x561": (lambda: (two_level_alpha(560, 561, 7), 560, 561, 4, 8), dict(distance=1.0, alpha_distance=0.0, options={"EFFORT": 7})),
+    # libjxl's effort-1 ("fast lossless") encoder: LZ77 run-length copies inside prefix-coded modular streams
+    "e1_rgb_1145x612": (lambda: (synth.synth_image(1145, 612, 91), 1145, 612, 3, 8), dict(lossless=True, options={"EFFORT": 1})),
+    "e1_rgba_208x244": (lambda: (synth.synth_image(208, 244, 21, alpha=True), 208, 244, 4, 8), dict(lossless=True, options={"EFFORT": 1})),
+    "e1_rgb16_485x332": (lambda: (synth.synth_image(485, 332, 13).astype(np.uint16) * 257, 485, 332, 3, 16), dict(lossless=True, options={"EFFORT": 1})),
     "pal_lossy_colour_lossless_alpha_82x569": (lambda: (synth.synth_image(82, 569, 72, alpha=True), 82, 569, 4, 8), dict(distance=2.0, alpha_distance=0.0, options={"EFFORT": 4})),
 }
 
