@@ -143,8 +143,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    # the library's pinned-buffer pool and host thread count are per process: share the host among the ranks
-    os.environ.setdefault("JXLB_PINNED_POOL_MB", str(max(8192, 40960 // world)))
+    # the library's pinned-buffer pool and host thread count are per process: share the host among the ranks.  The pool
+    # must hold every result buffer in flight (depth batches of 4 GiB) plus the batch the caller is still reading and one
+    # being recycled: a smaller cap turns every step into a 4 GiB cudaHostAlloc / cudaFreeHost pair (~1 s of page pinning)
+    depth = e2e_depth(args, world)
+    os.environ.setdefault("JXLB_PINNED_POOL_MB", str((depth + 2) * 4096 + 2048))
     os.environ.setdefault("JXLB_HOST_THREADS", str(max(2, (os.cpu_count() or 8) // world)))
     import jxl_coder_b200 as J
     J.load_library()
@@ -226,7 +229,6 @@ def run_ours(args):
     # latency chain -- its LF stage alone is ~86 ms of serial entropy chains -- so a single call at a time leaves the GPU
     # and the PCIe link idle most of the time; the reference's own callers overlap calls from worker pools).
     # every batch in flight keeps 4 GiB of pinned result buffers: on 4 / 8 GPUs (ranks share the host's RAM and cores) fewer
-    depth = max(1, args.depth if world <= 2 else min(args.depth, 3))
 
     def e2e_steps_run(nsteps):
         inflight = []
@@ -463,6 +465,11 @@ def run_c5(args):
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def e2e_depth(args, world):
+    """Batches one caller keeps in flight: 5 on one GPU, fewer when several ranks share the host's RAM and cores."""
+    return max(1, args.depth if world == 1 else min(args.depth, 4) if world == 2 else min(args.depth, 3))
 
 
 def main():

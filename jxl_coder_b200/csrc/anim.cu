@@ -22,7 +22,7 @@
 using namespace jxlb;
 
 struct jxlb_anim {
-  std::vector<uint8_t> cs;
+  ByteVec cs;
   size_t cs_len = 0;
   ImageMetadata md;
   std::vector<FrameHeader> frames;       // displayed frames (regular / skip-progressive)

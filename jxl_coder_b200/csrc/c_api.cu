@@ -125,7 +125,7 @@ int jxlb_decode_sampled(const uint8_t* data, size_t len, int32_t width, int32_t 
 int jxlb_get_size(const uint8_t* data, size_t len, uint32_t* width, uint32_t* height) try {
   // DecodeBasicInfo (interop/JxlDecoding.cpp:178-226): header-only, CPU.
   if (!data || !width || !height) return JXLB_BAD_ARG;
-  std::vector<uint8_t> cs;
+  ByteVec cs;
   size_t cs_len = 0;
   int st = ExtractCodestream(data, len, &cs, &cs_len);
   if (st == kParseNotJxl) return JXLB_NOT_JXL;

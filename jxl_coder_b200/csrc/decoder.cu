@@ -300,7 +300,7 @@ DeviceContext* GetContext(int device) {
 struct Parsed {
   int status = JXLB_OK;
   std::string message;
-  std::vector<uint8_t> cs;
+  ByteVec cs;
   size_t cs_len = 0;
   ImageMetadata md;
   FrameHeader fh;

@@ -5,6 +5,8 @@
 
 #include <cmath>
 #include <cstring>
+#include <memory>
+#include <mutex>
 
 #include "vardct_sections.h"
 
@@ -25,6 +27,52 @@ uint64_t BE(const uint8_t* p, int n) {
     if (err) *err = (msg);   \
     return (code);           \
   } while (0)
+
+// Parse scratch (arenas, permutation buffers, LZ77 windows) comes from a process-wide pool of grow-only blocks whose
+// contents are unspecified: a fresh zero-filled 8 MB vector per image costs more than the parse itself (page faults and
+// the kernel's per-process mapping lock, which made 8 parse threads 3.5x slower per image than one).
+class ScratchLease {
+ public:
+  explicit ScratchLease(size_t bytes) {
+    {
+      std::lock_guard<std::mutex> l(Mu());
+      auto& fl = Free();
+      for (size_t k = 0; k < fl.size(); ++k)
+        if (fl[k].cap >= bytes) {
+          b_ = std::move(fl[k]);
+          fl[k] = std::move(fl.back());
+          fl.pop_back();
+          return;
+        }
+    }
+    b_.mem.reset(new uint8_t[bytes]);
+    b_.cap = bytes;
+  }
+  ~ScratchLease() {
+    std::lock_guard<std::mutex> l(Mu());
+    if (Free().size() < 256) Free().push_back(std::move(b_));
+  }
+  ScratchLease(const ScratchLease&) = delete;
+  ScratchLease& operator=(const ScratchLease&) = delete;
+  uint8_t* data() { return b_.mem.get(); }
+  template <class T>
+  T* as() { return reinterpret_cast<T*>(b_.mem.get()); }
+
+ private:
+  struct Block {
+    std::unique_ptr<uint8_t[]> mem;
+    size_t cap = 0;
+  };
+  static std::mutex& Mu() {
+    static std::mutex m;
+    return m;
+  }
+  static std::vector<Block>& Free() {
+    static std::vector<Block> v;
+    return v;
+  }
+  Block b_;
+};
 
 void ReadSizeHeader(BitReader& br, uint32_t* xs, uint32_t* ys) {
   uint32_t small = br.Read(1);
@@ -61,8 +109,9 @@ int32_t ReadCustomXY(BitReader& br) { return UnpackSigned(br.U32(0, 19, 524288, 
 
 }  // namespace
 
-int ExtractCodestream(const uint8_t* data, size_t len, std::vector<uint8_t>* out, size_t* cs_len) {
+int ExtractCodestream(const uint8_t* data, size_t len, ByteVec* out, size_t* cs_len) {
   out->clear();
+  out->reserve(len + 20);  // one allocation: the padding below must not reallocate
   if (len >= 2 && data[0] == 0xFF && data[1] == 0x0A) {
     out->assign(data, data + len);
   } else if (len >= 12 && memcmp(data, kContainerSig, 12) == 0) {
@@ -87,11 +136,11 @@ int ExtractCodestream(const uint8_t* data, size_t len, std::vector<uint8_t>* out
       const uint8_t* body = data + pos + hdr;
       size_t blen = (size_t) size - hdr;
       if (memcmp(typ, "jxlc", 4) == 0) {
-        out->insert(out->end(), body, body + blen);
+        out->append(body, body + blen);
         any = true;
       } else if (memcmp(typ, "jxlp", 4) == 0) {
         if (blen < 4) return kParseInvalid;
-        out->insert(out->end(), body + 4, body + blen);
+        out->append(body + 4, body + blen);
         any = true;
       }
       pos += (size_t) size;
@@ -102,7 +151,7 @@ int ExtractCodestream(const uint8_t* data, size_t len, std::vector<uint8_t>* out
   }
   *cs_len = out->size();
   size_t padded = ((out->size() + 3) & ~(size_t) 3) + 16;
-  out->resize(padded, 0);
+  out->resize(padded, (uint8_t) 0);
   return kParseOk;
 }
 
@@ -399,17 +448,18 @@ int ParseFrameHeader(const uint8_t* cs, size_t cs_padded, size_t cs_len, const I
   std::vector<uint32_t> perm;
   bool permuted = br.Read(1);
   if (permuted) {
-    std::vector<uint8_t> arena_mem(1 << 20);
+    ScratchLease arena_mem(1 << 20);
     Arena arena;
-    arena.Init(arena_mem.data(), (uint32_t) arena_mem.size());
+    arena.Init(arena_mem.data(), 1u << 20);
     uint32_t coff;
     int st = ParseCode<false>(br, 8, true, arena, &coff);
     if (st != kOk) JXLB_FAIL(st == kErrUnsupported ? kParseUnsupported : kParseInvalid, "TOC permutation code");
     CodeView cv;
     cv.Bind(arena.base + coff);
-    std::vector<uint32_t> window(cv.lz77 ? (1u << kLz77WindowLog) : 1);
+    const uint32_t wn = cv.lz77 ? (1u << kLz77WindowLog) : 1u;
+    ScratchLease window((size_t) wn * 4);
     SymbolReader sr;
-    sr.Begin(cv, br, window.data(), (uint32_t) window.size() - 1);
+    sr.Begin(cv, br, window.as<uint32_t>(), wn - 1);
     perm.resize(n);
     std::vector<uint32_t> temp(n);
     st = ReadPermutation(cv, sr, br, n, 0, perm.data(), temp.data());
@@ -485,9 +535,9 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
   // LfChannelDequantization
   if (!br.Read(1))
     for (int c = 0; c < 3; ++c) g->lf_dequant[c] = br.F16();
-  std::vector<uint8_t> arena_mem(8u << 20);
+  ScratchLease arena_mem(8u << 20);
   Arena arena;
-  arena.Init(arena_mem.data(), (uint32_t) arena_mem.size());
+  arena.Init(arena_mem.data(), 8u << 20);
   if (fh.encoding == 0) {
     g->global_scale = br.U32(1, 11, 2049, 11, 4097, 12, 8193, 16);
     g->quant_lf = br.U32(16, 0, 1, 5, 1, 8, 1, 16);
@@ -578,8 +628,8 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
         if (g->chplan.nb_meta) {
           ModularContext mc{};
           Arena a2;
-          std::vector<uint8_t> amem(4u << 20);
-          a2.Init(amem.data(), (uint32_t) amem.size());
+          ScratchLease amem(4u << 20);
+          a2.Init(amem.data(), 4u << 20);
           if (g->global_mh.use_global_tree) {
             if (!g->has_global_tree) JXLB_FAIL(kParseInvalid, "global tree missing");
             mc.tree = reinterpret_cast<const TreeNode*>(g->tree_blob.data());
@@ -610,8 +660,8 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
             maxw = std::max(maxw, tr.nb_colours);
           }
           std::vector<int32_t> scratch(ModFastScratch::Ints(maxw + 8));
-          std::vector<uint32_t> lz(1u << 20);
-          st = DecodeModularChannelsFast(br, mc, g->global_mh.wp, chs.data(), g->chplan.nb_meta, 0, scratch.data(), lz.data(), (1u << 20) - 1);
+          ScratchLease lz((size_t) 4 << 20);
+          st = DecodeModularChannelsFast(br, mc, g->global_mh.wp, chs.data(), g->chplan.nb_meta, 0, scratch.data(), lz.as<uint32_t>(), (1u << 20) - 1);
           if (st == kErrUnsupported || st == kErrScratch) JXLB_FAIL(kParseUnsupported, "global modular stream");
           if (st != kOk || br.Overrun()) JXLB_FAIL(kParseInvalid, "global modular stream");
         }
@@ -642,8 +692,8 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
         // the global stream's channels follow the header: decode them here
         ModularContext mc{};
         Arena a2;
-        std::vector<uint8_t> amem(4u << 20);
-        a2.Init(amem.data(), (uint32_t) amem.size());
+        ScratchLease amem(4u << 20);
+        a2.Init(amem.data(), 4u << 20);
         if (g->global_mh.use_global_tree) {
           if (!g->has_global_tree) JXLB_FAIL(kParseInvalid, "global tree missing");
           mc.tree = reinterpret_cast<const TreeNode*>(g->tree_blob.data());
@@ -675,9 +725,9 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
           o += (size_t) chs[c].w * chs[c].h;
         }
         std::vector<int32_t> scratch(ModFastScratch::Ints(gd + 8));
-        std::vector<uint32_t> lz(1u << 20);
+        ScratchLease lz((size_t) 4 << 20);
         if (ng) {
-          st = DecodeModularChannelsFast(br, mc, g->global_mh.wp, chs.data(), ng, 0, scratch.data(), lz.data(), (1u << 20) - 1);
+          st = DecodeModularChannelsFast(br, mc, g->global_mh.wp, chs.data(), ng, 0, scratch.data(), lz.as<uint32_t>(), (1u << 20) - 1);
           if (st == kErrUnsupported || st == kErrScratch) JXLB_FAIL(kParseUnsupported, "global modular stream");
           if (st != kOk || br.Overrun()) JXLB_FAIL(kParseInvalid, "global modular stream");
         }
@@ -691,8 +741,8 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
     BitReader hbr;
     hbr.Init(cs, cs_padded, fh.sec_bit_begin[sec], fh.sec_bit_end[sec]);
     HfGlobalOut out;
-    std::vector<uint32_t> perm_scratch(2 * 65536);
-    int st = ParseHfGlobal(hbr, fh.num_groups, g->bctx.num_ctx, NaturalOrderPoolHost(), arena, perm_scratch.data(), &out);
+    ScratchLease perm_scratch((size_t) 2 * 65536 * 4);
+    int st = ParseHfGlobal(hbr, fh.num_groups, g->bctx.num_ctx, NaturalOrderPoolHost(), arena, perm_scratch.as<uint32_t>(), &out);
     if (st == kErrUnsupported) JXLB_FAIL(kParseUnsupported, "HfGlobal: custom quant tables");
     if (st != kOk || hbr.Overrun()) JXLB_FAIL(kParseInvalid, "HfGlobal");
     g->num_hf_presets = out.num_hf_presets;

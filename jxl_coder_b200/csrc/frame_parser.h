@@ -4,6 +4,7 @@
 // JXL_DEC_COLOR_ENCODING events (/root/reference/jxlcoder/src/main/cpp/interop/JxlDecoding.cpp:81-144) and from
 // JxlDecoderProcessInput's header handling.  Format digest: SURVEY.md App. B.1-B.5, B.7.
 #pragma once
+#include "recycle_alloc.h"
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -112,9 +113,9 @@ struct FrameGlobals {
   std::vector<uint8_t> bctx_map;
   CflParams cfl{84, 0.f, 1.f, 128, 128};
   bool has_global_tree = false;
-  std::vector<uint8_t> tree_blob;     // TreeNode[num_nodes]
+  ByteVec tree_blob;     // TreeNode[num_nodes]
   uint32_t tree_nodes = 0, tree_uses_wp = 0, tree_max_property = 0;
-  std::vector<uint8_t> tree_code;     // code blob for the tree's leaf contexts
+  ByteVec tree_code;     // code blob for the tree's leaf contexts
   uint64_t global_modular_bit = 0;    // where the global modular GroupHeader starts
   ModularHeader global_mh{};          // parsed for multi-section frames with a modular image
   ChannelPlan chplan{};               // ... its channel list (palette meta channels first)
@@ -129,15 +130,15 @@ struct FrameGlobals {
   // HfGlobal
   bool hf_parsed = false;
   uint32_t num_hf_presets = 1, used_orders = 0;
-  std::vector<uint16_t> order_pool;
+  U16Vec order_pool;
   OrderTableIndex orders{};
-  std::vector<uint8_t> ac_code;
+  ByteVec ac_code;
   uint64_t hf_global_end_bit = 0;
 };
 
 // Extracts the codestream from a bare (FF 0A) or boxed (ISOBMFF) file into `out`, zero-padded by 16 bytes and a
 // multiple of 4 long.  *cs_len = unpadded length.
-int ExtractCodestream(const uint8_t* data, size_t len, std::vector<uint8_t>* out, size_t* cs_len);
+int ExtractCodestream(const uint8_t* data, size_t len, ByteVec* out, size_t* cs_len);
 
 // Parses SizeHeader + ImageMetadata (+ICC skip) and leaves *frame_bit at the first frame header.
 int ParseImageHeader(const uint8_t* cs, size_t cs_padded, size_t cs_len, ImageMetadata* md, uint64_t* frame_bit, std::string* err);

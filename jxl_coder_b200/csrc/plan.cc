@@ -150,7 +150,10 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
 }
 
 void FillConstRegion(const FramePlan& plan, const uint8_t* cs_padded, const FrameHeader& fh, const FrameGlobals& g, uint8_t* dst) {
-  memset(dst, 0, plan.const_bytes);
+  // zero everything but the codestream copy, which is the bulk of the region and overwritten next
+  memset(dst, 0, plan.off_cs);
+  const size_t cs_end = plan.off_cs + plan.proto.cs_bytes;
+  memset(dst + cs_end, 0, plan.const_bytes - cs_end);
   memcpy(dst + plan.off_cs, cs_padded, plan.proto.cs_bytes);
   memcpy(dst + plan.off_sec_begin, fh.sec_bit_begin.data(), fh.sec_bit_begin.size() * 8);
   memcpy(dst + plan.off_sec_end, fh.sec_bit_end.data(), fh.sec_bit_end.size() * 8);

@@ -29,7 +29,8 @@ struct Emu {
   FrameHeader fh;
   FrameGlobals g;
   FramePlan plan;
-  std::vector<uint8_t> cs, cregion, wregion;
+  ByteVec cs;
+  std::vector<uint8_t> cregion, wregion;
   std::vector<float> xyb;
   FrameDev f;
   int status = 0;
@@ -288,7 +289,7 @@ int emu_resize(const uint8_t* src, uint32_t w, uint32_t h, int32_t req_w, int32_
 // api_level < 34 colour pass (color_matrix.h) of the image whose file is `jxl`, in place on an RGBA8 array.
 // 0 applied, 1 not needed for this colour encoding, 2 needed but not covered, -1 parse error.
 int emu_color_matrix(const uint8_t* jxl, size_t len, uint8_t* rgba, uint32_t w, uint32_t h) {
-  std::vector<uint8_t> cs;
+  ByteVec cs;
   size_t cs_len = 0;
   if (ExtractCodestream(jxl, len, &cs, &cs_len)) return -1;
   ImageMetadata md;
@@ -304,7 +305,7 @@ int emu_color_matrix(const uint8_t* jxl, size_t len, uint8_t* rgba, uint32_t w, 
 }
 // The 16-bit variant (applyColorMatrix16Bit) on RGBA16 rows.
 int emu_color_matrix16(const uint8_t* jxl, size_t len, uint16_t* rgba, uint32_t w, uint32_t h) {
-  std::vector<uint8_t> cs;
+  ByteVec cs;
   size_t cs_len = 0;
   if (ExtractCodestream(jxl, len, &cs, &cs_len)) return -1;
   ImageMetadata md;
