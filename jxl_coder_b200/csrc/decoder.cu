@@ -718,7 +718,6 @@ struct Batch {
     }
   }
   cudaEvent_t span_start = nullptr, span_end = nullptr;  // first run start / last run end since ResetStats
-  cudaEvent_t ev_block = nullptr;                         // blocking-sync event the host waits on (CollectRuns)
   bool span_armed = true;
   bool events = false, upload_timed = false;
   bool finished[kEventSets] = {};
@@ -735,7 +734,6 @@ struct Batch {
         for (auto& e : set) cudaEventDestroy(e);
     for (auto& v : sample_ev)
       for (auto& e : v) cudaEventDestroy(e);
-    if (ev_block) cudaEventDestroy(ev_block);
     if (span_start) cudaEventDestroy(span_start);
     if (span_end) cudaEventDestroy(span_end);
     if (own_streams) {
@@ -991,11 +989,8 @@ struct Batch {
     buf = use ? use : &own;
     CUDA_OK(cudaSetDevice(ctx->device));
     if (!events) {
-      // blocking-sync events: a thread waiting for a batch sleeps instead of spinning on a core (several batches are in
-      // flight per process, and several processes share the host on a multi-GPU box)
       for (auto& set : ev_ring)
-        for (auto& e : set) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventBlockingSync));
-      CUDA_OK(cudaEventCreateWithFlags(&ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+        for (auto& e : set) CUDA_OK(cudaEventCreate(&e));
       CUDA_OK(cudaEventCreate(&span_start));
       CUDA_OK(cudaEventCreate(&span_end));
       events = true;
@@ -1097,7 +1092,7 @@ struct Batch {
     for (size_t i = 0; i < n; ++i) {
       if (ps[i].status != JXLB_OK) continue;
       host_dst[i] = Pool().Get(final_bytes[i]);
-      CUDA_OK(cudaEventCreateWithFlags(&img_ev[i], cudaEventDisableTiming | cudaEventBlockingSync));
+      CUDA_OK(cudaEventCreateWithFlags(&img_ev[i], cudaEventDisableTiming));
     }
   }
 
@@ -1344,8 +1339,7 @@ struct Batch {
   // ms: [0] upload, [1] LF sections, [2] group sections, [3] LF final, [4] inverse transforms, [5] filters+colour+pack,
   //     [6] download, [7] all kernels
   void CollectRuns() {
-    CUDA_OK(cudaEventRecord(ev_block, stream));
-    CUDA_OK(cudaEventSynchronize(ev_block));
+    CUDA_OK(cudaStreamSynchronize(stream));
     for (int k = pending_runs - 1; k >= 0; --k) {
       const int set = ((run_index - k) % kEventSets + kEventSets) % kEventSets;
       cudaEvent_t* e = ev_ring[set];
