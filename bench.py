@@ -42,7 +42,9 @@ def load_inputs(batch=BATCH, distinct=DISTINCT, size=SIZE):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks and throttle reasons of this rank's GPU while the timed region runs: NVML in-process (a query costs
+    microseconds); only when the nvidia_ml_py module is missing does it fall back to spawning nvidia-smi, once a second --
+    one nvidia-smi process per rank every 150 ms kept several host cores and the driver's locks busy on 4 / 8 GPU boxes."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -52,7 +54,28 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.stop_flag = False
 
+    def _nvml_loop(self):
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        while not self.stop_flag:
+            try:
+                r = get_reasons(h)
+                self.samples.append([str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx)] +
+                                    ["Active" if r & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
     def run(self):
+        try:
+            self._nvml_loop()
+            return
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
@@ -61,7 +84,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            time.sleep(0.15)
+            time.sleep(1.0)
 
     def summary(self):
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
@@ -269,7 +292,7 @@ def run_ours(args):
     e2e_steps_run(2 * depth if args.warmup else 0)  # every decode slot allocates its buffers + pinned pool once
     barrier()
     t1 = time.perf_counter()
-    e2e_steps = max(1, args.steps, 4 * depth)
+    e2e_steps = max(1, args.steps, 6 * depth)  # long enough that filling and draining the pipeline (one batch latency) is a small share
     e2e_steps_run(e2e_steps)
     barrier()
     e2e_wall = time.perf_counter() - t1
@@ -469,7 +492,7 @@ def run_c5(args):
 
 def e2e_depth(args, world):
     """Batches one caller keeps in flight: 5 on one GPU, fewer when several ranks share the host's RAM and cores."""
-    return max(1, args.depth if world == 1 else min(args.depth, 4) if world == 2 else min(args.depth, 3))
+    return max(1, args.depth if world == 1 else min(args.depth, 4) if world <= 4 else min(args.depth, 3))
 
 
 def main():
