@@ -65,6 +65,35 @@ size_t HostThreads() {
   }();
   return v;
 }
+// Host waits.  cudaEventSynchronize spins on a core; with several batches in flight per process and one process per GPU
+// on a box with few cores per GPU (4 on the 8-GPU boxes) the spinning waiters starve the parse threads, while CUDA's
+// blocking-sync waits wake up far too late here (measured: e2e 165 ms per step instead of 112).  JXLB_WAIT_MODE=poll
+// polls the event every 50 us instead; the default ("auto") polls when the process has fewer than 6 host threads.
+bool PollWaits() {
+  static const bool v = [] {
+    const char* e = getenv("JXLB_WAIT_MODE");
+    if (e && !strcmp(e, "poll")) return true;
+    if (e && !strcmp(e, "spin")) return false;
+    return HostThreads() < 6;
+  }();
+  return v;
+}
+cudaError_t WaitEvent(cudaEvent_t ev) {
+  if (!PollWaits()) return cudaEventSynchronize(ev);
+  for (;;) {
+    const cudaError_t r = cudaEventQuery(ev);
+    if (r != cudaErrorNotReady) return r;
+    std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
+}
+cudaError_t WaitStream(cudaStream_t st) {
+  if (!PollWaits()) return cudaStreamSynchronize(st);
+  for (;;) {
+    const cudaError_t r = cudaStreamQuery(st);
+    if (r != cudaErrorNotReady) return r;
+    std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
+}
 template <class Fn>
 void ParallelFor(size_t n, Fn fn) {
   size_t nt = std::min<size_t>(n, HostThreads());
@@ -1339,7 +1368,7 @@ struct Batch {
   // ms: [0] upload, [1] LF sections, [2] group sections, [3] LF final, [4] inverse transforms, [5] filters+colour+pack,
   //     [6] download, [7] all kernels
   void CollectRuns() {
-    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(WaitStream(stream));
     for (int k = pending_runs - 1; k >= 0; --k) {
       const int set = ((run_index - k) % kEventSets + kEventSets) % kEventSets;
       cudaEvent_t* e = ev_ring[set];
@@ -1394,10 +1423,10 @@ struct Batch {
     if (to_host)
       for (size_t i = 0; i < n && i < host_dst.size(); ++i) {
         if (!host_dst[i] || ps[i].status != JXLB_OK) continue;
-        CUDA_OK(cudaEventSynchronize(img_ev[i]));
+        CUDA_OK(WaitEvent(img_ev[i]));
         CUDA_OK(cudaMemcpyAsync(host_dst[i], buf->final_out.p + final_off[i], final_bytes[i], cudaMemcpyDeviceToHost, D2hStream()));
       }
-    if (ran) CUDA_OK(cudaEventSynchronize(ev[7]));  // every kernel of the run is done: the status words are final
+    if (ran) CUDA_OK(WaitEvent(ev[7]));  // every kernel of the run is done: the status words are final
     uint32_t* sh = reinterpret_cast<uint32_t*>(buf->status_host.p);
     for (size_t i = 0; i < ps.size(); ++i) {
       Parsed& p = ps[i];
