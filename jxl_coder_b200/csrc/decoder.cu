@@ -249,7 +249,7 @@ struct DeviceContext {
     void Leave(uint64_t k, cudaStream_t s) { CUDA_OK(cudaEventRecord(ev[k % kRing], s)); }
   };
   StageGate gate_lf, gate_ac, gate_recon;
-  // One stream carries every device-to-host copy of result pixels on this GPU: measured on B200 / PCIe Gen5 (tests/gpu_pcie2.py),
+  // One stream carries every device-to-host copy of result pixels on this GPU: measured on B200 / PCIe Gen5 (tools/probes/gpu_pcie2.py),
   // 64 MiB copies into pinned buffers reach 48.5 GB/s from one or two streams and only 39 GB/s when four streams interleave.
   cudaStream_t d2h_stream = nullptr;
   cudaEvent_t origin = nullptr;  // JXLB_TIMELINE=1: stage boundaries of every run are printed relative to this event

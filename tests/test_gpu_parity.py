@@ -521,7 +521,7 @@ def test_corrupt_inputs_never_hang(J):
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, os.path.join(here, "gpu_fuzz.py"), "7"], capture_output=True, text=True, timeout=240)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(here), "tools", "probes", "gpu_fuzz.py"), "7"], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "fuzz ok=" in r.stdout
 
@@ -552,7 +552,7 @@ def test_cropped_frames_over_empty_canvas(J, ref):
 @pytest.mark.parametrize("o", [3, 6, 7])
 @pytest.mark.parametrize("cfg", [1, 2, 3])
 def test_orientation_on_16bit_lossy(J, ref, o, cfg):
-    """Sources deeper than 8 bits are staged as RGBA16 in front of the orientation pass (found by tests/gpu_sweep.py)."""
+    """Sources deeper than 8 bits are staged as RGBA16 in front of the orientation pass (found by tools/probes/gpu_sweep.py)."""
     from oracle import synth
     w, h = 218, 155
     img = synth.synth_image(w, h, 8).astype(np.uint16) * 257

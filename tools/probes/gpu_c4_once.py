@@ -3,7 +3,7 @@ pass and reformat kernels all run).  Used under ncu."""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import jxl_coder_b200 as J  # noqa: E402
 from oracle import gen_inputs  # noqa: E402

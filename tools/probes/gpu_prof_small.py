@@ -1,6 +1,6 @@
 """Tiny profiling workload for ncu: one prepared batch of N 4096x4096 images, run once."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import jxl_coder_b200 as J
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
