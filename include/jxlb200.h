@@ -136,6 +136,14 @@ JXLB_API int jxlb_get_size(const uint8_t* data, size_t len, uint32_t* width, uin
 
 JXLB_API void jxlb_image_free(jxlb_image* img);
 
+/* TEST HOOK (no counterpart in the reference; used by tests/test_gpu_recon_block.py).  Runs the reconstruction kernels
+   (dequantisation, LLF from LF, inverse transform) on ONE synthetic block of `strategy` (0 .. 26, JPEG XL's AcStrategy
+   numbering) on CUDA device `device` (-1 = current).  q: [3][8 cy][8 cx] quantised coefficients, X / Y / B, row = vertical
+   frequency; lf: [3][cy][cx] dequantised LF samples; out: [3][8 cy][8 cx] XYB samples.  libjxl's encoder never emits
+   DCT128 / DCT256 blocks, so no file reaches those transforms: this is how the tests drive them on the GPU. */
+JXLB_API int jxlb_test_recon_block(int device, uint32_t strategy, const int16_t* q, const float* lf, uint32_t hf_mul,
+                                   uint32_t global_scale, float* out);
+
 /* Prepared batches (throughput interface).  jxlb_batch_prepare parses the requests on the CPU and uploads the
    codestreams + tables, so the inputs are resident in HBM; jxlb_batch_run executes every kernel (entropy decode ->
    packed pixels) and leaves the results in HBM; it can be called repeatedly.  jxlb_batch_fetch copies one result to

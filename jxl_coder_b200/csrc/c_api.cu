@@ -122,6 +122,13 @@ int jxlb_decode_sampled(const uint8_t* data, size_t len, int32_t width, int32_t 
   return st;
 }
 
+int jxlb_test_recon_block(int device, uint32_t strategy, const int16_t* q, const float* lf, uint32_t hf_mul, uint32_t global_scale,
+                          float* out) try {
+  return TestReconBlock(device, strategy, q, lf, hf_mul, global_scale, out);
+} catch (...) {
+  return JXLB_ERROR;
+}
+
 int jxlb_get_size(const uint8_t* data, size_t len, uint32_t* width, uint32_t* height) try {
   // DecodeBasicInfo (interop/JxlDecoding.cpp:178-226): header-only, CPU.
   if (!data || !width || !height) return JXLB_BAD_ARG;

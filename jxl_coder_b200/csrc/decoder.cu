@@ -30,6 +30,7 @@
 #include "numeric_tables.h"
 #include "plan.h"
 #include "resize.h"
+#include "test_block.h"
 
 namespace jxlb {
 
@@ -1780,5 +1781,54 @@ void BatchStageMsMean(const Batch* b, float* ms8, int* runs) {
   if (runs) *runs = b ? b->stage_runs : 0;
 }
 void FreeBatch(Batch* b) { delete b; }
+
+
+// ---- test hook: one synthetic block through the reconstruction kernels (test_block.h) ---------------------------------
+int TestReconBlock(int device, uint32_t strategy, const int16_t* q, const float* lf, uint32_t hf_mul, uint32_t global_scale,
+                   float* out) {
+  if (strategy >= (uint32_t) kNumStrategies || !q || !lf || !out || !hf_mul || !global_scale) return JXLB_BAD_ARG;
+  uint8_t *cb_d = nullptr, *wb_d = nullptr;
+  float* xyb_d = nullptr;
+  cudaStream_t st = nullptr;
+  int rc = JXLB_OK;
+  try {
+    DeviceContext* ctx = GetContext(device);
+    CUDA_OK(cudaSetDevice(ctx->device));
+    ImageMetadata md;
+    FrameHeader fh;
+    FrameGlobals g;
+    FramePlan plan;
+    MakeSingleBlockPlan(strategy, global_scale, &md, &fh, &g, &plan);
+    std::vector<uint8_t> cb(plan.const_bytes), wb(plan.work_bytes), cs(16);
+    FillConstRegion(plan, cs.data(), fh, g, cb.data());
+    FillSingleBlock(BindFrameDev(plan, cb.data(), wb.data()), strategy, q, lf, hf_mul);
+    CUDA_OK(cudaMalloc(&cb_d, plan.const_bytes));
+    CUDA_OK(cudaMalloc(&wb_d, plan.work_bytes));
+    CUDA_OK(cudaMalloc(&xyb_d, plan.xyb_bytes));
+    CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CUDA_OK(cudaMemcpyAsync(cb_d, cb.data(), plan.const_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(wb_d, wb.data(), plan.work_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemsetAsync(xyb_d, 0, plan.xyb_bytes, st));
+    FrameDev f = BindFrameDev(plan, cb_d, wb_d);
+    f.xyb0 = f.xyb1 = xyb_d;
+    LaunchRecon(f, ctx->nt_dev, st);
+    const uint32_t R = 8 * StrategyCellsY(strategy), C = 8 * StrategyCellsX(strategy);
+    CUDA_OK(cudaMemcpy2DAsync(out, C * sizeof(float), xyb_d, f.plane_stride * sizeof(float), C * sizeof(float), R, cudaMemcpyDeviceToHost, st));
+    for (uint32_t c = 1; c < 3; ++c)
+      CUDA_OK(cudaMemcpy2DAsync(out + (size_t) c * R * C, C * sizeof(float), xyb_d + (size_t) c * f.plane_h * f.plane_stride,
+                                f.plane_stride * sizeof(float), C * sizeof(float), R, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  } catch (CudaError&) {
+    cudaGetLastError();
+    rc = JXLB_ERROR_NO_DEVICE;
+  } catch (const std::exception&) {
+    rc = JXLB_OOM;
+  }
+  if (st) cudaStreamDestroy(st);
+  cudaFree(cb_d);
+  cudaFree(wb_d);
+  cudaFree(xyb_d);
+  return rc;
+}
 
 }  // namespace jxlb

@@ -64,4 +64,6 @@ void BatchStageMs(const Batch* b, float* ms8);
 const void* BatchDevicePixels(const Batch* b, size_t i, size_t* bytes);
 cudaStream_t BatchStream(const Batch* b);
 void FreeBatch(Batch* b);
+// Test hook (include/jxlb200.h: jxlb_test_recon_block).
+int TestReconBlock(int device, uint32_t strategy, const int16_t* q, const float* lf, uint32_t hf_mul, uint32_t global_scale, float* out);
 }  // namespace jxlb

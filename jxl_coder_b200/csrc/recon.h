@@ -337,9 +337,11 @@ JXLB_HD void ReconRegion(const FrameDev& f, const NumericTables& nt, uint32_t rx
 
 // Blocks that are not contained in one 64x64 region (larger than 64 pixels in a dimension, or straddling region
 // borders): reconstructed in place in f.xyb0 through global memory.  (bx, by) = top-left cell of the block.
+// Stage 1: dequantised coefficients + chroma-from-luma + the lowest frequencies from the LF image, written in the block's
+// rectangle of f.xyb0 as F[vertical frequency][horizontal frequency].  The caller synchronises after it.
 template <class Sync>
-JXLB_HD void ReconLargeBlock(const FrameDev& f, const NumericTables& nt, uint32_t bx, uint32_t by, int tid, int nthreads,
-                             Sync sync) {
+JXLB_HD void ReconLargeCoefficients(const FrameDev& f, const NumericTables& nt, uint32_t bx, uint32_t by, int tid, int nthreads,
+                                    Sync sync) {
   const size_t ci = (size_t) by * f.w8 + bx;
   const uint32_t t = f.cell_strategy[ci] & 0x7F;
   const uint32_t cx = StrategyCellsX(t), cy = StrategyCellsY(t);
@@ -377,7 +379,14 @@ JXLB_HD void ReconLargeBlock(const FrameDev& f, const NumericTables& nt, uint32_
     }
     f.xyb0[c * pplane + (size_t) (by * 8 + kyi) * f.plane_stride + bx * 8 + kxi] = v;
   }
-  sync();
+}
+
+// Stage 2: separable inverse DCT in place (columns, then rows).
+template <class Sync>
+JXLB_HD void ReconLargeInverse(const FrameDev& f, uint32_t bx, uint32_t by, int tid, int nthreads, Sync sync) {
+  const uint32_t t = f.cell_strategy[(size_t) by * f.w8 + bx] & 0x7F;
+  const uint32_t R = 8 * StrategyCellsY(t), C = 8 * StrategyCellsX(t);
+  const size_t pplane = (size_t) f.plane_h * f.plane_stride;
   float scratch[512];
   for (uint32_t i = (uint32_t) tid; i < 3 * C; i += (uint32_t) nthreads) {
     const uint32_t c = i / C, u = i % C;
@@ -392,6 +401,16 @@ JXLB_HD void ReconLargeBlock(const FrameDev& f, const NumericTables& nt, uint32_
     if (C > 64) Idct1dLarge(p, 1, (int) C, scratch);
     else Idct1dDispatch(p, 1, (int) C);
   }
+}
+
+// Blocks that are not contained in one 64x64 region (larger than 64 pixels in a dimension, or straddling region
+// borders): reconstructed in place in f.xyb0 through global memory.  (bx, by) = top-left cell of the block.
+template <class Sync>
+JXLB_HD void ReconLargeBlock(const FrameDev& f, const NumericTables& nt, uint32_t bx, uint32_t by, int tid, int nthreads,
+                             Sync sync) {
+  ReconLargeCoefficients(f, nt, bx, by, tid, nthreads, sync);
+  sync();
+  ReconLargeInverse(f, bx, by, tid, nthreads, sync);
 }
 
 // True when the block whose top-left cell is (bx, by) is handled by ReconLargeBlock rather than ReconRegion.

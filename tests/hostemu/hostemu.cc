@@ -16,6 +16,7 @@
 
 #include "../../jxl_coder_b200/csrc/frame_parser.h"
 #include "../../jxl_coder_b200/csrc/plan.h"
+#include "../../jxl_coder_b200/csrc/test_block.h"
 #include "../../jxl_coder_b200/csrc/vardct_sections.h"
 #include "../../jxl_coder_b200/csrc/color_params.h"
 #include "../../jxl_coder_b200/csrc/numeric_tables.h"
@@ -238,6 +239,38 @@ uint32_t emu_plane_h(void* h) { return static_cast<Emu*>(h)->f.plane_h; }
 // Unit hooks for table checks.
 uint32_t emu_freq_ctx(uint32_t k) { return ZeroDensityFreqCtx(k); }
 uint32_t emu_nnz_ctx(uint32_t k) { return ZeroDensityNnzCtx(k); }
+// One synthetic block through the reconstruction code (test_block.h): coeffs_out = the dequantised + LLF coefficient arrays
+// F[c][vertical][horizontal] the inverse transform consumes, pixels_out = its result; both [3][8 cy][8 cx].
+int emu_recon_block(uint32_t strategy, const int16_t* q, const float* lf, uint32_t hf_mul, uint32_t global_scale, float* coeffs_out,
+                    float* pixels_out) {
+  // plain DCT strategies only: the special 8x8 transforms (IDENTITY, DCT2X2, DCT4X4, DCT4X8, AFV) keep their own coefficient
+  // layouts and are reached by encoder-made files
+  if (strategy >= (uint32_t) kNumStrategies || (strategy >= 1 && strategy <= 3) || (strategy >= 12 && strategy <= 17)) return 1;
+  ImageMetadata md;
+  FrameHeader fh;
+  FrameGlobals g;
+  FramePlan plan;
+  MakeSingleBlockPlan(strategy, global_scale, &md, &fh, &g, &plan);
+  std::vector<uint8_t> cb(plan.const_bytes), wb(plan.work_bytes), cs(16);
+  FillConstRegion(plan, cs.data(), fh, g, cb.data());
+  FrameDev f = BindFrameDev(plan, cb.data(), wb.data());
+  std::vector<float> xyb(plan.xyb_bytes / sizeof(float));
+  f.xyb0 = f.xyb1 = xyb.data();
+  FillSingleBlock(f, strategy, q, lf, hf_mul);
+  const NumericTables& nt = GetHostNumericTables().tables;
+  auto nosync = [] {};
+  const uint32_t R = 8 * StrategyCellsY(strategy), C = 8 * StrategyCellsX(strategy);
+  const size_t pplane = (size_t) f.plane_h * f.plane_stride;
+  auto grab = [&](float* dst) {
+    for (uint32_t c = 0; c < 3; ++c)
+      for (uint32_t r = 0; r < R; ++r) memcpy(dst + ((size_t) c * R + r) * C, f.xyb0 + c * pplane + (size_t) r * f.plane_stride, C * sizeof(float));
+  };
+  ReconLargeCoefficients(f, nt, 0, 0, 0, 1, nosync);
+  grab(coeffs_out);
+  ReconLargeInverse(f, 0, 0, 0, 1, nosync);
+  grab(pixels_out);
+  return 0;
+}
 // PlanChannels (modular.h) on a hand-made header.  tr: per transform (id, begin_c, num_c, nb_colours).
 // out: [0] nb_meta, [1] ncoded, [2..9] coded_plane, [10..17] meta_tr, [18] meta_ints
 int emu_plan_channels(uint32_t nfinal, uint32_t ntr, const uint32_t* tr, uint32_t* out) {
