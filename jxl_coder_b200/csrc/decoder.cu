@@ -958,7 +958,7 @@ struct Batch {
         bool lane = false;
         if (f.encoding == 0 && !p.g.ac_code.empty()) {
           const CodeHeader* chh = reinterpret_cast<const CodeHeader*>(p.g.ac_code.data());
-          lane = !chh->lz77 && chh->total_bytes <= kMaxAcSmemCode && getenv("JXLB_NO_LANE_AC") == nullptr;
+          lane = !chh->lz77 && chh->total_bytes <= kMaxAcSmemCode && f.num_passes == 1 && getenv("JXLB_NO_LANE_AC") == nullptr;
           if (lane) {
             ac_smem_code_bytes = std::max(ac_smem_code_bytes, chh->total_bytes);
             if (chh->use_prefix) ac_fast = false;

@@ -93,6 +93,14 @@ struct OrderTableIndex {
   uint32_t offset[kNumOrders][3];  // into the uint32_t order pool; 0xFFFFFFFF if the order cannot occur
 };
 
+// Tables of one further pass of a progressive frame (passes 1 .. num_passes - 1), in the const region; the blobs are
+// addressed relative to the start of the PassDev array.
+struct PassDev {
+  OrderTableIndex orders;
+  uint32_t used_orders, shift;
+  uint64_t ac_code_rel, order_pool_rel;
+};
+
 // Everything global to one frame that the device needs (POD; device pointers filled by the decoder).
 struct FrameDev {
   // geometry of the coded frame
@@ -131,6 +139,8 @@ struct FrameDev {
   const uint8_t* ac_code;          // code blob
   const uint16_t* order_pool;
   OrderTableIndex orders;
+  const PassDev* pass_table;       // progressive frames: tables of passes 1 ..; pass 0 uses the fields above
+  uint32_t pass_shift0, pass_pad;  // coefficients of pass 0 are coded >> pass_shift0
   RestorationFilter rf;
   // extra channels / modular image
   uint32_t num_mod_channels;       // channels of the frame's modular image (colour for modular frames + extras)

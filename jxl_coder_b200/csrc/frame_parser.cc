@@ -335,7 +335,7 @@ int ParseFrameHeader(const uint8_t* cs, size_t cs_padded, size_t cs_len, const I
       fh->num_passes = br.U32(1, 0, 2, 0, 3, 0, 4, 3);
       if (fh->num_passes != 1) {
         uint32_t nds = br.U32(0, 0, 1, 0, 2, 0, 3, 1);
-        for (uint32_t i = 0; i + 1 < fh->num_passes; ++i) br.Read(2);
+        for (uint32_t i = 0; i + 1 < fh->num_passes; ++i) fh->pass_shift[i] = br.Read(2);
         for (uint32_t i = 0; i < nds; ++i) br.U32(1, 0, 2, 0, 4, 0, 8, 0);
         for (uint32_t i = 0; i < nds; ++i) br.U32(0, 0, 1, 0, 2, 0, 0, 3);
       }
@@ -527,7 +527,9 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
   if (fh.upsampling != 1) JXLB_FAIL(kParseUnsupported, "upsampled frame");
   for (uint32_t u : fh.ec_upsampling)
     if (u != 1) JXLB_FAIL(kParseUnsupported, "upsampled extra channel");
-  if (fh.num_passes != 1) JXLB_FAIL(kParseUnsupported, "progressive passes");
+  // progressive passes: the AC coefficients of a group arrive in num_passes sections that add up; the modular channels of
+  // such frames (extra channels split over the passes by their shifts) are not handled
+  if (fh.num_passes != 1 && (fh.encoding != 0 || !md.extra.empty())) JXLB_FAIL(kParseUnsupported, "progressive passes with modular channels");
   if (fh.frame_type != 0) JXLB_FAIL(kParseUnsupported, "non-regular frame type");
   if (fh.do_ycbcr) JXLB_FAIL(kParseUnsupported, "YCbCr frame");
   BitReader br;
@@ -752,6 +754,21 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
                          reinterpret_cast<const uint16_t*>(arena.base + out.order_pool_off) + out.order_pool_entries);
     const CodeHeader* ch = reinterpret_cast<const CodeHeader*>(arena.base + out.ac_code_off);
     g->ac_code.assign(arena.base + out.ac_code_off, arena.base + out.ac_code_off + ch->total_bytes);
+    for (uint32_t ps = 1; ps < fh.num_passes; ++ps) {
+      HfGlobalOut po;
+      po.num_hf_presets = out.num_hf_presets;
+      arena.used = 0;  // the previous pass's tables were copied out
+      st = ParseHfPass(hbr, g->bctx.num_ctx, NaturalOrderPoolHost(), arena, perm_scratch.as<uint32_t>(), &po);
+      if (st != kOk || hbr.Overrun()) JXLB_FAIL(st == kErrUnsupported || st == kErrScratch ? kParseUnsupported : kParseInvalid, "HfGlobal pass");
+      FrameGlobals::ExtraPass ep;
+      ep.used_orders = po.used_orders;
+      ep.orders = po.orders;
+      ep.order_pool.assign(reinterpret_cast<const uint16_t*>(arena.base + po.order_pool_off),
+                           reinterpret_cast<const uint16_t*>(arena.base + po.order_pool_off) + po.order_pool_entries);
+      const CodeHeader* pch = reinterpret_cast<const CodeHeader*>(arena.base + po.ac_code_off);
+      ep.ac_code.assign(arena.base + po.ac_code_off, arena.base + po.ac_code_off + pch->total_bytes);
+      g->extra_passes.push_back(std::move(ep));
+    }
     g->hf_parsed = true;
     g->hf_global_end_bit = hbr.Position();
   }

@@ -86,6 +86,7 @@ struct FrameHeader {
   uint32_t group_size_shift = 1;
   uint32_t x_qm_scale = 3, b_qm_scale = 2;
   uint32_t num_passes = 1;
+  uint32_t pass_shift[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // coefficients of pass p are coded >> pass_shift[p] (0 for the last)
   uint32_t lf_level = 0;
   bool have_crop = false;
   int32_t x0 = 0, y0 = 0;
@@ -133,6 +134,14 @@ struct FrameGlobals {
   U16Vec order_pool;
   OrderTableIndex orders{};
   ByteVec ac_code;
+  // progressive frames: the tables of passes 1 .. num_passes - 1 (pass 0 uses the fields above)
+  struct ExtraPass {
+    uint32_t used_orders = 0;
+    OrderTableIndex orders{};
+    U16Vec order_pool;
+    ByteVec ac_code;
+  };
+  std::vector<ExtraPass> extra_passes;
   uint64_t hf_global_end_bit = 0;
 };
 

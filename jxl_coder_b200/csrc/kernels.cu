@@ -201,16 +201,19 @@ __global__ void __launch_bounds__(kStreamBlockThreads) PassGroupKernel(const Fra
   const FrameDev& f = frames[job.frame];
   StreamScratch sc = CarveScratch(scratch, j, nullptr, nullptr);
   BindLz77Window(scratch, job, &sc);
-  BitReader br;
-  const uint32_t sec = 1 + f.num_lf_groups + 1 + job.index;
-  br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);
   int st = kOk;
-  if (f.encoding == 0) {
-    // the group's blocks come from its LF group's placement: unusable when that section failed
-    const uint32_t lfg = (job.index / f.ngx / 8) * f.nlfx + (job.index % f.ngx) / 8;
-    st = f.status[lfg] == kOk ? DecodeAcGroup(br, f, job.index, nat, sc) : (int) kErrBadStream;
+  // progressive frames: the group's sections of pass 0, 1, ... in turn (their coefficients add up)
+  for (uint32_t pass = 0; pass < f.num_passes && st == kOk; ++pass) {
+    BitReader br;
+    const uint32_t sec = 1 + f.num_lf_groups + 1 + pass * f.num_groups + job.index;
+    br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);
+    if (f.encoding == 0) {
+      // the group's blocks come from its LF group's placement: unusable when that section failed
+      const uint32_t lfg = (job.index / f.ngx / 8) * f.nlfx + (job.index % f.ngx) / 8;
+      st = f.status[lfg] == kOk ? DecodeAcGroup(br, f, job.index, nat, sc, pass) : (int) kErrBadStream;
+    }
+    if (st == kOk) st = DecodeModularGroup(br, f, job.index, sc, scratch.max_local_nodes);
   }
-  if (st == kOk) st = DecodeModularGroup(br, f, job.index, sc, scratch.max_local_nodes);
   f.status[job.status_slot] = st;
 }
 

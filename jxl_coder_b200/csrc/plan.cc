@@ -101,6 +101,13 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
     p.off_sq_global = take(g.sq_global_data.size() * sizeof(int32_t));
   }
   if (!g.meta_data.empty()) p.off_meta = take(g.meta_data.size() * sizeof(int32_t));
+  f.pass_shift0 = fh.num_passes > 1 ? fh.pass_shift[0] : 0;
+  if (!g.extra_passes.empty()) {
+    // [PassDev x (num_passes - 1)] then, per pass, its order pool and its code blob (offsets relative to the table)
+    size_t bytes = Align(g.extra_passes.size() * sizeof(PassDev));
+    for (const auto& ep : g.extra_passes) bytes += Align(ep.order_pool.size() * 2) + Align(ep.ac_code.size());
+    p.off_pass_table = take(bytes);
+  }
   p.const_bytes = o;
 
   // ---- work region
@@ -168,6 +175,23 @@ void FillConstRegion(const FramePlan& plan, const uint8_t* cs_padded, const Fram
     memcpy(dst + plan.off_sq_global, g.sq_global_data.data(), g.sq_global_data.size() * sizeof(int32_t));
   }
   if (!g.meta_data.empty()) memcpy(dst + plan.off_meta, g.meta_data.data(), g.meta_data.size() * sizeof(int32_t));
+  if (!g.extra_passes.empty()) {
+    uint8_t* base = dst + plan.off_pass_table;
+    PassDev* pd = reinterpret_cast<PassDev*>(base);
+    size_t rel = Align(g.extra_passes.size() * sizeof(PassDev));
+    for (size_t i = 0; i < g.extra_passes.size(); ++i) {
+      const auto& ep = g.extra_passes[i];
+      pd[i].orders = ep.orders;
+      pd[i].used_orders = ep.used_orders;
+      pd[i].shift = i + 1 < (size_t) fh.num_passes ? fh.pass_shift[i + 1] : 0;
+      pd[i].order_pool_rel = rel;
+      if (!ep.order_pool.empty()) memcpy(base + rel, ep.order_pool.data(), ep.order_pool.size() * 2);
+      rel += Align(ep.order_pool.size() * 2);
+      pd[i].ac_code_rel = rel;
+      memcpy(base + rel, ep.ac_code.data(), ep.ac_code.size());
+      rel += Align(ep.ac_code.size());
+    }
+  }
   uint32_t* bo = reinterpret_cast<uint32_t*>(dst + plan.off_blockinfo_off);
   size_t acc = 0;
   for (uint32_t l = 0; l < fh.num_lf_groups; ++l) {
@@ -220,6 +244,7 @@ FrameDev BindFrameDev(const FramePlan& p, const uint8_t* cb, uint8_t* wb) {
     f.sq_buf = reinterpret_cast<int32_t*>(wb + p.off_sq_buf);
   }
   f.meta = p.off_meta ? reinterpret_cast<const int32_t*>(cb + p.off_meta) : nullptr;
+  f.pass_table = p.off_pass_table ? reinterpret_cast<const PassDev*>(cb + p.off_pass_table) : nullptr;
   return f;
 }
 

@@ -29,10 +29,9 @@ struct HfGlobalOut {
 };
 
 // perm_scratch: 2 * 65536 uint32_t.
-JXLB_HD_NOINLINE int ParseHfGlobal(BitReader& br, uint32_t num_groups, uint32_t nb_block_ctx, const NaturalOrders& nat,
-                                   Arena& arena, uint32_t* perm_scratch, HfGlobalOut* out) {
-  if (!br.Read(1)) return kErrUnsupported;  // custom quant tables
-  out->num_hf_presets = br.Read(CeilLog2(num_groups)) + 1;
+// One pass of HfGlobal: the coefficient orders the pass uses and its AC code (out->num_hf_presets must be set).
+JXLB_HD_NOINLINE int ParseHfPass(BitReader& br, uint32_t nb_block_ctx, const NaturalOrders& nat, Arena& arena, uint32_t* perm_scratch,
+                                 HfGlobalOut* out) {
   uint32_t used = br.U32(0x5F, 0, 0x13, 0, 0, 0, 0, 13);
   out->used_orders = used;
   for (uint32_t o = 0; o < kNumOrders; ++o)
@@ -84,6 +83,15 @@ JXLB_HD_NOINLINE int ParseHfGlobal(BitReader& br, uint32_t num_groups, uint32_t 
   }
   uint32_t nctx = kContextsPerBlockCtx * nb_block_ctx * out->num_hf_presets;
   return ParseCode<false>(br, nctx, true, arena, &out->ac_code_off);
+}
+
+// HfGlobal of a single-pass frame (quant-table flag, preset count, the one pass).  Progressive frames call ParseHfPass
+// once more per further pass (frame_parser.cc).
+JXLB_HD_NOINLINE int ParseHfGlobal(BitReader& br, uint32_t num_groups, uint32_t nb_block_ctx, const NaturalOrders& nat,
+                                   Arena& arena, uint32_t* perm_scratch, HfGlobalOut* out) {
+  if (!br.Read(1)) return kErrUnsupported;  // custom quant tables
+  out->num_hf_presets = br.Read(CeilLog2(num_groups)) + 1;
+  return ParseHfPass(br, nb_block_ctx, nat, arena, perm_scratch, out);
 }
 
 // ---- helpers shared by the section decoders ---------------------------------------------------------------------------
@@ -379,8 +387,23 @@ JXLB_HD uint32_t BlockContext(const FrameDev& f, uint32_t order, uint32_t hf_mul
 // AC part of a PassGroup section (App. B.7).  Writes the non-zero quantised coefficients of group g into the frame's
 // coefficient planes (pre-zeroed), each block's coefficient array occupying the block's pixel rectangle, transposed
 // for tall blocks (DESIGN.md "coefficient planes").
-JXLB_HD_NOINLINE int DecodeAcGroup(BitReader& br_io, const FrameDev& f, uint32_t g, const NaturalOrders& nat, StreamScratch& s) {
+// pass: which progressive pass this section is (0 for ordinary frames); the tables of passes > 0 come from f.pass_table and
+// their coefficients, coded >> shift, are added to what the earlier passes left in the planes.
+JXLB_HD_NOINLINE int DecodeAcGroup(BitReader& br_io, const FrameDev& f, uint32_t g, const NaturalOrders& nat, StreamScratch& s,
+                                   uint32_t pass = 0) {
   BitReader br = br_io;  // register copy: the coefficient stores below must not force reloads of the reader state
+  const uint8_t* ac_code = f.ac_code;
+  const uint16_t* order_pool = f.order_pool;
+  const OrderTableIndex* orders = &f.orders;
+  uint32_t shift = f.pass_shift0;
+  if (pass > 0) {
+    const PassDev& pd = f.pass_table[pass - 1];
+    ac_code = reinterpret_cast<const uint8_t*>(f.pass_table) + pd.ac_code_rel;
+    order_pool = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(f.pass_table) + pd.order_pool_rel);
+    orders = &pd.orders;
+    shift = pd.shift;
+  }
+  const bool accumulate = f.num_passes > 1;
   const uint32_t gx = g % f.ngx, gy = g / f.ngx;
   const uint32_t bx0 = gx * kGroupCells, by0 = gy * kGroupCells;
   const uint32_t bw = f.w8 - bx0 < kGroupCells ? f.w8 - bx0 : kGroupCells;
@@ -390,7 +413,7 @@ JXLB_HD_NOINLINE int DecodeAcGroup(BitReader& br_io, const FrameDev& f, uint32_t
   if (hfp >= f.num_hf_presets) return kErrBadStream;
   const uint32_t ctx_off = hfp * kContextsPerBlockCtx * nbc;
   CodeView code;
-  code.Bind(f.ac_code);
+  code.Bind(ac_code);
   if (code.lz77 && s.lz77 == nullptr) return kErrUnsupported;
   SymbolReader sr;
   sr.Begin(code, br, s.lz77, s.lz77_mask);
@@ -441,8 +464,8 @@ JXLB_HD_NOINLINE int DecodeAcGroup(BitReader& br_io, const FrameDev& f, uint32_t
         for (uint32_t yy = 0; yy < cy; ++yy)
           for (uint32_t xx = 0; xx < cx; ++xx) nzm[(by + yy) * 32 + bx + xx] = nzv;
         if (nz == 0) continue;
-        const uint32_t ooff = f.orders.offset[ord][c];
-        const uint16_t* order = (ooff & kOrderInFramePool) ? f.order_pool + (ooff & ~kOrderInFramePool)
+        const uint32_t ooff = orders->offset[ord][c];
+        const uint16_t* order = (ooff & kOrderInFramePool) ? order_pool + (ooff & ~kOrderInFramePool)
                                                             : nat.pool + ooff;
         int16_t* plane = f.coef + (size_t) c * f.coef_h * f.coef_stride + (size_t) (by0 + by) * 8 * f.coef_stride + (bx0 + bx) * 8;
         const uint32_t h0 = ctx_off + nbc * kNonZeroBuckets + kZeroDensityContexts * bc;
@@ -462,6 +485,10 @@ JXLB_HD_NOINLINE int DecodeAcGroup(BitReader& br_io, const FrameDev& f, uint32_t
               uint32_t tmp = r;
               r = col;
               col = tmp;
+            }
+            if (accumulate) {
+              v = plane[(size_t) r * f.coef_stride + col] + v * (1 << shift);
+              if (v > 32767 || v < -32768) return kErrUnsupported;
             }
             plane[(size_t) r * f.coef_stride + col] = (int16_t) v;
           }

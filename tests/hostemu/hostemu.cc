@@ -125,12 +125,14 @@ void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, si
       if (e->status) e->failed_stream = (int) l;
     }
     for (uint32_t gi = 0; gi < f.num_groups && !e->status; ++gi) {
-      uint32_t sec = 1 + f.num_lf_groups + 1 + gi;
-      BitReader br;
-      br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);
-      s.arena.used = 0;
-      if (f.encoding == 0) e->status = DecodeAcGroup(br, f, gi, nat, s);
-      if (!e->status) e->status = DecodeModularGroup(br, f, gi, s, kMaxNodes);
+      for (uint32_t pass = 0; pass < f.num_passes && !e->status; ++pass) {
+        uint32_t sec = 1 + f.num_lf_groups + 1 + pass * f.num_groups + gi;
+        BitReader br;
+        br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);
+        s.arena.used = 0;
+        if (f.encoding == 0) e->status = DecodeAcGroup(br, f, gi, nat, s, pass);
+        if (!e->status) e->status = DecodeModularGroup(br, f, gi, s, kMaxNodes);
+      }
       if (e->status) e->failed_stream = (int) (f.num_lf_groups + gi);
     }
     if (!e->status && f.sq_nch) UnsqueezeAllSerial(f);
