@@ -93,8 +93,10 @@ JXLB_HD_NOINLINE int ReadModularHeader(BitReader& br, ModularHeader* h) {
       t.nb_colours = br.U32(0, 8, 256, 10, 1280, 12, 5376, 16);
       t.nb_deltas = br.U32(0, 0, 1, 8, 257, 10, 1281, 16);
       t.d_pred = br.Read(4);
-      // delta palettes (entries predicted from neighbouring output pixels: the encoder's opt-in lossy-palette mode)
-      if (t.nb_deltas != 0 || t.d_pred != 0) return kErrUnsupported;
+      // delta palettes (entries predicted from neighbouring output pixels: the encoder's opt-in lossy-palette mode).  A
+      // predictor alone (the lossless encoder writes one now and then) only matters for negative indices, which then
+      // fail the stream where they occur (InversePalettePixel).
+      if (t.nb_deltas != 0) return kErrUnsupported;
       if (t.num_c > (uint32_t) kMaxModPlanes) return kErrUnsupported;
     } else if (t.id == 2) {
       if (h->has_squeeze) return kErrUnsupported;  // one squeeze transform per header
@@ -539,20 +541,24 @@ JXLB_HD int32_t PaletteValue(const int32_t* pal, int32_t index, uint32_t c, uint
   return ImplicitPaletteValue(index, c, (int32_t) nb_colours, bit_depth);
 }
 
-// One pixel of the inverse palette: the index sits in the first output plane.
-JXLB_HD void InversePalettePixel(const ModTransform& tr, const int32_t* meta, uint32_t bit_depth, int32_t index, int32_t* out) {
+// One pixel of the inverse palette: the index sits in the first output plane.  False: a negative index (an implicit delta
+// colour) under a predictor, which would need the neighbouring output pixels -- not covered.
+JXLB_HD bool InversePalettePixel(const ModTransform& tr, const int32_t* meta, uint32_t bit_depth, int32_t index, int32_t* out) {
   const int32_t* pal = meta + tr.meta_off;
+  const bool ok = !(index < 0 && tr.d_pred != 0 && tr.num_c > 1);
   if (tr.num_c == 1) {  // single-channel palettes clamp the index instead of using implicit colours
     const int32_t hi = (int32_t) tr.nb_colours - 1;
     if (index > hi) index = hi;
     if (index < 0) index = hi < 0 ? -1 : 0;
   }
   for (uint32_t c = 0; c < tr.num_c; ++c) out[c] = PaletteValue(pal, index, c, tr.nb_colours, bit_depth);
+  return ok;
 }
 
 // Serial inverse of every transform of a stream header over whole planes (`planes`: the stream's output planes, all of one
 // size).  The per-pixel form for frame-level transforms of large images is StageGlobalInverse (pixel_stages.h).
-JXLB_HD void ApplyInverseTransforms(const ModularHeader& mh, const ModChannel* planes, const int32_t* meta, uint32_t bit_depth) {
+JXLB_HD int ApplyInverseTransforms(const ModularHeader& mh, const ModChannel* planes, const int32_t* meta, uint32_t bit_depth) {
+  bool ok = true;
   for (int t = (int) mh.nb_transforms - 1; t >= 0; --t) {
     const ModTransform& tr = mh.tr[t];
     if (tr.id == 0) {
@@ -578,12 +584,13 @@ JXLB_HD void ApplyInverseTransforms(const ModularHeader& mh, const ModChannel* p
       for (uint32_t y = 0; y < ic.h; ++y) {
         for (uint32_t x = 0; x < ic.w; ++x) {
           int32_t v[kMaxModPlanes];
-          InversePalettePixel(tr, meta, bit_depth, ic.data[(size_t) y * ic.stride + x], v);
+          ok &= InversePalettePixel(tr, meta, bit_depth, ic.data[(size_t) y * ic.stride + x], v);
           for (uint32_t c = 0; c < tr.num_c; ++c) planes[tr.pl[c]].data[(size_t) y * planes[tr.pl[c]].stride + x] = v[c];
         }
       }
     }
   }
+  return ok ? kOk : kErrUnsupported;
 }
 
 }  // namespace jxlb

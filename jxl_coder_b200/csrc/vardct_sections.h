@@ -215,8 +215,7 @@ JXLB_HD_NOINLINE int DecodeTransformedStream(BitReader& br, StreamScratch& s, Mo
   st = DecodeModularChannelsFast(br, mc, mh.wp, list, n, stream_id, wp, s.lz77, s.lz77_mask,
                                  s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
   if (st != kOk) return st;
-  ApplyInverseTransforms(mh, planes, meta, bit_depth);
-  return kOk;
+  return ApplyInverseTransforms(mh, planes, meta, bit_depth);
 }
 
 JXLB_HD void LfGroupRect(const FrameDev& f, uint32_t lfg, uint32_t* cx0, uint32_t* cy0, uint32_t* w8, uint32_t* h8,
