@@ -42,7 +42,11 @@ def build(verbose=False, force=False):
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(lambda s: _compile(s, hdr_time, verbose), SOURCES))
     if force or not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
-        cmd = ["nvcc", "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        # the C++ runtime is linked in and kept local (--exclude-libs): a host process may already hold another C++ runtime
+        # in its global symbol scope (the test oracle loads the reference's Android libc++ build that way), and this
+        # library's exceptions / operator new must not bind to it
+        cmd = ["nvcc", "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-static-libstdc++",
+                                                        "-Xcompiler", "-static-libgcc", "-Xlinker", "--exclude-libs,ALL"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
