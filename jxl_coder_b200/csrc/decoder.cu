@@ -516,9 +516,10 @@ void ParseRequest(const jxlb_request& r, int api, Parsed* p, int target_frame = 
     frame_bit = p->fh.end_byte * 8;
   }
   const FrameHeader& fh = p->fh;
-  p->fw = fh.coded_w;
-  p->fh_ = fh.coded_h;
-  const bool covers_canvas = !fh.have_crop && fh.coded_w == md.xsize && fh.coded_h == md.ysize;
+  // the picture a frame yields: its coded size, or the frame's size in image pixels when it is coded at half resolution
+  p->fw = fh.upsampling == 2 ? fh.width : fh.coded_w;
+  p->fh_ = fh.upsampling == 2 ? fh.height : fh.coded_h;
+  const bool covers_canvas = !fh.have_crop && p->fw == md.xsize && p->fh_ == md.ysize;
   if (!layer_only && (nframes > 1 || !covers_canvas)) {
     // Frames are decoded as independent pictures.  That is what a kReplace frame is when it covers the canvas, or when
     // the canvas it is laid over is empty (its source slots were never written): then the picture is the frame at its
@@ -883,7 +884,7 @@ struct Batch {
       Parsed& p = ps[i];
       if (p.status != JXLB_OK) continue;
       // an image whose planes alone could not be allocated fails by itself instead of failing the batch's allocation
-      if (p.plan.work_bytes + p.plan.const_bytes + 3 * p.plan.xyb_bytes > kMaxImageDeviceBytes) {
+      if (p.plan.work_bytes + p.plan.const_bytes + 3 * p.plan.xyb_bytes + p.plan.up_bytes > kMaxImageDeviceBytes) {
         Fail(&p, JXLB_OOM, "Not enough memory to decode this image");
         continue;
       }
@@ -894,7 +895,7 @@ struct Batch {
       p.stage_stride = Align256((size_t) p.fw * 4 * (p.out16 ? 2 : 1));
       p.stage_off = stage_total;
       // the fused VarDCT kernel packs straight into final_out; only modular frames (and the unfused debug path) stage RGBA
-      if (p.plan.proto.encoding != 0 || UseUnfusedFilters() || p.resize || p.color_matrix || p.orient != 1 || p.placed || p.layer_only || p.composed)
+      if (p.plan.proto.encoding != 0 || UseUnfusedFilters() || p.plan.up_bytes || p.resize || p.color_matrix || p.orient != 1 || p.placed || p.layer_only || p.composed)
         stage_total += Align256(p.stage_stride * p.fh_);
       if (p.composed) {
         p.canvas_bytes = Align256((size_t) p.md.xsize * p.md.ysize * 16);  // float RGBA reference slots; the picture fits in one too
@@ -928,7 +929,8 @@ struct Batch {
         p.rs_work_off = work_total;
         work_total += p.rs_mid_bytes + p.rs_scaled_bytes;
       }
-      xyb_slot_bytes = std::max(xyb_slot_bytes, Align256(p.plan.xyb_bytes * (UseUnfusedFilters() ? 2 : 1)));
+      // a ring slot: one plane set for the fused kernels; two for the unfused filters; + the upsampled planes of a half-resolution frame
+      xyb_slot_bytes = std::max(xyb_slot_bytes, Align256(p.plan.xyb_bytes * ((UseUnfusedFilters() || p.plan.up_bytes) ? 2 : 1) + p.plan.up_bytes));
       if (p.plan.proto.encoding == 0) ++n_vardct;
       final_bytes[i] = p.layer_only ? 0 : (size_t) p.out_w * FormatBytesPerPixel((uint32_t) p.format) * p.out_h;
       final_off[i] = final_total;
@@ -1082,7 +1084,7 @@ struct Batch {
       if (p.plan.xyb_bytes) {
         uint8_t* slot = buf->xyb_ring.p + (i % kXybRing) * xyb_slot_bytes;
         fd.xyb0 = reinterpret_cast<float*>(slot);
-        fd.xyb1 = UseUnfusedFilters() ? reinterpret_cast<float*>(slot + p.plan.xyb_bytes) : fd.xyb0;
+        fd.xyb1 = (UseUnfusedFilters() || p.plan.up_bytes) ? reinterpret_cast<float*>(slot + p.plan.xyb_bytes) : fd.xyb0;
       }
       frames[frame_of[i]] = fd;
     });
@@ -1229,7 +1231,19 @@ struct Batch {
         if (timed) CUDA_OK(cudaEventRecord(sev[3 * sampled], s));
         LaunchRecon(f, ctx->nt_dev, s);
         if (timed) CUDA_OK(cudaEventRecord(sev[3 * sampled + 1], s));
-        if (!UseUnfusedFilters()) {
+        if (f.upsampling == 2) {
+          // half-resolution frame: separate filter kernels, 2x upsampling of the XYB planes, colour + pack at full size
+          const int cur = LaunchFilters(f, ctx->nt_dev, s);
+          float* up = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(f.xyb0) + 2 * p.plan.xyb_bytes);
+          LaunchUpsample2(f, cur ? f.xyb1 : f.xyb0, up, f.up_stride, f.up_h, s);
+          FrameDev fu = f;
+          fu.width = f.up_width;
+          fu.height = f.up_height;
+          fu.plane_stride = f.up_stride;
+          fu.plane_h = f.up_h;
+          LaunchColor(fu, p.cp, ctx->nt_dev, up, od, s);
+          LaunchPack(pk, s);
+        } else if (!UseUnfusedFilters()) {
           LaunchFilterColorPack(f, p.cp, ctx->nt_dev, od, pk, s);
         } else {
           int cur = LaunchFilters(f, ctx->nt_dev, s);

@@ -178,6 +178,8 @@ struct FrameDev {
   float* xyb0;                     // [3][plane_h][plane_stride]
   float* xyb1;
   uint32_t plane_stride, plane_h;
+  // frames coded at half resolution (upsampling 2): size of the frame in image pixels and of the upsampled XYB planes
+  uint32_t upsampling, up_width, up_height, up_stride, up_h;
   int32_t* frame_bad;              // [1] set by FrameStatusKernel when any entropy-coded section of the frame failed: the
                                    // reconstruction kernels then skip the frame (its metadata planes are garbage)
   int32_t* mod;                    // [num_mod_channels][height][mod_stride]

@@ -524,7 +524,10 @@ void NaturalCoeffOrder(uint32_t cx, uint32_t cy, std::vector<uint32_t>* out) {
 int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& md, const FrameHeader& fh, FrameGlobals* g,
                       std::string* err) {
   if (fh.flags & ~(uint64_t) 0x80) JXLB_FAIL(kParseUnsupported, "noise / patches / splines / LF-frame flags");
-  if (fh.upsampling != 1) JXLB_FAIL(kParseUnsupported, "upsampled frame");
+  // frames coded at half resolution (libjxl's encoder: distances of about 10 and more) are upsampled 2x with the default
+  // kernel (pixel_stages.h: StageUpsample2); 4x / 8x, custom kernels and upsampled extra / modular channels are refused
+  if (fh.upsampling != 1 && (fh.upsampling != 2 || fh.encoding != 0 || !md.extra.empty() || md.custom_upsampling || fh.have_crop))
+    JXLB_FAIL(kParseUnsupported, "upsampled frame");
   for (uint32_t u : fh.ec_upsampling)
     if (u != 1) JXLB_FAIL(kParseUnsupported, "upsampled extra channel");
   // progressive passes: the AC coefficients of a group arrive in num_passes sections that add up; the modular channels of

@@ -319,6 +319,13 @@ __global__ void __launch_bounds__(256) ColorKernel(const FrameDev f, const Color
   StageColorToRgba(f, cp, *nt, src, out, x, y);
 }
 
+__global__ void __launch_bounds__(256) Upsample2Kernel(const FrameDev f, const float* src, float* dst, uint32_t up_stride, uint32_t up_h) {
+  if (*f.frame_bad) return;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= (int) f.width || y >= (int) f.height) return;
+  StageUpsample2(f, src, dst, up_stride, up_h, x, y);
+}
+
 __global__ void __launch_bounds__(256) ModularToRgbaKernel(const FrameDev f, OutputDesc out) {
   if (*f.frame_bad) return;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -468,6 +475,11 @@ int LaunchFilters(const FrameDev& f, const NumericTables* nt_dev, cudaStream_t s
 void LaunchColor(const FrameDev& f, const ColorParams& cp, const NumericTables* nt_dev, const float* src, OutputDesc out,
                  cudaStream_t stream) {
   ColorKernel<<<PixelGrid(f.width, f.height, 256), 256, 0, stream>>>(f, cp, nt_dev, src, out);
+  ++g_launches;
+}
+
+void LaunchUpsample2(const FrameDev& f, const float* src, float* dst, uint32_t up_stride, uint32_t up_h, cudaStream_t stream) {
+  Upsample2Kernel<<<PixelGrid(f.width, f.height, 256), 256, 0, stream>>>(f, src, dst, up_stride, up_h);
   ++g_launches;
 }
 

@@ -124,6 +124,8 @@ void LaunchColor(const FrameDev& f, const ColorParams& cp, const NumericTables* 
                  cudaStream_t stream);
 void LaunchModularToRgba(const FrameDev& f, OutputDesc out, cudaStream_t stream);
 void LaunchModularGlobalInverse(const FrameDev& f, cudaStream_t stream);
+// 2x upsampling of the filtered XYB planes of a frame coded at half resolution: src (f geometry) -> dst [3][up_h][up_stride]
+void LaunchUpsample2(const FrameDev& f, const float* src, float* dst, uint32_t up_stride, uint32_t up_h, cudaStream_t stream);
 // Fused Gaborish + EPF + colour + pack (kernels_filter.cu): XYB planes in f.xyb0 -> packed pixels.
 void LaunchFilterColorPack(const FrameDev& f, const ColorParams& cp, const NumericTables* nt_dev, const OutputDesc& od,
                            const PackParams& pack, cudaStream_t stream);

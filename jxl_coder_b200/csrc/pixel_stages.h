@@ -108,6 +108,48 @@ JXLB_HD void StageColorToRgba(const FrameDev& f, const ColorParams& cp, const Nu
   StoreRgba(out, x, y, v[0], v[1], v[2], AlphaAt(f, out, x, y));
 }
 
+// 2x upsampling of a frame coded at half resolution (what libjxl's encoder does at distances of about 10 and more): every
+// coded XYB sample (x, y) becomes the 2 x 2 output samples (2x + ox, 2y + oy), each a 5 x 5 weighting of the coded
+// neighbourhood (borders mirrored) with the default kernel of the format -- a symmetric matrix given by 15 weights,
+// mirrored for ox / oy = 1 -- clamped to the range of that neighbourhood.  Unfused multiply / add in row-major order, as
+// the reference's SSE2 build accumulates.  src: coded planes (f geometry); dst: [3][up_h][up_stride].
+JXLB_HD void StageUpsample2(const FrameDev& f, const float* src, float* dst, uint32_t up_stride, uint32_t up_h, int x, int y) {
+  const float kW[15] = {-0.01716200f, -0.03452303f, -0.04022174f, -0.02921014f, -0.00624645f, 0.14111091f, 0.28896755f, 0.00278718f,
+                        -0.01610267f, 0.56661550f, 0.03777607f, -0.01986694f, -0.03144731f, -0.01185068f, -0.00213539f};
+  const size_t plane = (size_t) f.plane_h * f.plane_stride, uplane = (size_t) up_h * up_stride;
+  int xs[5], ys[5];
+  for (int k = 0; k < 5; ++k) {
+    xs[k] = Mirror(x + k - 2, (int) f.width);
+    ys[k] = Mirror(y + k - 2, (int) f.height);
+  }
+  for (int c = 0; c < 3; ++c) {
+    float v[5][5];
+    float mn = 0.0f, mx = 0.0f;
+    for (int iy = 0; iy < 5; ++iy)
+      for (int ix = 0; ix < 5; ++ix) {
+        const float t = src[c * plane + (size_t) ys[iy] * f.plane_stride + xs[ix]];
+        v[iy][ix] = t;
+        if (iy == 0 && ix == 0) mn = mx = t;
+        else {
+          mn = t < mn ? t : mn;
+          mx = t > mx ? t : mx;
+        }
+      }
+    for (int oy = 0; oy < 2; ++oy)
+      for (int ox = 0; ox < 2; ++ox) {
+        float acc = 0.0f;
+        for (int iy = 0; iy < 5; ++iy)
+          for (int ix = 0; ix < 5; ++ix) {
+            const int ky = oy ? 4 - iy : iy, kx = ox ? 4 - ix : ix;
+            const int a = ky < kx ? ky : kx, b = ky < kx ? kx : ky;
+            acc = AddRn(MulRn(kW[5 * a - a * (a - 1) / 2 + b - a], v[iy][ix]), acc);
+          }
+        acc = acc < mn ? mn : acc > mx ? mx : acc;
+        dst[c * uplane + (size_t) (2 * y + oy) * up_stride + 2 * x + ox] = acc;
+      }
+  }
+}
+
 // Modular (non-XYB) frames: integer samples straight to the output depth.
 JXLB_HD void StageModularToRgba(const FrameDev& f, const OutputDesc& out, int x, int y) {
   const uint32_t maxout = out.bits16 ? 65535u : 255u;

@@ -43,6 +43,9 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
   f.encoding = fh.encoding;
   f.flags = (uint32_t) fh.flags;
   f.single_section = fh.toc_entries == 1;
+  f.upsampling = fh.upsampling;
+  f.up_width = fh.width;
+  f.up_height = fh.height;
   f.x_qm_scale = fh.x_qm_scale;
   f.b_qm_scale = fh.b_qm_scale;
   f.cs_bytes = cs_padded_bytes;
@@ -150,6 +153,11 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
     p.off_lf = take((size_t) 3 * f.h8 * f.lf_stride * 4);
     p.off_large_list = take(((size_t) f.h8 * f.w8 / 2 + 2) * 4);  // [0] = count, then one entry per block outside the region kernel
     p.xyb_bytes = (size_t) 3 * f.plane_h * f.plane_stride * 4;
+    if (fh.upsampling == 2) {
+      f.up_stride = RoundUp(2 * f.width, 64);
+      f.up_h = 2 * f.height;
+      p.up_bytes = (size_t) 3 * f.up_h * f.up_stride * 4;
+    }
   }
   if (f.num_mod_channels) p.off_mod = take((size_t) f.num_mod_channels * f.height * f.mod_stride * 4);
   if (g.squeeze) p.off_sq_buf = take(g.sq.buffer_ints * sizeof(int32_t));

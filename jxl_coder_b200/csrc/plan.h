@@ -19,6 +19,7 @@ struct FramePlan {
          off_extra_prec = 0, off_cell_strategy = 0, off_cell_hfmul = 0, off_cell_sharp = 0, off_cell_off = 0, off_group_blocks = 0, off_group_nblocks = 0, off_group_ac_end = 0, off_coef = 0, off_lf = 0, off_large_list = 0,
          off_xyb0 = 0, off_xyb1 = 0, off_mod = 0, off_status = 0, off_sq_buf = 0, off_frame_bad = 0;
   size_t coef_bytes = 0;   // zero-filled before the AC decode
+  size_t up_bytes = 0;     // upsampled XYB planes of a frame coded at half resolution (same ring slot, after two plane sets)
   size_t xyb_bytes = 0;    // one XYB f32 plane set [3][plane_h][plane_stride]; NOT part of the work region: the decoder
                            // binds FrameDev::xyb0 (and xyb1 for the unfused debug path) to a small ring of such buffers
   uint32_t num_streams = 0;  // status entries: [lf groups][groups] (+1 for the single-section chain)

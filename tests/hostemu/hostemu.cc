@@ -149,13 +149,15 @@ int emu_status(void* h) { return static_cast<Emu*>(h)->status; }
 int emu_failed_stream(void* h) { return static_cast<Emu*>(h)->failed_stream; }
 
 // out[]: width, height, w8, h8, lf_stride, coef_stride, coef_h, num_groups, num_lf_groups, encoding, num_mod_channels,
-//        mod_stride, w64, h64, single_section, global_nb_transforms, xsize, ysize, bits, num_extra, is_last, orientation
+//        mod_stride, w64, h64, single_section, global_nb_transforms, xsize, ysize, bits, num_extra, is_last, orientation,
+//        upsampling, up_width, up_height
 void emu_info(void* h, uint32_t* out) {
   Emu* e = static_cast<Emu*>(h);
   const FrameDev& f = e->f;
   uint32_t v[] = {f.width, f.height, f.w8, f.h8, f.lf_stride, f.coef_stride, f.coef_h, f.num_groups, f.num_lf_groups, f.encoding,
                   f.num_mod_channels, f.mod_stride, f.w64, f.h64, f.single_section, f.global_nb_transforms, e->md.xsize, e->md.ysize,
-                  e->md.bits_per_sample, (uint32_t) e->md.extra.size(), (uint32_t) e->fh.is_last, e->md.orientation};
+                  e->md.bits_per_sample, (uint32_t) e->md.extra.size(), (uint32_t) e->fh.is_last, e->md.orientation,
+                  f.upsampling, f.up_width, f.up_height};
   memcpy(out, v, sizeof v);
 }
 const int32_t* emu_lf_quant(void* h) { return static_cast<Emu*>(h)->f.lf_quant; }
@@ -223,6 +225,19 @@ int emu_render(void* h, uint8_t* out, uint32_t stride_bytes, int bits16, float* 
     if (f.rf.epf_iters >= 1) run([&](int x, int y) { StageEpf(f, nt, 1, src, dst, x, y); });
     if (f.rf.epf_iters >= 2) run([&](int x, int y) { StageEpf(f, nt, 2, src, dst, x, y); });
     if (xyb_final) memcpy(xyb_final, src, 3 * plane * sizeof(float));
+    if (f.upsampling == 2) {
+      std::vector<float> up((size_t) 3 * f.up_h * f.up_stride);
+      for (uint32_t y = 0; y < f.height; ++y)
+        for (uint32_t x = 0; x < f.width; ++x) StageUpsample2(f, src, up.data(), f.up_stride, f.up_h, (int) x, (int) y);
+      FrameDev fu = f;
+      fu.width = f.up_width;
+      fu.height = f.up_height;
+      fu.plane_stride = f.up_stride;
+      fu.plane_h = f.up_h;
+      for (uint32_t y = 0; y < fu.height; ++y)
+        for (uint32_t x = 0; x < fu.width; ++x) StageColorToRgba(fu, cp, nt, up.data(), od, (int) x, (int) y);
+      return 0;
+    }
     for (uint32_t y = 0; y < f.height; ++y)
       for (uint32_t x = 0; x < f.width; ++x) StageColorToRgba(f, cp, nt, src, od, (int) x, (int) y);
   } else {

@@ -55,7 +55,7 @@ def lib():
 
 INFO = ["width", "height", "w8", "h8", "lf_stride", "coef_stride", "coef_h", "num_groups", "num_lf_groups", "encoding",
         "num_mod_channels", "mod_stride", "w64", "h64", "single_section", "global_nb_transforms", "xsize", "ysize", "bits",
-        "num_extra", "is_last", "orientation"]
+        "num_extra", "is_last", "orientation", "upsampling", "up_width", "up_height"]
 
 
 class Decoded:
@@ -104,7 +104,8 @@ class Decoded:
         i = self.info
         L = lib()
         dt = np.uint16 if bits16 else np.uint8
-        out = np.zeros((i["height"], i["width"], 4), dt)
+        ow, oh = (i["up_width"], i["up_height"]) if i["upsampling"] == 2 else (i["width"], i["height"])
+        out = np.zeros((oh, ow, 4), dt)
         ps, ph = L.emu_plane_stride(self.h), L.emu_plane_h(self.h)
         a = np.zeros((3, ph, ps), np.float32) if want_planes else None
         b = np.zeros((3, ph, ps), np.float32) if want_planes else None

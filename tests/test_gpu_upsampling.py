@@ -1,0 +1,41 @@
+"""GPU parity on frames coded at half resolution (tests/upsampling_cases.py) through the C ABI: one batch, then one of
+them through decodeSampled (rescale + 1010102) and with an orientation."""
+import numpy as np
+import pytest
+
+import golden_lib
+import upsampling_cases as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def J():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import jxl_coder_b200 as J
+    J.load_library()
+    return J
+
+
+def test_upsampled_files_match_reference(J, ref):
+    datas = [U.make(ref, *g) for g in U.GRID]
+    outs = J.decode_batch(datas, config=2)
+    for g, d, o in zip(U.GRID, datas, outs):
+        want = ref.decode_sampled(d, cfg=2)["pixels"]
+        assert o.pixels.shape == want.shape, g
+        golden_lib.lossy_close(o.pixels, want, U.name(*g))
+
+
+def test_upsampled_file_through_decode_sampled(J, ref):
+    d = U.make(ref, 600, 400, 12.0, -1, 7)
+    want = ref.decode_sampled(d, w=300, h=200, cfg=2, scale_mode=1, filt=1)
+    got = J.JxlCoder.decode_sampled(d, 300, 200, 2, 1, 1)
+    assert (got.width, got.height) == (want["width"], want["height"])
+    dd = np.abs(got.pixels.astype(int) - want["pixels"].astype(int))
+    assert dd.max() <= 1
+    want = ref.decode_sampled(d, cfg=3)  # RGBA_F16
+    got = J.JxlCoder.decode(d, 3)
+    fa = got.pixels.view(np.float16).astype(np.float32)
+    fb = want["pixels"].view(np.float16).astype(np.float32)
+    assert np.abs(fa - fb).max() <= 1.01 / 255
