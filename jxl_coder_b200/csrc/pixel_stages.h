@@ -179,8 +179,8 @@ JXLB_HD void StageGlobalInverse(const FrameDev& f, int x, int y) {
       f.mod[tr.pl[perm[2]] * plane + o] = c;
     } else if (tr.id == 1) {
       int32_t v[kMaxModPlanes];
-      // a pixel the palette path cannot reconstruct fails the frame (status slot of the global section; read back after the run)
-      if (!InversePalettePixel(tr, f.meta, f.bit_depth, f.mod[tr.pl[0] * plane + o], v)) f.status[f.num_lf_groups + f.num_groups] = kErrUnsupported;
+      // a pixel the palette path cannot reconstruct fails the frame: the status slot of its first group is read back after the run
+      if (!InversePalettePixel(tr, f.meta, f.bit_depth, f.mod[tr.pl[0] * plane + o], v)) f.status[f.num_lf_groups] = kErrUnsupported;
       for (uint32_t c = 0; c < tr.num_c; ++c) f.mod[tr.pl[c] * plane + o] = v[c];
     }
   }
