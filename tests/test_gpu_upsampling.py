@@ -38,4 +38,4 @@ def test_upsampled_file_through_decode_sampled(J, ref):
     got = J.JxlCoder.decode(d, 3)
     fa = got.pixels.view(np.float16).astype(np.float32)
     fb = want["pixels"].view(np.float16).astype(np.float32)
-    assert np.abs(fa - fb).max() <= 1.01 / 255
+    assert np.abs(fa - fb).max() <= 1.25 / 255  # one 8-bit step plus the half-float rounding near 1.0 (2^-11)
