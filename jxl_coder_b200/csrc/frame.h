@@ -141,6 +141,7 @@ struct FrameDev {
   OrderTableIndex orders;
   const PassDev* pass_table;       // progressive frames: tables of passes 1 ..; pass 0 uses the fields above
   uint32_t pass_shift0, pass_pad;  // coefficients of pass 0 are coded >> pass_shift0
+  uint8_t pass_min_shift[12], pass_max_shift[12];  // modular channels a pass carries: min_shift <= min(hshift, vshift) <= max_shift
   RestorationFilter rf;
   // extra channels / modular image
   uint32_t num_mod_channels;       // channels of the frame's modular image (colour for modular frames + extras)

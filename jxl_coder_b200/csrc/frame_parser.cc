@@ -336,8 +336,9 @@ int ParseFrameHeader(const uint8_t* cs, size_t cs_padded, size_t cs_len, const I
       if (fh->num_passes != 1) {
         uint32_t nds = br.U32(0, 0, 1, 0, 2, 0, 3, 1);
         for (uint32_t i = 0; i + 1 < fh->num_passes; ++i) fh->pass_shift[i] = br.Read(2);
-        for (uint32_t i = 0; i < nds; ++i) br.U32(1, 0, 2, 0, 4, 0, 8, 0);
-        for (uint32_t i = 0; i < nds; ++i) br.U32(0, 0, 1, 0, 2, 0, 0, 3);
+        fh->num_ds = nds;
+        for (uint32_t i = 0; i < nds; ++i) fh->pass_downsample[i] = br.U32(1, 0, 2, 0, 4, 0, 8, 0);
+        for (uint32_t i = 0; i < nds; ++i) fh->pass_last[i] = br.U32(0, 0, 1, 0, 2, 0, 0, 3);
       }
     }
     if (fh->frame_type == 1) {
@@ -530,9 +531,9 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
     JXLB_FAIL(kParseUnsupported, "upsampled frame");
   for (uint32_t u : fh.ec_upsampling)
     if (u != 1) JXLB_FAIL(kParseUnsupported, "upsampled extra channel");
-  // progressive passes: the AC coefficients of a group arrive in num_passes sections that add up; the modular channels of
-  // such frames (extra channels split over the passes by their shifts) are not handled
-  if (fh.num_passes != 1 && (fh.encoding != 0 || !md.extra.empty())) JXLB_FAIL(kParseUnsupported, "progressive passes with modular channels");
+  // progressive passes: the AC coefficients of a group arrive in num_passes sections that add up; its extra channels are
+  // split over the passes by their shifts (FrameDev::pass_min_shift / pass_max_shift)
+  if (fh.num_passes != 1 && fh.encoding != 0) JXLB_FAIL(kParseUnsupported, "progressive passes of a modular frame");
   if (fh.frame_type != 0) JXLB_FAIL(kParseUnsupported, "non-regular frame type");
   if (fh.do_ycbcr) JXLB_FAIL(kParseUnsupported, "YCbCr frame");
   BitReader br;

@@ -87,6 +87,7 @@ struct FrameHeader {
   uint32_t x_qm_scale = 3, b_qm_scale = 2;
   uint32_t num_passes = 1;
   uint32_t pass_shift[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // coefficients of pass p are coded >> pass_shift[p] (0 for the last)
+  uint32_t num_ds = 0, pass_downsample[4] = {1, 1, 1, 1}, pass_last[4] = {0, 0, 0, 0};  // resolution a pass completes (modular shifts)
   uint32_t lf_level = 0;
   bool have_crop = false;
   int32_t x0 = 0, y0 = 0;

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kStreamBlockThreads) PassGroupKernel(const Fra
       const uint32_t lfg = (job.index / f.ngx / 8) * f.nlfx + (job.index % f.ngx) / 8;
       st = f.status[lfg] == kOk ? DecodeAcGroup(br, f, job.index, nat, sc, pass) : (int) kErrBadStream;
     }
-    if (st == kOk) st = DecodeModularGroup(br, f, job.index, sc, scratch.max_local_nodes);
+    if (st == kOk) st = DecodeModularGroup(br, f, job.index, sc, scratch.max_local_nodes, pass);
   }
   f.status[job.status_slot] = st;
 }

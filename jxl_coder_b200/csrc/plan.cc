@@ -105,6 +105,20 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
   }
   if (!g.meta_data.empty()) p.off_meta = take(g.meta_data.size() * sizeof(int32_t));
   f.pass_shift0 = fh.num_passes > 1 ? fh.pass_shift[0] : 0;
+  {
+    // which modular channels each pass carries (ISO/IEC 18181-1 passes: the downsampling a pass completes); a single pass
+    // carries shifts 0 .. 2, the LF groups everything from 3 up
+    int max_shift = 2, min_shift = 3;
+    for (uint32_t ps = 0; ps < fh.num_passes && ps < 12; ++ps) {
+      for (uint32_t j = 0; j < fh.num_ds && j < 4; ++j)
+        if (fh.pass_last[j] == ps) min_shift = fh.pass_downsample[j] == 8 ? 3 : fh.pass_downsample[j] == 4 ? 2 : fh.pass_downsample[j] == 2 ? 1 : 0;
+      if (ps + 1 == fh.num_passes) min_shift = 0;
+      f.pass_min_shift[ps] = (uint8_t) min_shift;
+      f.pass_max_shift[ps] = (uint8_t) (max_shift < 0 ? 0 : max_shift);
+      if (max_shift < min_shift) f.pass_min_shift[ps] = 255;  // empty bracket: the pass carries no modular channel
+      max_shift = min_shift - 1;
+    }
+  }
   if (!g.extra_passes.empty()) {
     // [PassDev x (num_passes - 1)] then, per pass, its order pool and its code blob (offsets relative to the table)
     size_t bytes = Align(g.extra_passes.size() * sizeof(PassDev));

@@ -504,7 +504,10 @@ JXLB_HD_NOINLINE int DecodeAcGroup(BitReader& br_io, const FrameDev& f, uint32_t
 
 // Per-group modular data of group g (the tail of a PassGroup section, or the whole section of a modular frame):
 // all channels of the frame's modular image that were not decoded globally, restricted to the group's rectangle.
-JXLB_HD_NOINLINE int DecodeModularGroup(BitReader& br, const FrameDev& f, uint32_t g, StreamScratch& s, uint32_t max_local_nodes) {
+JXLB_HD_NOINLINE int DecodeModularGroup(BitReader& br, const FrameDev& f, uint32_t g, StreamScratch& s, uint32_t max_local_nodes,
+                                        uint32_t pass = 0) {
+  const uint32_t min_shift = f.pass_min_shift[pass], max_shift = f.pass_max_shift[pass];
+  if (min_shift == 255) return kOk;  // this pass carries no modular channel
   const uint32_t gd = f.group_dim;
   const uint32_t gx = g % f.ngx, gy = g / f.ngx;
   const uint32_t x0 = gx * gd, y0 = gy * gd;
@@ -512,12 +515,13 @@ JXLB_HD_NOINLINE int DecodeModularGroup(BitReader& br, const FrameDev& f, uint32
   uint32_t nch = 0;
   if (f.sq_nch) {
     // squeezed extra channels (squeeze.h); a group that no channel reaches codes nothing, not even a header
-    const int cst = CollectSqueezeChannels(f, x0, y0, gd, 0, 2, ch, &nch);
+    const int cst = CollectSqueezeChannels(f, x0, y0, gd, min_shift, max_shift, ch, &nch);
     if (cst != kOk) return cst;
     if (!nch) return kOk;
   } else {
     // the coded channels left once the frame-level palettes are applied (all of them, without palettes)
     if (f.global_mod_decoded >= f.num_mod_channels) return kOk;
+    if (min_shift > 0) return kOk;  // full-resolution channels arrive with the pass that reaches shift 0
     nch = f.num_coded;
     if (nch > 8) return kErrUnsupported;
     const uint32_t w = f.width - x0 < gd ? f.width - x0 : gd;
@@ -534,7 +538,7 @@ JXLB_HD_NOINLINE int DecodeModularGroup(BitReader& br, const FrameDev& f, uint32
   uint32_t arena_mark = s.arena.used;
   int st = BeginModularStream(br, f, s, max_local_nodes, &mh, &mc, /*allow_palette=*/!f.sq_nch);
   if (st != kOk) return st;
-  const uint32_t stream_id = 1 + 3 * f.num_lf_groups + 17 + g;
+  const uint32_t stream_id = 1 + 3 * f.num_lf_groups + 17 + f.num_groups * pass + g;
   if (f.sq_nch) {
     if (mh.nb_transforms) return kErrUnsupported;
     st = DecodeModularChannelsFast(br, mc, mh.wp, ch, nch, stream_id, s.wp, s.lz77, s.lz77_mask,

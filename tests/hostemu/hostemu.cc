@@ -131,7 +131,7 @@ void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, si
         br.Init(f.cs, f.cs_bytes, f.sec_bit_begin[sec], f.sec_bit_end[sec]);
         s.arena.used = 0;
         if (f.encoding == 0) e->status = DecodeAcGroup(br, f, gi, nat, s, pass);
-        if (!e->status) e->status = DecodeModularGroup(br, f, gi, s, kMaxNodes);
+        if (!e->status) e->status = DecodeModularGroup(br, f, gi, s, kMaxNodes, pass);
       }
       if (e->status) e->failed_stream = (int) (f.num_lf_groups + gi);
     }
