@@ -1241,7 +1241,16 @@ struct Batch {
           fu.height = f.up_height;
           fu.plane_stride = f.up_stride;
           fu.plane_h = f.up_h;
-          LaunchColor(fu, p.cp, ctx->nt_dev, up, od, s);
+          OutputDesc odu = od;
+          if (od.alpha_channel >= 0) {  // the alpha plane is coded at half resolution too
+            int32_t* up_alpha = reinterpret_cast<int32_t*>(up + (size_t) 3 * f.up_h * f.up_stride);
+            LaunchUpsampleAlpha2(f, f.mod + (size_t) od.alpha_channel * f.height * f.mod_stride, od.alpha_bits, up_alpha, f.up_stride, s);
+            fu.mod = up_alpha;
+            fu.mod_stride = f.up_stride;
+            odu.alpha_channel = 0;
+            odu.alpha_float = 1;
+          }
+          LaunchColor(fu, p.cp, ctx->nt_dev, up, odu, s);
           LaunchPack(pk, s);
         } else if (!UseUnfusedFilters()) {
           LaunchFilterColorPack(f, p.cp, ctx->nt_dev, od, pk, s);

@@ -527,10 +527,11 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
   if (fh.flags & ~(uint64_t) 0x80) JXLB_FAIL(kParseUnsupported, "noise / patches / splines / LF-frame flags");
   // frames coded at half resolution (libjxl's encoder: distances of about 10 and more) are upsampled 2x with the default
   // kernel (pixel_stages.h: StageUpsample2); 4x / 8x, custom kernels and upsampled extra / modular channels are refused
-  if (fh.upsampling != 1 && (fh.upsampling != 2 || fh.encoding != 0 || !md.extra.empty() || md.custom_upsampling || fh.have_crop))
+  if (fh.upsampling != 1 && (fh.upsampling != 2 || fh.encoding != 0 || md.custom_upsampling || fh.have_crop))
     JXLB_FAIL(kParseUnsupported, "upsampled frame");
+  // extra channels: at the frame's own resolution (full, or half together with the colour planes)
   for (uint32_t u : fh.ec_upsampling)
-    if (u != 1) JXLB_FAIL(kParseUnsupported, "upsampled extra channel");
+    if (u != fh.upsampling) JXLB_FAIL(kParseUnsupported, "upsampled extra channel");
   // progressive passes: the AC coefficients of a group arrive in num_passes sections that add up; its extra channels are
   // split over the passes by their shifts (FrameDev::pass_min_shift / pass_max_shift)
   if (fh.num_passes != 1 && fh.encoding != 0) JXLB_FAIL(kParseUnsupported, "progressive passes of a modular frame");

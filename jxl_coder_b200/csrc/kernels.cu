@@ -326,6 +326,14 @@ __global__ void __launch_bounds__(256) Upsample2Kernel(const FrameDev f, const f
   StageUpsample2(f, src, dst, up_stride, up_h, x, y);
 }
 
+__global__ void __launch_bounds__(256) UpsampleAlpha2Kernel(const FrameDev f, const int32_t* src, uint32_t bits, int32_t* dst,
+                                                             uint32_t up_stride) {
+  if (*f.frame_bad) return;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= (int) f.width || y >= (int) f.height) return;
+  StageUpsampleAlpha2(f, src, bits, dst, up_stride, x, y);
+}
+
 __global__ void __launch_bounds__(256) ModularToRgbaKernel(const FrameDev f, OutputDesc out) {
   if (*f.frame_bad) return;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -480,6 +488,12 @@ void LaunchColor(const FrameDev& f, const ColorParams& cp, const NumericTables* 
 
 void LaunchUpsample2(const FrameDev& f, const float* src, float* dst, uint32_t up_stride, uint32_t up_h, cudaStream_t stream) {
   Upsample2Kernel<<<PixelGrid(f.width, f.height, 256), 256, 0, stream>>>(f, src, dst, up_stride, up_h);
+  ++g_launches;
+}
+
+void LaunchUpsampleAlpha2(const FrameDev& f, const int32_t* src, uint32_t bits, int32_t* dst, uint32_t up_stride,
+                          cudaStream_t stream) {
+  UpsampleAlpha2Kernel<<<PixelGrid(f.width, f.height, 256), 256, 0, stream>>>(f, src, bits, dst, up_stride);
   ++g_launches;
 }
 

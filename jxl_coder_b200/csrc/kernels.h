@@ -126,6 +126,9 @@ void LaunchModularToRgba(const FrameDev& f, OutputDesc out, cudaStream_t stream)
 void LaunchModularGlobalInverse(const FrameDev& f, cudaStream_t stream);
 // 2x upsampling of the filtered XYB planes of a frame coded at half resolution: src (f geometry) -> dst [3][up_h][up_stride]
 void LaunchUpsample2(const FrameDev& f, const float* src, float* dst, uint32_t up_stride, uint32_t up_h, cudaStream_t stream);
+// ... and of its alpha plane (coded int32 samples of `bits` bits -> floats in [0, 1], [up_h][up_stride]; OutputDesc::alpha_float)
+void LaunchUpsampleAlpha2(const FrameDev& f, const int32_t* src, uint32_t bits, int32_t* dst, uint32_t up_stride,
+                          cudaStream_t stream);
 // Fused Gaborish + EPF + colour + pack (kernels_filter.cu): XYB planes in f.xyb0 -> packed pixels.
 void LaunchFilterColorPack(const FrameDev& f, const ColorParams& cp, const NumericTables* nt_dev, const OutputDesc& od,
                            const PackParams& pack, cudaStream_t stream);

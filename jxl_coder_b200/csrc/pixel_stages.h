@@ -14,6 +14,7 @@ struct OutputDesc {
   int32_t alpha_channel;   // index into the frame's modular image, or -1
   uint32_t alpha_bits;     // bit depth of the alpha samples
   uint32_t color_bits;     // bit depth of modular colour samples (modular frames)
+  uint32_t alpha_float = 0;  // the alpha plane holds floats in [0, 1] (an upsampled alpha): quantised -- and, at 8 bits, dithered -- like colour
 };
 
 JXLB_HD Planes3 ViewPlanes(const FrameDev& f, const float* base) {
@@ -94,18 +95,26 @@ JXLB_HD void StageColorToRgba(const FrameDev& f, const ColorParams& cp, const Nu
   float rgb[3];
   XybToEncodedRgb(src[o], src[plane + o], src[2 * plane + o], cp, rgb);
   uint32_t v[3];
+  // an upsampled alpha is a float in [0, 1] that goes through the same output conversion as colour
+  const float af = out.alpha_float ? reinterpret_cast<const float*>(f.mod)[(size_t) y * f.mod_stride + x] : 0.0f;
+  uint32_t alpha;
   if (out.bits16) {
     for (int c = 0; c < 3; ++c) {
       float s = rgb[c] * 65535.0f;
       s = s < 0.0f ? 0.0f : s > 65535.0f ? 65535.0f : s;
       v[c] = (uint32_t) rintf(s);
     }
+    float s = af * 65535.0f;
+    s = s < 0.0f ? 0.0f : s > 65535.0f ? 65535.0f : s;
+    alpha = (uint32_t) rintf(s);
   } else {
     const float d = nt.dither[DitherIndex(f, (uint32_t) x, (uint32_t) y)];
     for (int c = 0; c < 3; ++c) v[c] = ToU8Dithered(rgb[c], d);
+    alpha = ToU8Dithered(af, d);
   }
+  if (!out.alpha_float) alpha = AlphaAt(f, out, x, y);
   if (cp.grey) v[0] = v[2] = v[1];
-  StoreRgba(out, x, y, v[0], v[1], v[2], AlphaAt(f, out, x, y));
+  StoreRgba(out, x, y, v[0], v[1], v[2], alpha);
 }
 
 // 2x upsampling of a frame coded at half resolution (what libjxl's encoder does at distances of about 10 and more): every
@@ -148,6 +157,41 @@ JXLB_HD void StageUpsample2(const FrameDev& f, const float* src, float* dst, uin
         dst[c * uplane + (size_t) (2 * y + oy) * up_stride + 2 * x + ox] = acc;
       }
   }
+}
+
+// The alpha channel of a half-resolution frame, coded at half resolution too: libjxl turns its integers into floats in
+// [0, 1], upsamples them with the same kernel and clamping as the colour planes and converts back on output.  src: the
+// coded int32 plane (f.width x f.height, row stride f.mod_stride); dst: [up_h][up_stride] FLOATS in [0, 1] (OutputDesc::
+// alpha_float): libjxl quantises them on output like the colour channels -- with the 8-bit dither, which an exact k / 255
+// never shows but an upsampled value does.
+JXLB_HD void StageUpsampleAlpha2(const FrameDev& f, const int32_t* src, uint32_t bits, int32_t* dst, uint32_t up_stride, int x, int y) {
+  const float kW[15] = {-0.01716200f, -0.03452303f, -0.04022174f, -0.02921014f, -0.00624645f, 0.14111091f, 0.28896755f, 0.00278718f,
+                        -0.01610267f, 0.56661550f, 0.03777607f, -0.01986694f, -0.03144731f, -0.01185068f, -0.00213539f};
+  const float inv = 1.0f / (float) ((1u << bits) - 1);
+  float v[5][5];
+  float mn = 0.0f, mx = 0.0f;
+  for (int iy = 0; iy < 5; ++iy)
+    for (int ix = 0; ix < 5; ++ix) {
+      const float t = MulRn((float) src[(size_t) Mirror(y + iy - 2, (int) f.height) * f.mod_stride + Mirror(x + ix - 2, (int) f.width)], inv);
+      v[iy][ix] = t;
+      if (iy == 0 && ix == 0) mn = mx = t;
+      else {
+        mn = t < mn ? t : mn;
+        mx = t > mx ? t : mx;
+      }
+    }
+  for (int oy = 0; oy < 2; ++oy)
+    for (int ox = 0; ox < 2; ++ox) {
+      float acc = 0.0f;
+      for (int iy = 0; iy < 5; ++iy)
+        for (int ix = 0; ix < 5; ++ix) {
+          const int ky = oy ? 4 - iy : iy, kx = ox ? 4 - ix : ix;
+          const int a = ky < kx ? ky : kx, b = ky < kx ? kx : ky;
+          acc = AddRn(MulRn(kW[5 * a - a * (a - 1) / 2 + b - a], v[iy][ix]), acc);
+        }
+      acc = acc < mn ? mn : acc > mx ? mx : acc;
+      reinterpret_cast<float*>(dst)[(size_t) (2 * y + oy) * up_stride + 2 * x + ox] = acc;
+    }
 }
 
 // Modular (non-XYB) frames: integer samples straight to the output depth.

@@ -170,7 +170,7 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
     if (fh.upsampling == 2) {
       f.up_stride = RoundUp(2 * f.width, 64);
       f.up_h = 2 * f.height;
-      p.up_bytes = (size_t) 3 * f.up_h * f.up_stride * 4;
+      p.up_bytes = (size_t) (3 + (md.extra.empty() ? 0 : 1)) * f.up_h * f.up_stride * 4;  // XYB planes (+ the upsampled alpha plane)
     }
   }
   if (f.num_mod_channels) p.off_mod = take((size_t) f.num_mod_channels * f.height * f.mod_stride * 4);

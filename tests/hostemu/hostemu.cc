@@ -147,6 +147,11 @@ void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, si
 void emu_free(void* h) { delete static_cast<Emu*>(h); }
 int emu_status(void* h) { return static_cast<Emu*>(h)->status; }
 int emu_failed_stream(void* h) { return static_cast<Emu*>(h)->failed_stream; }
+// Status a pixel stage raised while rendering (a palette pixel it cannot reconstruct: pixel_stages.h StageGlobalInverse).
+int emu_late_status(void* h) {
+  Emu* e = static_cast<Emu*>(h);
+  return e->f.single_section ? 0 : e->f.status[e->f.num_lf_groups];
+}
 
 // out[]: width, height, w8, h8, lf_stride, coef_stride, coef_h, num_groups, num_lf_groups, encoding, num_mod_channels,
 //        mod_stride, w64, h64, single_section, global_nb_transforms, xsize, ysize, bits, num_extra, is_last, orientation,
@@ -234,8 +239,21 @@ int emu_render(void* h, uint8_t* out, uint32_t stride_bytes, int bits16, float* 
       fu.height = f.up_height;
       fu.plane_stride = f.up_stride;
       fu.plane_h = f.up_h;
+      OutputDesc odu = od;
+      std::vector<int32_t> up_alpha;
+      if (od.alpha_channel >= 0) {
+        up_alpha.resize((size_t) f.up_h * f.up_stride);
+        const int32_t* a = f.mod + (size_t) od.alpha_channel * f.height * f.mod_stride;
+        for (uint32_t y = 0; y < f.height; ++y)
+          for (uint32_t x = 0; x < f.width; ++x)
+            StageUpsampleAlpha2(f, a, od.alpha_bits, up_alpha.data(), f.up_stride, (int) x, (int) y);
+        fu.mod = up_alpha.data();
+        fu.mod_stride = f.up_stride;
+        odu.alpha_channel = 0;
+        odu.alpha_float = 1;
+      }
       for (uint32_t y = 0; y < fu.height; ++y)
-        for (uint32_t x = 0; x < fu.width; ++x) StageColorToRgba(fu, cp, nt, up.data(), od, (int) x, (int) y);
+        for (uint32_t x = 0; x < fu.width; ++x) StageColorToRgba(fu, cp, nt, up.data(), odu, (int) x, (int) y);
       return 0;
     }
     for (uint32_t y = 0; y < f.height; ++y)

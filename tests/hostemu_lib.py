@@ -30,7 +30,7 @@ def lib():
         L = C.CDLL(build())
         L.emu_decode.restype = C.c_void_p
         L.emu_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]
-        for n in ("emu_free", "emu_status", "emu_failed_stream"):
+        for n in ("emu_free", "emu_status", "emu_failed_stream", "emu_late_status"):
             getattr(L, n).argtypes = [C.c_void_p]
         L.emu_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
         for n, t in (("emu_lf_quant", C.c_int32), ("emu_xfromy", C.c_int32), ("emu_bfromy", C.c_int32), ("emu_cell_strategy", C.c_uint8),
@@ -116,6 +116,10 @@ class Decoded:
         if want_planes:
             return out, a[:, :i["height"], :i["width"]], b[:, :i["height"], :i["width"]]
         return out
+
+    def late_status(self):
+        """Status raised by a pixel stage during render() (what the product reads back after its kernels)."""
+        return lib().emu_late_status(self.h)
 
     def close(self):
         if self.h:

@@ -24,11 +24,11 @@ def test_upsampled_files_match_reference(J, ref):
     for g, d, o in zip(U.GRID, datas, outs):
         want = ref.decode_sampled(d, cfg=2)["pixels"]
         assert o.pixels.shape == want.shape, g
-        golden_lib.lossy_close(o.pixels, want, U.name(*g))
+        golden_lib.lossy_close(o.pixels, want, U.name(*g), min_exact=0.97)
 
 
 def test_upsampled_file_through_decode_sampled(J, ref):
-    d = U.make(ref, 600, 400, 12.0, -1, 7)
+    d = U.make(ref, 600, 400, 12.0, -1, 7, None)
     want = ref.decode_sampled(d, w=300, h=200, cfg=2, scale_mode=1, filt=1)
     got = J.JxlCoder.decode_sampled(d, 300, 200, 2, 1, 1)
     assert (got.width, got.height) == (want["width"], want["height"])

@@ -3,17 +3,22 @@ emits at distances of about 10 and more (the reference's quality scale below ~25
 import cases
 from oracle import synth
 
-GRID = [(w, h, dist, res, effort) for (w, h) in [(600, 400), (257, 255), (1101, 703), (97, 33), (16, 9)]
+# (w, h, distance, resampling option or -1, effort, alpha_distance or None): with an alpha channel the alpha plane is coded at
+# half resolution too and upsampled as floats (pixel_stages.h: StageUpsampleAlpha2)
+GRID = [(w, h, dist, res, effort, None) for (w, h) in [(600, 400), (257, 255), (1101, 703), (97, 33), (16, 9)]
         for (dist, res, effort) in [(12.0, -1, 7), (20.0, -1, 7), (2.0, 2, 7), (25.0, -1, 3)]]
+GRID += [(w, h, dist, -1, 7, ad) for (w, h) in [(600, 400), (1101, 703), (33, 97)] for (dist, ad) in [(12.0, 0.0), (12.0, 2.0), (20.0, 4.0)]]
 
 
-def name(w, h, dist, res, effort):
-    return "up2_%dx%d_d%g_r%d_e%d" % (w, h, dist, res, effort)
+def name(w, h, dist, res, effort, ad):
+    return "up2_%dx%d_d%g_r%d_e%d%s" % (w, h, dist, res, effort, "" if ad is None else "_a%g" % ad)
 
 
-def make(ref, w, h, dist, res, effort):
-    img = synth.synth_image(w, h, 5)
+def make(ref, w, h, dist, res, effort, ad):
+    img = synth.synth_image(w, h, 5, alpha=ad is not None)
     opts = {"EFFORT": effort}
     if res > 0:
         opts["RESAMPLING"] = res
-    return cases._cached(name(w, h, dist, res, effort), lambda: ref.encode_ex(img, w, h, 3, distance=dist, options=opts))
+    if ad is None:
+        return cases._cached(name(w, h, dist, res, effort, ad), lambda: ref.encode_ex(img, w, h, 3, distance=dist, options=opts))
+    return cases._cached(name(w, h, dist, res, effort, ad), lambda: ref.encode_ex(img, w, h, 4, distance=dist, alpha_distance=ad, options=opts))
