@@ -944,12 +944,17 @@ struct Batch {
       bool lz = false;
       if (f.num_mod_channels && p.g.has_global_tree && p.g.tree_code.size() >= sizeof(CodeHeader) &&
           reinterpret_cast<const CodeHeader*>(p.g.tree_code.data())->lz77) {
-        lz = true;
         const uint64_t side = std::min<uint64_t>(f.group_dim, std::max(f.width, f.height));
         const uint64_t symbols = std::min<uint64_t>(side * side, (uint64_t) f.width * f.height) * f.num_mod_channels + 65536;
         uint32_t e = 1u << 12;
         while (e < symbols && e < (1u << kLz77WindowLog)) e <<= 1;
-        lz_entries = std::max(lz_entries, e);
+        // windows are sized for the batch's largest stream: past 8 GiB in total the image goes without (its LZ77 streams
+        // then report "unsupported") instead of failing the whole batch's allocation
+        const uint64_t img_slots = f.single_section ? 1 : f.num_groups;
+        if ((lz_slots + img_slots) * (uint64_t) std::max(lz_entries, e) * 4 <= ((uint64_t) 8 << 30)) {
+          lz = true;
+          lz_entries = std::max(lz_entries, e);
+        }
       }
       if (f.single_section) {
         jobs_single.push_back(StreamJob{frame_of[i], 0, f.num_lf_groups + f.num_groups, lz ? ++lz_slots : 0});

@@ -483,7 +483,7 @@ JXLB_HD int PlanChannels(ModularHeader* mh, uint32_t nfinal, ChannelPlan* cp) {
     } else if (tr.id == 1) {
       if (tr.num_c == 0 || tr.begin_c + tr.num_c > len) return kErrBadStream;
       if (tr.begin_c < nb_meta) return kErrUnsupported;  // palette of a palette
-      if (tr.nb_colours > (1u << 20)) return kErrUnsupported;
+      if (tr.nb_colours > (1u << 20) || cp->meta_ints + (uint64_t) tr.nb_colours * tr.num_c > (16u << 20)) return kErrUnsupported;
       for (uint32_t k = 0; k < tr.num_c; ++k) tr.pl[k] = list[tr.begin_c + k];
       for (uint32_t i = tr.begin_c + tr.num_c; i < len; ++i) list[i - (tr.num_c - 1)] = list[i];
       len -= tr.num_c - 1;
