@@ -1269,6 +1269,7 @@ struct Batch {
           ++sampled;
         }
       } else {
+        if (!f.single_section && f.global_serial) LaunchModularGlobalInverse(f, s);  // delta palette: serial inverse first
         LaunchModularToRgba(f, od, s);
         if (!post) LaunchPack(pk, s);
       }

@@ -149,6 +149,7 @@ struct FrameDev {
   uint32_t global_mod_decoded;     // channels fully decoded in the global stream (filled by host plan)
   uint32_t global_nb_transforms;   // frame-level modular transforms (multi-section frames; host-parsed, PlanChannels applied)
   ModTransform global_tr[kMaxTransforms];
+  uint32_t global_serial;          // a frame-level palette needs the serial inverse (deltas / predictor): GlobalInverseSerialKernel, not per pixel
   uint32_t num_coded;              // multi-section frames: coded (non-meta) channels once the frame-level palettes are applied
   uint8_t coded_plane[kMaxModPlanes];  // ... and the plane of `mod` each of them is decoded into
   const int32_t* meta;             // palette colours of the frame-level transforms (host-decoded meta channels)

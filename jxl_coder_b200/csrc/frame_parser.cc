@@ -624,7 +624,7 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
     }
     if (parse_here) {
       int st = ReadModularHeader(br, &g->global_mh);
-      if (st == kErrUnsupported) JXLB_FAIL(kParseUnsupported, "delta palette or too many modular transforms");
+      if (st == kErrUnsupported) JXLB_FAIL(kParseUnsupported, "weighted-predictor delta palette or too many modular transforms");
       if (st != kOk || br.Overrun()) JXLB_FAIL(kParseInvalid, "global modular header");
       if (!g->global_mh.has_squeeze && fh.toc_entries > 1) {
         // frame-level RCTs / palettes: replay them on the channel list; the palettes' colours (meta channels) are the only
@@ -661,10 +661,10 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
           for (uint32_t c = 0; c < g->chplan.nb_meta; ++c) {
             const ModTransform& tr = g->global_mh.tr[g->chplan.meta_tr[c]];
             chs[c].data = g->meta_data.data() + tr.meta_off;
-            chs[c].w = tr.nb_colours;
+            chs[c].w = PaletteWidth(tr);
             chs[c].h = tr.num_c;
-            chs[c].stride = tr.nb_colours;
-            maxw = std::max(maxw, tr.nb_colours);
+            chs[c].stride = PaletteWidth(tr);
+            maxw = std::max(maxw, PaletteWidth(tr));
           }
           std::vector<int32_t> scratch(ModFastScratch::Ints(maxw + 8));
           ScratchLease lz((size_t) 4 << 20);

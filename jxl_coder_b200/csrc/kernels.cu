@@ -338,8 +338,23 @@ __global__ void __launch_bounds__(256) ModularToRgbaKernel(const FrameDev f, Out
   if (*f.frame_bad) return;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= (int) f.width || y >= (int) f.height) return;
-  if (!f.single_section) StageGlobalInverse(f, x, y);
+  if (!f.single_section && !f.global_serial) StageGlobalInverse(f, x, y);
   StageModularToRgba(f, out, x, y);
+}
+
+// Frame-level transforms that include a delta palette: one lane walks the whole image in raster order (modular.h:
+// ApplyInverseTransforms).  Rare (libjxl's lossless encoder picks such palettes for about one file in a hundred).
+__global__ void __launch_bounds__(32) GlobalInverseSerialKernel(const FrameDev f) {
+  if (*f.frame_bad || threadIdx.x != 0) return;
+  ModChannel planes[kMaxModPlanes];
+  for (uint32_t c = 0; c < f.num_mod_channels && c < (uint32_t) kMaxModPlanes; ++c) {
+    planes[c].data = f.mod + (size_t) c * f.height * f.mod_stride;
+    planes[c].w = f.width;
+    planes[c].h = f.height;
+    planes[c].stride = f.mod_stride;
+  }
+  const int st = ApplyInverseTransforms(f.global_tr, f.global_nb_transforms, planes, f.meta, f.bit_depth);
+  if (st != kOk) f.status[f.num_lf_groups] = st;
 }
 
 // Frame-level transforms on the extra channels of a multi-section VarDCT frame (e.g. a palette on a lossless alpha).
@@ -498,7 +513,8 @@ void LaunchUpsampleAlpha2(const FrameDev& f, const int32_t* src, uint32_t bits, 
 }
 
 void LaunchModularGlobalInverse(const FrameDev& f, cudaStream_t stream) {
-  ModularGlobalInverseKernel<<<PixelGrid(f.width, f.height, 256), 256, 0, stream>>>(f);
+  if (f.global_serial) GlobalInverseSerialKernel<<<1, 32, 0, stream>>>(f);
+  else ModularGlobalInverseKernel<<<PixelGrid(f.width, f.height, 256), 256, 0, stream>>>(f);
   ++g_launches;
 }
 

@@ -93,10 +93,9 @@ JXLB_HD_NOINLINE int ReadModularHeader(BitReader& br, ModularHeader* h) {
       t.nb_colours = br.U32(0, 8, 256, 10, 1280, 12, 5376, 16);
       t.nb_deltas = br.U32(0, 0, 1, 8, 257, 10, 1281, 16);
       t.d_pred = br.Read(4);
-      // delta palettes (entries predicted from neighbouring output pixels: the encoder's opt-in lossy-palette mode).  A
-      // predictor alone (the lossless encoder writes one now and then) only matters for negative indices, which then
-      // fail the stream where they occur (InversePalettePixel).
-      if (t.nb_deltas != 0) return kErrUnsupported;
+      // delta palettes: entries below nb_deltas, and the implicit colours of negative indices, are ADDED to a prediction
+      // from the neighbouring output pixels (PaletteNeedsSerialInverse); libjxl's lossless encoder uses them now and then
+      if (t.d_pred == 6 || t.d_pred > 13) return kErrUnsupported;  // a delta palette over the weighted predictor
       if (t.num_c > (uint32_t) kMaxModPlanes) return kErrUnsupported;
     } else if (t.id == 2) {
       if (h->has_squeeze) return kErrUnsupported;  // one squeeze transform per header
@@ -287,6 +286,31 @@ JXLB_HD int32_t ClampedGradient(int32_t w, int32_t n, int32_t nw) {
   return g < mn ? mn : g > mx ? mx : (int32_t) g;
 }
 
+// The 13 predictors that need no weighted-predictor state (ISO/IEC 18181-1 modular predictors; 6 = weighted is separate).
+JXLB_HD int64_t PredictNoWp(uint32_t predictor, int32_t W, int32_t N, int32_t NW, int32_t NE, int32_t NN, int32_t WW, int32_t NEE) {
+  switch (predictor) {
+    case 0: return 0;
+    case 1: return W;
+    case 2: return N;
+    case 3: return ((int64_t) W + N) / 2;
+    case 4: {
+      int64_t p = (int64_t) W + N - NW;
+      int64_t pa = p - W, pb = p - N;
+      if (pa < 0) pa = -pa;
+      if (pb < 0) pb = -pb;
+      return pa < pb ? W : N;
+    }
+    case 5: return ClampedGradient(W, N, NW);
+    case 7: return NE;
+    case 8: return NW;
+    case 9: return WW;
+    case 10: return ((int64_t) W + NW) / 2;
+    case 11: return ((int64_t) N + NW) / 2;
+    case 12: return ((int64_t) N + NE) / 2;
+    default: return (6 * (int64_t) N - 2 * (int64_t) NN + 7 * (int64_t) W + WW + NEE + 3 * (int64_t) NE + 8) / 16;
+  }
+}
+
 // Everything a stream needs besides the bits: tree + code (global or local) and scratch.
 struct ModularContext {
   const TreeNode* tree;
@@ -468,6 +492,12 @@ struct ChannelPlan {
   uint32_t meta_ints;                    // size of the meta-channel buffer
 };
 
+// Entries of a palette's meta channel per colour channel: nb_deltas delta entries (the indices below nb_deltas) followed
+// by nb_colours colours.
+JXLB_HD uint32_t PaletteWidth(const ModTransform& tr) { return tr.nb_colours + tr.nb_deltas; }
+// True when the inverse has to walk the pixels in raster order: a value may be added to a prediction from its neighbours.
+JXLB_HD bool PaletteNeedsSerialInverse(const ModTransform& tr) { return tr.id == 1 && (tr.nb_deltas != 0 || tr.d_pred != 0); }
+
 JXLB_HD int PlanChannels(ModularHeader* mh, uint32_t nfinal, ChannelPlan* cp) {
   if (nfinal > (uint32_t) kMaxModPlanes) return kErrUnsupported;
   uint8_t list[kMaxModPlanes + kMaxTransforms];  // plane id, or 0x80 | transform for a meta channel
@@ -483,7 +513,9 @@ JXLB_HD int PlanChannels(ModularHeader* mh, uint32_t nfinal, ChannelPlan* cp) {
     } else if (tr.id == 1) {
       if (tr.num_c == 0 || tr.begin_c + tr.num_c > len) return kErrBadStream;
       if (tr.begin_c < nb_meta) return kErrUnsupported;  // palette of a palette
-      if (tr.nb_colours > (1u << 20) || cp->meta_ints + (uint64_t) tr.nb_colours * tr.num_c > (16u << 20)) return kErrUnsupported;
+      if (tr.nb_colours > (1u << 20) || tr.nb_deltas > (1u << 20) ||
+          cp->meta_ints + (uint64_t) PaletteWidth(tr) * tr.num_c > (16u << 20))
+        return kErrUnsupported;
       for (uint32_t k = 0; k < tr.num_c; ++k) tr.pl[k] = list[tr.begin_c + k];
       for (uint32_t i = tr.begin_c + tr.num_c; i < len; ++i) list[i - (tr.num_c - 1)] = list[i];
       len -= tr.num_c - 1;
@@ -492,7 +524,7 @@ JXLB_HD int PlanChannels(ModularHeader* mh, uint32_t nfinal, ChannelPlan* cp) {
       ++len;
       ++nb_meta;
       tr.meta_off = cp->meta_ints;
-      cp->meta_ints += tr.nb_colours * tr.num_c;
+      cp->meta_ints += PaletteWidth(tr) * tr.num_c;
     } else {
       return kErrUnsupported;  // squeeze: handled by its own path (squeeze.h), never together with the others here
     }
@@ -536,31 +568,33 @@ JXLB_HD_NOINLINE int32_t ImplicitPaletteValue(int32_t index, uint32_t c, int32_t
   return (int32_t) (((int64_t) (index % 5) * ((1ll << bit_depth) - 1)) / 4);
 }
 
-JXLB_HD int32_t PaletteValue(const int32_t* pal, int32_t index, uint32_t c, uint32_t nb_colours, uint32_t bit_depth) {
-  if (index >= 0 && (uint32_t) index < nb_colours) return pal[(size_t) c * nb_colours + (uint32_t) index];
-  return ImplicitPaletteValue(index, c, (int32_t) nb_colours, bit_depth);
+JXLB_HD int32_t PaletteValue(const int32_t* pal, int32_t index, uint32_t c, uint32_t width, uint32_t bit_depth) {
+  if (index >= 0 && (uint32_t) index < width) return pal[(size_t) c * width + (uint32_t) index];
+  return ImplicitPaletteValue(index, c, (int32_t) width, bit_depth);
 }
 
 // One pixel of the inverse palette: the index sits in the first output plane.  False: a negative index (an implicit delta
 // colour) under a predictor, which would need the neighbouring output pixels -- not covered.
 JXLB_HD bool InversePalettePixel(const ModTransform& tr, const int32_t* meta, uint32_t bit_depth, int32_t index, int32_t* out) {
   const int32_t* pal = meta + tr.meta_off;
-  const bool ok = !(index < 0 && tr.d_pred != 0 && tr.num_c > 1);
+  const bool ok = !(PaletteNeedsSerialInverse(tr) && index < (int32_t) tr.nb_deltas);  // callers route such palettes to the serial inverse
   if (tr.num_c == 1) {  // single-channel palettes clamp the index instead of using implicit colours
-    const int32_t hi = (int32_t) tr.nb_colours - 1;
+    const int32_t hi = (int32_t) PaletteWidth(tr) - 1;
     if (index > hi) index = hi;
     if (index < 0) index = hi < 0 ? -1 : 0;
   }
-  for (uint32_t c = 0; c < tr.num_c; ++c) out[c] = PaletteValue(pal, index, c, tr.nb_colours, bit_depth);
+  for (uint32_t c = 0; c < tr.num_c; ++c) out[c] = PaletteValue(pal, index, c, PaletteWidth(tr), bit_depth);
   return ok;
 }
 
-// Serial inverse of every transform of a stream header over whole planes (`planes`: the stream's output planes, all of one
-// size).  The per-pixel form for frame-level transforms of large images is StageGlobalInverse (pixel_stages.h).
-JXLB_HD int ApplyInverseTransforms(const ModularHeader& mh, const ModChannel* planes, const int32_t* meta, uint32_t bit_depth) {
+// Serial inverse of transforms tr[0 .. n) (undone last to first) over whole planes (`planes`: the stream's output planes, all
+// of one size).  The per-pixel form for frame-level transforms of large images is StageGlobalInverse (pixel_stages.h);
+// palettes with deltas or a predictor only exist in this form: their pixels are visited in raster order and a delta is
+// added to the prediction from the already reconstructed neighbours of the same output plane.
+JXLB_HD int ApplyInverseTransforms(const ModTransform* trs, uint32_t n, const ModChannel* planes, const int32_t* meta, uint32_t bit_depth) {
   bool ok = true;
-  for (int t = (int) mh.nb_transforms - 1; t >= 0; --t) {
-    const ModTransform& tr = mh.tr[t];
+  for (int t = (int) n - 1; t >= 0; --t) {
+    const ModTransform& tr = trs[t];
     if (tr.id == 0) {
       const ModChannel& a = planes[tr.pl[0]];
       const ModChannel& b = planes[tr.pl[1]];
@@ -579,13 +613,41 @@ JXLB_HD int ApplyInverseTransforms(const ModularHeader& mh, const ModChannel* pl
           dst[2]->data[(size_t) y * dst[2]->stride + x] = v2;
         }
       }
-    } else if (tr.id == 1) {
+    } else if (tr.id == 1 && !PaletteNeedsSerialInverse(tr)) {
       const ModChannel& ic = planes[tr.pl[0]];
       for (uint32_t y = 0; y < ic.h; ++y) {
         for (uint32_t x = 0; x < ic.w; ++x) {
           int32_t v[kMaxModPlanes];
           ok &= InversePalettePixel(tr, meta, bit_depth, ic.data[(size_t) y * ic.stride + x], v);
           for (uint32_t c = 0; c < tr.num_c; ++c) planes[tr.pl[c]].data[(size_t) y * planes[tr.pl[c]].stride + x] = v[c];
+        }
+      }
+    } else if (tr.id == 1) {
+      // delta palette.  The index plane is output plane 0 of the transform; at (x, y) every neighbour a predictor looks at
+      // (W, WW, N, NW, NE, NEE, NN) has already been turned into an output sample, in every plane.
+      const ModChannel& ic = planes[tr.pl[0]];
+      const int32_t* pal = meta + tr.meta_off;
+      const uint32_t width = PaletteWidth(tr);
+      for (uint32_t y = 0; y < ic.h; ++y) {
+        for (uint32_t x = 0; x < ic.w; ++x) {
+          const int32_t index = ic.data[(size_t) y * ic.stride + x];
+          for (uint32_t c = 0; c < tr.num_c; ++c) {
+            const ModChannel& pc = planes[tr.pl[c]];
+            int32_t* pp = pc.data + (size_t) y * pc.stride + x;
+            int64_t val = PaletteValue(pal, index, c, width, bit_depth);
+            if (index < (int32_t) tr.nb_deltas) {
+              const ptrdiff_t row = (ptrdiff_t) pc.stride;
+              const int32_t W = x ? pp[-1] : (y ? pp[-row] : 0);
+              const int32_t N = y ? pp[-row] : W;
+              const int32_t NW = (x && y) ? pp[-1 - row] : W;
+              const int32_t NE = (x + 1 < pc.w && y) ? pp[1 - row] : N;
+              const int32_t WW = x > 1 ? pp[-2] : W;
+              const int32_t NN = y > 1 ? pp[-2 * row] : N;
+              const int32_t NEE = (x + 2 < pc.w && y) ? pp[2 - row] : NE;
+              val += PredictNoWp(tr.d_pred, W, N, NW, NE, NN, WW, NEE);
+            }
+            *pp = (int32_t) val;
+          }
         }
       }
     }

@@ -130,30 +130,6 @@ JXLB_HD_NOINLINE SubtreeInfo AnalyseSubtree(const TreeNode* tree, uint32_t num_n
   return s;
 }
 
-JXLB_HD int64_t PredictNoWp(uint32_t predictor, int32_t W, int32_t N, int32_t NW, int32_t NE, int32_t NN, int32_t WW, int32_t NEE) {
-  switch (predictor) {
-    case 0: return 0;
-    case 1: return W;
-    case 2: return N;
-    case 3: return ((int64_t) W + N) / 2;
-    case 4: {
-      int64_t p = (int64_t) W + N - NW;
-      int64_t pa = p - W, pb = p - N;
-      if (pa < 0) pa = -pa;
-      if (pb < 0) pb = -pb;
-      return pa < pb ? W : N;
-    }
-    case 5: return ClampedGradient(W, N, NW);
-    case 7: return NE;
-    case 8: return NW;
-    case 9: return WW;
-    case 10: return ((int64_t) W + NW) / 2;
-    case 11: return ((int64_t) N + NW) / 2;
-    case 12: return ((int64_t) N + NE) / 2;
-    default: return (6 * (int64_t) N - 2 * (int64_t) NN + 7 * (int64_t) W + WW + NEE + 3 * (int64_t) NE + 8) / 16;
-  }
-}
-
 JXLB_HD_NOINLINE int DecodeModularChannelsFast(BitReader& br_io, const ModularContext& mc, const WPHeader& wph, const ModChannel* ch,
                                                uint32_t nch, uint32_t stream_id, int32_t* scratch, uint32_t* lz77_window,
                                                uint32_t lz77_mask, int32_t* fast_scratch = nullptr, uint32_t fast_ints = 0) {

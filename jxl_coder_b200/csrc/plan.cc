@@ -72,6 +72,8 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
   f.num_coded = f.num_mod_channels;
   for (uint32_t i = 0; i < (uint32_t) kMaxModPlanes; ++i) f.coded_plane[i] = (uint8_t) i;
   if (g.global_mh.nb_transforms && !g.squeeze && fh.toc_entries > 1) {
+    for (uint32_t t = 0; t < g.global_mh.nb_transforms; ++t)
+      if (PaletteNeedsSerialInverse(g.global_mh.tr[t])) f.global_serial = 1;
     f.num_coded = g.chplan.ncoded;
     for (uint32_t i = 0; i < g.chplan.ncoded; ++i) f.coded_plane[i] = g.chplan.coded_plane[i];
   }

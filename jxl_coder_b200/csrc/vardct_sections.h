@@ -194,10 +194,10 @@ JXLB_HD_NOINLINE int DecodeTransformedStream(BitReader& br, StreamScratch& s, Mo
   for (uint32_t i = 0; i < cp.nb_meta; ++i) {
     const ModTransform& tr = mh.tr[cp.meta_tr[i]];
     list[n].data = meta + tr.meta_off;
-    list[n].w = tr.nb_colours;
+    list[n].w = PaletteWidth(tr);
     list[n].h = tr.num_c;
-    list[n].stride = tr.nb_colours;
-    if (tr.nb_colours > maxw) maxw = tr.nb_colours;
+    list[n].stride = PaletteWidth(tr);
+    if (PaletteWidth(tr) > maxw) maxw = PaletteWidth(tr);
     ++n;
   }
   for (uint32_t i = 0; i < cp.ncoded; ++i) {
@@ -215,7 +215,7 @@ JXLB_HD_NOINLINE int DecodeTransformedStream(BitReader& br, StreamScratch& s, Mo
   st = DecodeModularChannelsFast(br, mc, mh.wp, list, n, stream_id, wp, s.lz77, s.lz77_mask,
                                  s.fast ? reinterpret_cast<int32_t*>(s.fast + s.fast_code_bytes) : nullptr, s.fast_ints);
   if (st != kOk) return st;
-  return ApplyInverseTransforms(mh, planes, meta, bit_depth);
+  return ApplyInverseTransforms(mh.tr, mh.nb_transforms, planes, meta, bit_depth);
 }
 
 JXLB_HD void LfGroupRect(const FrameDev& f, uint32_t lfg, uint32_t* cx0, uint32_t* cy0, uint32_t* w8, uint32_t* h8,

@@ -137,7 +137,11 @@ void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, si
     }
     if (!e->status && f.sq_nch) UnsqueezeAllSerial(f);
     // frame-level transforms on the extra channels of a VarDCT frame (the device runs ModularGlobalInverseKernel)
-    if (!e->status && f.encoding == 0 && !f.sq_nch && f.num_mod_channels && f.global_nb_transforms)
+    if (!e->status && !f.sq_nch && f.num_mod_channels && f.global_serial) {  // delta palette: the serial inverse (GlobalInverseSerialKernel)
+      ModChannel planes[kMaxModPlanes];
+      for (uint32_t c = 0; c < f.num_mod_channels; ++c) planes[c] = ModChannel{f.mod + (size_t) c * f.height * f.mod_stride, f.width, f.height, f.mod_stride};
+      e->status = ApplyInverseTransforms(f.global_tr, f.global_nb_transforms, planes, f.meta, f.bit_depth);
+    } else if (!e->status && f.encoding == 0 && !f.sq_nch && f.num_mod_channels && f.global_nb_transforms)
       for (uint32_t y = 0; y < f.height; ++y)
         for (uint32_t x = 0; x < f.width; ++x) StageGlobalInverse(f, (int) x, (int) y);
   }
@@ -262,7 +266,7 @@ int emu_render(void* h, uint8_t* out, uint32_t stride_bytes, int bits16, float* 
     if (e->md.xyb_encoded) return 3;
     for (uint32_t y = 0; y < f.height; ++y)
       for (uint32_t x = 0; x < f.width; ++x) {
-        if (!f.single_section) StageGlobalInverse(f, (int) x, (int) y);
+        if (!f.single_section && !f.global_serial) StageGlobalInverse(f, (int) x, (int) y);
         StageModularToRgba(f, od, (int) x, (int) y);
       }
   }

@@ -19,6 +19,11 @@ def few_colours(w, h, seed, n, alpha=False):
     return pal[idx]
 
 
+def gradient(w, h):
+    yy, xx = np.mgrid[0:h, 0:w]
+    return np.stack([xx * 255 // max(1, w - 1), yy * 255 // max(1, h - 1), (xx + yy) % 256], axis=2).astype(np.uint8)
+
+
 def two_level_alpha(w, h, seed):
     img = synth.synth_image(w, h, seed, alpha=True).reshape(h, w, 4).copy()
     img[..., 3] = np.where(img[..., 3] > 128, 255, 0)
@@ -40,6 +45,13 @@ CASES = {
     "e1_rgb_1145x612": (lambda: (synth.synth_image(1145, 612, 91), 1145, 612, 3, 8), dict(lossless=True, options={"EFFORT": 1})),
     "e1_rgba_208x244": (lambda: (synth.synth_image(208, 244, 21, alpha=True), 208, 244, 4, 8), dict(lossless=True, options={"EFFORT": 1})),
     "e1_rgb16_485x332": (lambda: (synth.synth_image(485, 332, 13).astype(np.uint16) * 257, 485, 332, 3, 16), dict(lossless=True, options={"EFFORT": 1})),
+    # delta palettes (found by the randomised CPU sweep): implicit delta colours through negative indices under predictor 13,
+    # and explicit delta entries (nb_deltas = 3) -- frame-level, so the serial inverse kernel runs
+    "pal_delta_implicit_215x409": (lambda: (synth.synth_image(215, 409, 18 + 1000 * 102), 215, 409, 3, 8),
+                                   dict(lossless=True, options={"EFFORT": 5, "MODULAR_GROUP_SIZE": 1})),
+    "pal_delta_entries_2137x567": (lambda: (gradient(2137, 567), 2137, 567, 3, 8), dict(lossless=True, options={"EFFORT": 5, "MODULAR_GROUP_SIZE": 1})),
+    "pal_delta_noise_rgba_650x362": (lambda: (np.random.default_rng(5).integers(0, 256, (362, 650, 4)).astype(np.uint8), 650, 362, 4, 8),
+                                     dict(lossless=True, options={"EFFORT": 4, "DECODING_SPEED": 4, "MODULAR_GROUP_SIZE": 1})),
     "pal_lossy_colour_lossless_alpha_82x569": (lambda: (synth.synth_image(82, 569, 72, alpha=True), 82, 569, 4, 8), dict(distance=2.0, alpha_distance=0.0, options={"EFFORT": 4})),
 }
 

@@ -49,17 +49,3 @@ def test_palette_batch_mixes_with_other_images(J, ref):
             golden_lib.lossy_close(o.pixels, want, "batch")
         else:
             assert np.array_equal(o.pixels, want)
-
-
-def test_implicit_delta_colours_are_refused_not_misdecoded(J, ref):
-    """A lossless file whose palette works through NEGATIVE indices (implicit delta colours added to a prediction from the
-    neighbouring output pixels; nb_deltas = 0, predictor 13 -- found by the randomised CPU sweep): the decoder has no
-    serial predictor pass for palettes, notices the first such index on the device and reports the file as unsupported."""
-    import numpy as np
-    import cases
-    from oracle import synth
-    img = np.ascontiguousarray(synth.synth_image(215, 409, 18 + 1000 * 102))
-    data = cases._cached("pal_implicit_delta_215x409", lambda: ref.encode_ex(img, 215, 409, 3, lossless=True,
-                                                                             options={"EFFORT": 5, "MODULAR_GROUP_SIZE": 1}))
-    with pytest.raises(J.UnsupportedJXLException):
-        J.JxlCoder.decode(data, 2)

@@ -15,7 +15,19 @@ def test_palette_files_decode_exactly(name, ref):
     out = e.render(bits16=bits == 16)
     e.close()
     ch = img.shape[2]
-    if kw.get("lossless"):
+    if kw.get("lossless") and bits == 8:
+        # parity is with the REFERENCE's decode; the source image is a second check wherever the reference reproduces it (the
+        # delta-palette files do not: libjxl's encoder, asked for lossless with these options, comes back up to 75 off the
+        # source through its own decoder)
+        want = ref.decode_sampled(data, cfg=2)["pixels"][:, : img.shape[1] * 4].reshape(img.shape[0], img.shape[1], 4)
+        if np.array_equal(want[..., :ch][want[..., 3] == 255], img[want[..., 3] == 255]):
+            assert np.array_equal(out[..., :ch], img), name
+        else:
+            assert name.startswith("pal_delta"), name
+        a = out[..., 3:4].astype(np.uint16)
+        out[..., :3] = (out[..., :3].astype(np.uint16) * a // 255).astype(np.uint8)  # ReformatColorConfig premultiplies
+        assert np.array_equal(out, want), name
+    elif kw.get("lossless"):
         assert np.array_equal(out[..., :ch], img), name
     else:
         assert np.array_equal(out[..., 3], img[..., 3]), name
