@@ -1229,6 +1229,7 @@ struct Batch {
         pk.dst_stride = od.stride_bytes;
       }
       if (f.sq_nch) LaunchUnsqueeze(f, p.g.sq.steps.data(), s);
+      if (f.global_planes) LaunchScatterGlobalPlanes(f, s);
       if (f.encoding == 0 && !f.single_section && !f.sq_nch && f.num_mod_channels && f.global_nb_transforms) LaunchModularGlobalInverse(f, s);
       if (f.encoding == 0) {
         const bool timed = (vd++ % kTimeEvery) == 0;

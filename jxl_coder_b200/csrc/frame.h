@@ -153,6 +153,7 @@ struct FrameDev {
   uint32_t num_coded;              // multi-section frames: coded (non-meta) channels once the frame-level palettes are applied
   uint8_t coded_plane[kMaxModPlanes];  // ... and the plane of `mod` each of them is decoded into
   const int32_t* meta;             // palette colours of the frame-level transforms (host-decoded meta channels)
+  const int32_t* global_planes;    // multi-section frame no larger than a group: its modular channels [num_coded][height][width], host-decoded
   uint32_t bit_depth;              // bits per sample of the image (implicit palette colours scale with it)
   // ---- planes (device) ----
   int32_t* lf_quant;               // [3][h8][lf_stride]  (Y, X, B as coded)

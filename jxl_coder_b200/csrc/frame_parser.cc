@@ -632,7 +632,10 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
         st = PlanChannels(&g->global_mh, nmod, &g->chplan);
         if (st == kErrUnsupported) JXLB_FAIL(kParseUnsupported, "nested palette transforms");
         if (st != kOk) JXLB_FAIL(kParseInvalid, "modular transform channel range");
-        if (g->chplan.nb_meta) {
+        // the global stream of a multi-section frame holds the palettes' colours and -- when the frame is no larger than one
+        // group, i.e. a small progressive picture -- the modular channels themselves
+        const bool planes_global = fh.coded_w <= fh.group_dim && fh.coded_h <= fh.group_dim && g->chplan.ncoded > 0;
+        if (g->chplan.nb_meta || planes_global) {
           ModularContext mc{};
           Arena a2;
           ScratchLease amem(4u << 20);
@@ -656,8 +659,19 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
             mc.code.Bind(a2.base + coff);
           }
           g->meta_data.assign((size_t) g->chplan.meta_ints + 1, 0);
-          std::vector<ModChannel> chs(g->chplan.nb_meta);
-          uint32_t maxw = 0;
+          const uint32_t nglobal = g->chplan.nb_meta + (planes_global ? g->chplan.ncoded : 0);
+          std::vector<ModChannel> chs(nglobal);
+          uint32_t maxw = planes_global ? fh.coded_w : 0;
+          if (planes_global) {
+            g->global_planes.assign((size_t) g->chplan.ncoded * fh.coded_w * fh.coded_h, 0);
+            for (uint32_t c = 0; c < g->chplan.ncoded; ++c) {
+              ModChannel& mcn = chs[g->chplan.nb_meta + c];
+              mcn.data = g->global_planes.data() + (size_t) c * fh.coded_w * fh.coded_h;
+              mcn.w = fh.coded_w;
+              mcn.h = fh.coded_h;
+              mcn.stride = fh.coded_w;
+            }
+          }
           for (uint32_t c = 0; c < g->chplan.nb_meta; ++c) {
             const ModTransform& tr = g->global_mh.tr[g->chplan.meta_tr[c]];
             chs[c].data = g->meta_data.data() + tr.meta_off;
@@ -668,7 +682,7 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
           }
           std::vector<int32_t> scratch(ModFastScratch::Ints(maxw + 8));
           ScratchLease lz((size_t) 4 << 20);
-          st = DecodeModularChannelsFast(br, mc, g->global_mh.wp, chs.data(), g->chplan.nb_meta, 0, scratch.data(), lz.as<uint32_t>(), (1u << 20) - 1);
+          st = DecodeModularChannelsFast(br, mc, g->global_mh.wp, chs.data(), nglobal, 0, scratch.data(), lz.as<uint32_t>(), (1u << 20) - 1);
           if (st == kErrUnsupported || st == kErrScratch) JXLB_FAIL(kParseUnsupported, "global modular stream");
           if (st != kOk || br.Overrun()) JXLB_FAIL(kParseInvalid, "global modular stream");
         }

@@ -122,6 +122,9 @@ struct FrameGlobals {
   ModularHeader global_mh{};          // parsed for multi-section frames with a modular image
   ChannelPlan chplan{};               // ... its channel list (palette meta channels first)
   std::vector<int32_t> meta_data;     // ... and the palette colours, decoded on the host (they live in the global stream)
+  // ... and, for a multi-section frame no larger than one group (a small progressive picture), its modular channels
+  // themselves, which then live in the global stream too: [chplan.ncoded][coded_h][coded_w], decoded on the host
+  std::vector<int32_t> global_planes;
   // squeezed extra channels (squeeze.h): channel pyramid, inverse steps, and the samples of the channels that live in
   // the global stream (decoded on the host: they are at most group_dim x group_dim), concatenated in channel order
   bool squeeze = false;

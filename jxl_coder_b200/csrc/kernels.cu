@@ -357,6 +357,16 @@ __global__ void __launch_bounds__(32) GlobalInverseSerialKernel(const FrameDev f
   if (st != kOk) f.status[f.num_lf_groups] = st;
 }
 
+// Modular channels that the host decoded from the global stream of a small multi-section (progressive) frame: into their planes.
+__global__ void __launch_bounds__(256) ScatterGlobalPlanesKernel(const FrameDev f) {
+  if (*f.frame_bad) return;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= (int) f.width || y >= (int) f.height) return;
+  for (uint32_t c = 0; c < f.num_coded; ++c)
+    f.mod[(size_t) f.coded_plane[c] * f.height * f.mod_stride + (size_t) y * f.mod_stride + x] =
+        f.global_planes[((size_t) c * f.height + y) * f.width + x];
+}
+
 // Frame-level transforms on the extra channels of a multi-section VarDCT frame (e.g. a palette on a lossless alpha).
 __global__ void __launch_bounds__(256) ModularGlobalInverseKernel(const FrameDev f) {
   if (*f.frame_bad) return;
@@ -509,6 +519,11 @@ void LaunchUpsample2(const FrameDev& f, const float* src, float* dst, uint32_t u
 void LaunchUpsampleAlpha2(const FrameDev& f, const int32_t* src, uint32_t bits, int32_t* dst, uint32_t up_stride,
                           cudaStream_t stream) {
   UpsampleAlpha2Kernel<<<PixelGrid(f.width, f.height, 256), 256, 0, stream>>>(f, src, bits, dst, up_stride);
+  ++g_launches;
+}
+
+void LaunchScatterGlobalPlanes(const FrameDev& f, cudaStream_t stream) {
+  ScatterGlobalPlanesKernel<<<PixelGrid(f.width, f.height, 256), 256, 0, stream>>>(f);
   ++g_launches;
 }
 

@@ -124,6 +124,7 @@ void LaunchColor(const FrameDev& f, const ColorParams& cp, const NumericTables* 
                  cudaStream_t stream);
 void LaunchModularToRgba(const FrameDev& f, OutputDesc out, cudaStream_t stream);
 void LaunchModularGlobalInverse(const FrameDev& f, cudaStream_t stream);
+void LaunchScatterGlobalPlanes(const FrameDev& f, cudaStream_t stream);
 // 2x upsampling of the filtered XYB planes of a frame coded at half resolution: src (f geometry) -> dst [3][up_h][up_stride]
 void LaunchUpsample2(const FrameDev& f, const float* src, float* dst, uint32_t up_stride, uint32_t up_h, cudaStream_t stream);
 // ... and of its alpha plane (coded int32 samples of `bits` bits -> floats in [0, 1], [up_h][up_stride]; OutputDesc::alpha_float)

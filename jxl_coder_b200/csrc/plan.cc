@@ -106,6 +106,7 @@ void MakeFramePlan(const ImageMetadata& md, const FrameHeader& fh, const FrameGl
     p.off_sq_global = take(g.sq_global_data.size() * sizeof(int32_t));
   }
   if (!g.meta_data.empty()) p.off_meta = take(g.meta_data.size() * sizeof(int32_t));
+  if (!g.global_planes.empty()) p.off_global_planes = take(g.global_planes.size() * sizeof(int32_t));
   f.pass_shift0 = fh.num_passes > 1 ? fh.pass_shift[0] : 0;
   {
     // which modular channels each pass carries (ISO/IEC 18181-1 passes: the downsampling a pass completes); a single pass
@@ -199,6 +200,7 @@ void FillConstRegion(const FramePlan& plan, const uint8_t* cs_padded, const Fram
     memcpy(dst + plan.off_sq_global, g.sq_global_data.data(), g.sq_global_data.size() * sizeof(int32_t));
   }
   if (!g.meta_data.empty()) memcpy(dst + plan.off_meta, g.meta_data.data(), g.meta_data.size() * sizeof(int32_t));
+  if (!g.global_planes.empty()) memcpy(dst + plan.off_global_planes, g.global_planes.data(), g.global_planes.size() * sizeof(int32_t));
   if (!g.extra_passes.empty()) {
     uint8_t* base = dst + plan.off_pass_table;
     PassDev* pd = reinterpret_cast<PassDev*>(base);
@@ -268,6 +270,7 @@ FrameDev BindFrameDev(const FramePlan& p, const uint8_t* cb, uint8_t* wb) {
     f.sq_buf = reinterpret_cast<int32_t*>(wb + p.off_sq_buf);
   }
   f.meta = p.off_meta ? reinterpret_cast<const int32_t*>(cb + p.off_meta) : nullptr;
+  f.global_planes = p.off_global_planes ? reinterpret_cast<const int32_t*>(cb + p.off_global_planes) : nullptr;
   f.pass_table = p.off_pass_table ? reinterpret_cast<const PassDev*>(cb + p.off_pass_table) : nullptr;
   return f;
 }

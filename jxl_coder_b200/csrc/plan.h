@@ -12,7 +12,7 @@ struct FramePlan {
   // const region
   size_t const_bytes = 0;
   size_t off_cs = 0, off_sec_begin = 0, off_sec_end = 0, off_bctx_map = 0, off_tree = 0, off_tree_code = 0, off_ac_code = 0,
-         off_order_pool = 0, off_blockinfo_off = 0, off_sq_ch = 0, off_sq_steps = 0, off_sq_global = 0, off_meta = 0, off_pass_table = 0;
+         off_order_pool = 0, off_blockinfo_off = 0, off_sq_ch = 0, off_sq_steps = 0, off_sq_global = 0, off_meta = 0, off_pass_table = 0, off_global_planes = 0;
   // work region
   size_t work_bytes = 0;
   size_t off_lf_quant = 0, off_xfromy = 0, off_bfromy = 0, off_sharp_i32 = 0, off_blockinfo = 0, off_nb_blocks = 0,

@@ -136,6 +136,11 @@ void* emu_decode(const uint8_t* data, size_t len, int frame_index, char* err, si
       if (e->status) e->failed_stream = (int) (f.num_lf_groups + gi);
     }
     if (!e->status && f.sq_nch) UnsqueezeAllSerial(f);
+    if (!e->status && f.global_planes)  // ScatterGlobalPlanesKernel
+      for (uint32_t c = 0; c < f.num_coded; ++c)
+        for (uint32_t y = 0; y < f.height; ++y)
+          for (uint32_t x = 0; x < f.width; ++x)
+            f.mod[(size_t) f.coded_plane[c] * f.height * f.mod_stride + (size_t) y * f.mod_stride + x] = f.global_planes[((size_t) c * f.height + y) * f.width + x];
     // frame-level transforms on the extra channels of a VarDCT frame (the device runs ModularGlobalInverseKernel)
     if (!e->status && !f.sq_nch && f.num_mod_channels && f.global_serial) {  // delta palette: the serial inverse (GlobalInverseSerialKernel)
       ModChannel planes[kMaxModPlanes];

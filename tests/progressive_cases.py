@@ -10,6 +10,8 @@ GRID = [(w, h, opt, dist, effort, None) for (w, h) in [(600, 400), (256, 256), (
         for opt in ("PROGRESSIVE_AC", "QPROGRESSIVE_AC") for (dist, effort) in [(1.0, 7), (3.0, 3)]]
 GRID += [(w, h, opt, 1.0, 7, ad) for (w, h) in [(600, 400), (2200, 300)] for opt in ("PROGRESSIVE_AC", "QPROGRESSIVE_AC")
          for ad in (0.0, 1.0)]
+# no larger than one group: still several sections (one per pass), and the extra channels then live in the global stream
+GRID += [(w, h, "QPROGRESSIVE_AC", 1.5, 5, ad) for (w, h) in [(185, 226), (9, 22), (256, 256)] for ad in (0.0, 1.0)]
 
 
 def name(w, h, opt, dist, effort, ad):

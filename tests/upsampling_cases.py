@@ -8,6 +8,8 @@ from oracle import synth
 GRID = [(w, h, dist, res, effort, None) for (w, h) in [(600, 400), (257, 255), (1101, 703), (97, 33), (16, 9)]
         for (dist, res, effort) in [(12.0, -1, 7), (20.0, -1, 7), (2.0, 2, 7), (25.0, -1, 3)]]
 GRID += [(w, h, dist, -1, 7, ad) for (w, h) in [(600, 400), (1101, 703), (33, 97)] for (dist, ad) in [(12.0, 0.0), (12.0, 2.0), (20.0, 4.0)]]
+# ... together with progressive passes (resampling option 102 / 202: RESAMPLING = 2 + PROGRESSIVE_AC / QPROGRESSIVE_AC)
+GRID += [(w, h, 2.0, res, 5, ad) for (w, h) in [(425, 156), (700, 520)] for res in (102, 202) for ad in (None, 0.0, 2.0)]
 
 
 def name(w, h, dist, res, effort, ad):
@@ -17,7 +19,10 @@ def name(w, h, dist, res, effort, ad):
 def make(ref, w, h, dist, res, effort, ad):
     img = synth.synth_image(w, h, 5, alpha=ad is not None)
     opts = {"EFFORT": effort}
-    if res > 0:
+    if res > 100:
+        opts["RESAMPLING"] = 2
+        opts["PROGRESSIVE_AC" if res == 102 else "QPROGRESSIVE_AC"] = 1
+    elif res > 0:
         opts["RESAMPLING"] = res
     if ad is None:
         return cases._cached(name(w, h, dist, res, effort, ad), lambda: ref.encode_ex(img, w, h, 3, distance=dist, options=opts))
