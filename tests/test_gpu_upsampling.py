@@ -24,7 +24,13 @@ def test_upsampled_files_match_reference(J, ref):
     for g, d, o in zip(U.GRID, datas, outs):
         want = ref.decode_sampled(d, cfg=2)["pixels"]
         assert o.pixels.shape == want.shape, g
-        golden_lib.lossy_close(o.pixels, want, U.name(*g), min_exact=0.97)
+        if g[5] is None:
+            golden_lib.lossy_close(o.pixels, want, U.name(*g), min_exact=0.97)
+        else:
+            # an upsampled alpha is float work in the reference too (within one step), and the output is PREMULTIPLIED: one
+            # step in alpha times one step in colour reaches 2 on isolated samples (seen: 1 sample in 1.5 million)
+            d = np.abs(o.pixels.astype(np.int32) - want.astype(np.int32))
+            assert d.max() <= 2 and float((d > 1).mean()) < 1e-5 and float((d == 0).mean()) >= 0.97, (g, int(d.max()), float((d > 1).mean()))
 
 
 def test_upsampled_file_through_decode_sampled(J, ref):
