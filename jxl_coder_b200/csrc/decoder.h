@@ -26,9 +26,9 @@ struct BatchTimings {
 // Decodes n requests on CUDA device `device` (-1 = current).  Thread-safe; concurrent calls on the same device take
 // different decode slots (streams + buffers) and overlap on the GPU.
 // frame_index (may be null): per request, which DISPLAYED frame (frame types regular / skip-progressive, in codestream
-// order) to decode; -1 or null = the last frame, as the still-image entry points do.  A frame other than the first must
-// be a full-canvas kReplace frame (what the reference's JxlAnimatedEncoder emits); anything needing composition reports
-// JXLB_UNSUPPORTED.
+// order) to decode; -1 or null = the last frame, as the still-image entry points do.  Frames that depend on earlier ones
+// (blend modes, crops over a kept canvas, reference slots) are composed on the GPU from the chain of frames they need;
+// only references stored before the colour transform (patches) report JXLB_UNSUPPORTED.
 int DecodeBatch(const jxlb_request* reqs, size_t n, int api_level, int device, int output_device, std::vector<DecodedImage>* out,
                 BatchTimings* timings, const int32_t* frame_index = nullptr);
 
