@@ -541,7 +541,7 @@ int ParseFrameGlobals(const uint8_t* cs, size_t cs_padded, const ImageMetadata& 
   br.Init(cs, cs_padded, fh.sec_bit_begin[0], fh.sec_bit_end[0]);
   // LfChannelDequantization
   if (!br.Read(1))
-    for (int c = 0; c < 3; ++c) g->lf_dequant[c] = br.F16();
+    for (int c = 0; c < 3; ++c) g->lf_dequant[c] = br.F16() * (1.0f / 128.0f);  // coded unscaled: the defaults are (1/32, 1/4, 1/2) / 128
   ScratchLease arena_mem(8u << 20);
   Arena arena;
   arena.Init(arena_mem.data(), 8u << 20);
