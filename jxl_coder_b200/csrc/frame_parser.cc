@@ -4,6 +4,7 @@
 #include "modular_fast.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -42,11 +43,13 @@ class ScratchLease {
           b_ = std::move(fl[k]);
           fl[k] = std::move(fl.back());
           fl.pop_back();
+          Poison();
           return;
         }
     }
     b_.mem.reset(new uint8_t[bytes]);
     b_.cap = bytes;
+    Poison();
   }
   ~ScratchLease() {
     std::lock_guard<std::mutex> l(Mu());
@@ -54,6 +57,12 @@ class ScratchLease {
   }
   ScratchLease(const ScratchLease&) = delete;
   ScratchLease& operator=(const ScratchLease&) = delete;
+  // JXLB_POISON_SCRATCH=1 (debugging aid): every lease starts as 0xCD bytes, so that a read of scratch that was never written
+  // shows up as a reproducible difference instead of depending on what the previous image left behind
+  void Poison() {
+    static const bool on = getenv("JXLB_POISON_SCRATCH") != nullptr;
+    if (on) memset(b_.mem.get(), 0xCD, b_.cap);
+  }
   uint8_t* data() { return b_.mem.get(); }
   template <class T>
   T* as() { return reinterpret_cast<T*>(b_.mem.get()); }

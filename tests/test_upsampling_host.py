@@ -9,7 +9,7 @@ import upsampling_cases as U
 @pytest.mark.parametrize("w,h,dist,res,effort,ad", U.GRID)
 def test_upsampled_frames(w, h, dist, res, effort, ad, ref):
     data = U.make(ref, w, h, dist, res, effort, ad)
-    want = ref.decode_sampled(data, cfg=2)["pixels"][:, : w * 4].reshape(h, w, 4)
+    want = U.ref_decode_stable(ref, data, cfg=2)["pixels"][:, : w * 4].reshape(h, w, 4)
     e = H.Decoded(data)
     assert e.status == 0 and e.info["upsampling"] == 2
     out = e.render()

@@ -98,6 +98,12 @@ def run_case(ref, H, img, d):
     else:
         # one 8-bit step; isolated samples (a dark channel of a saturated colour, premultiplied lossy alpha) may reach 2
         ok = dd.max() <= 2 and float((dd > 1).mean()) < 1e-5 and float((dd == 0).mean()) > 0.97
+    if not ok:
+        # the reference itself is not always deterministic on upsampled frames (tests/upsampling_cases.py: ref_decode_stable)
+        for _ in range(4):
+            again = ref.decode_sampled(data, cfg=2)["pixels"][:, : w * 4].reshape(h, w, 4)
+            if not np.array_equal(again, want):
+                return "skip", "reference not deterministic"
     return ("ok", "") if ok else ("bad", "max %d, exact %.4f, beyond one step %.2e" % (dd.max(), (dd == 0).mean(), (dd > 1).mean()))
 
 
